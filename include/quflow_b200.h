@@ -1,0 +1,142 @@
+/*
+ * quflow_b200 — C ABI of the B200-native isomp hot path.
+ *
+ * This header is the drop-in boundary for the time-stepping hot path of
+ * klasmodin/quflow (Python).  Every entry point names the reference interface
+ * it replaces (paths relative to the upstream tree).  The reference is a pure
+ * Python package, so its "FFI" for this path is a ctypes binding; the stub a
+ * maintainer would add is shown in INTEGRATION.md and implemented in
+ * quflow_b200/_cuda/binding.py.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all matrices are N x N complex128,
+ *     row-major, interleaved (re, im) — numpy's C-contiguous complex128;
+ *   - pointers suffixed _dev are device pointers borrowed from the caller
+ *     (the Python side owns them through torch tensors); _host are host
+ *     pointers (pageable or pinned);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns 0 on success or a negative qf_status; nothing
+ *     throws across the boundary; qf_last_error() returns the message of the
+ *     last failure on the calling thread;
+ *   - a handle owns all scratch memory, the precomputed Laplacian factors and
+ *     the CUDA graphs; one handle per (N, batch, device); not re-entrant;
+ *   - there is no CPU fallback: without a CUDA device qf_create fails.
+ */
+#ifndef QUFLOW_B200_H
+#define QUFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qf_handle_s *qf_handle_t;
+
+typedef enum {
+    QF_OK = 0,
+    QF_ERR_INVALID = -1,    /* bad argument (maps to AssertionError / ValueError in Python) */
+    QF_ERR_CUDA = -2,       /* CUDA runtime / driver failure */
+    QF_ERR_NONFINITE = -3,  /* residual became NaN/Inf: scipy.linalg.norm's ValueError, isospectral.py:534 */
+    QF_ERR_NCCL = -4,       /* NCCL failure (multi-GPU path) */
+    QF_ERR_UNSUPPORTED = -5
+} qf_status;
+
+/* Statistics of one qf_isomp call.
+ * Replaces the `stats` dict of isomp_fixedpoint (quflow/integrators/isospectral.py:426-427,
+ * 451-452, 538-540, 607-611): tol_auto, iterations = total/steps, number_of_maxit = count/steps. */
+typedef struct {
+    double tol_used;            /* tolerance actually used (auto or given) */
+    double last_resnorm;        /* residual of the last executed iteration */
+    int64_t total_iterations;   /* fixed-point iterations over all steps */
+    int64_t number_of_maxit;    /* steps that ran maxit iterations without meeting the stopping rule */
+    int32_t nonfinite;          /* 1 if a NaN/Inf residual stopped the run */
+    int32_t steps_done;         /* steps completed (== steps unless nonfinite) */
+} qf_stats;
+
+/* Flags for qf_isomp */
+#define QF_FLAG_COMPSUM 1u       /* compensated (Kahan) update, isospectral.py:553-589 */
+#define QF_FLAG_REINITIALIZE 2u  /* zero the iterate dW at every step, isospectral.py:471-472 */
+
+/* Library / device info. Returns the number of CUDA devices (>=0) or a negative qf_status. */
+int qf_device_count(void);
+const char *qf_version(void);
+const char *qf_last_error(void);
+
+/* Create / destroy a solver context for N x N matrices and `batch` independent members
+ * (batch = 1 for a single simulation; >1 for ensembles where every member has its own
+ * convergence — BASELINE config 5).  Builds the Hoppe-Yau coefficient table and its LU
+ * factors (quflow/laplacian/cpu.py:55-95 `_compute_cpu_laplacian`, cached by `laplacian()`
+ * :604-625; the reference recomputes the LU on every solve, :320-328). */
+int qf_create(int N, int batch, int device, qf_handle_t *out);
+int qf_destroy(qf_handle_t h);
+
+/* P = Delta_N^{-1} W   — replaces quflow.laplacian.cpu.solve_poisson (cpu.py:681-734,
+ * kernel `_solve_cpu_skewh` :281-362), dense skew-Hermitian branch: only the upper triangle
+ * of W is read, tr(W)/N is removed from the m=0 right-hand side, P is trace-free and exactly
+ * skew-Hermitian.  W_dev and P_dev hold `batch` matrices; they may not alias. */
+int qf_solve_poisson(qf_handle_t h, const void *W_dev, void *P_dev, void *stream);
+
+/* W = Delta_N P        — replaces quflow.laplacian.cpu.laplace (cpu.py:628-669, kernel
+ * `_dot_cpu_generic` :98-108), dense branch, general (not necessarily skew-Hermitian) P. */
+int qf_laplace(qf_handle_t h, const void *P_dev, void *W_dev, void *stream);
+
+/* max row sum of |z| per member — np.linalg.norm(W, inf) (isospectral.py:446-448) /
+ * scipy.linalg.norm(., ord=inf) (:534).  out_host receives `batch` doubles. Synchronises. */
+int qf_norm_inf(qf_handle_t h, const void *W_dev, double *out_host, void *stream);
+
+/* C = A @ B for N x N complex128 (batch members) with the hand-written DMMA kernel —
+ * the np.matmul / zgemm calls at isospectral.py:496,499.  Exposed for tests and micro-benchmarks. */
+int qf_zgemm(qf_handle_t h, const void *A_dev, const void *B_dev, void *C_dev, void *stream);
+
+/* Advance W by `steps` isospectral-midpoint steps — replaces
+ * quflow.integrators.isospectral.isomp_fixedpoint (isospectral.py:338-613) for the default
+ * autonomous Hamiltonian solve_poisson, 2-D state (or `batch` independent states).
+ *   W_dev         in/out, overwritten like the reference's W
+ *   dt            time step;  epsilon = dt / (2 hbar(N))            (:436-437)
+ *   tol           < 0 => 'auto': sqrt(eps) * dt/hbar * ||W||_inf (eps un-rooted with compsum) (:440-452)
+ *   maxit, minit  iteration cap / floor (:400-401 asserted by the caller and re-checked here)
+ *   flags         QF_FLAG_*
+ *   stats         [batch] out, may be NULL
+ *   iters_per_step[batch*steps] out (member-major), may be NULL — per-step iteration counts
+ * The fixed-point loop, the stopping rule (:523-536) and the update (:547-596) run on the
+ * device without host synchronisation; the call synchronises the stream once at the end. */
+int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double tol, int maxit, int minit,
+             unsigned flags, qf_stats *stats, int32_t *iters_per_step, void *stream);
+
+/* Same as qf_isomp / qf_solve_poisson with HOST buffers: the library copies in, runs, copies out.
+ * This is what the ctypes shim calls for numpy inputs (the reference's calling convention). */
+int qf_isomp_host(qf_handle_t h, void *W_host, double dt, int steps, double tol, int maxit, int minit,
+                  unsigned flags, qf_stats *stats, int32_t *iters_per_step);
+int qf_solve_poisson_host(qf_handle_t h, const void *W_host, void *P_host);
+int qf_laplace_host(qf_handle_t h, const void *P_host, void *W_host);
+
+/* Introspection used by bench.py: number of kernels this library launched since creation
+ * of the handle, and per-phase device time of the last qf_profile_iteration call. */
+int64_t qf_launch_count(qf_handle_t h);
+
+typedef struct {
+    float poisson_ms;   /* W~ = W + dW, P~ = eps * Delta^{-1} W~ */
+    float gemm1_ms;     /* A = P~ W~ */
+    float gemm2_ms;     /* S = A P~ (+ fused epilogue when enabled) */
+    float post_ms;      /* dW = S + A - A^H, residual row sums, control */
+    float update_ms;    /* W += 2 (A - A^H) */
+} qf_phase_times;
+
+/* Runs `reps` fixed-point iterations on the current state of W_dev (which is left unchanged)
+ * with CUDA events around every phase, on `stream`; returns the per-phase averages. */
+int qf_profile_iteration(qf_handle_t h, const void *W_dev, double dt, int reps, qf_phase_times *out, void *stream);
+
+/* ---- multi-GPU (one process per GPU) -------------------------------------------------
+ * Row-block sharding of one large-N simulation: rank r owns rows [r*N/G, (r+1)*N/G) of the
+ * GEMM outputs; the state is replicated; one NCCL all-gather per GEMM.
+ * The 128-byte unique id is created on rank 0 and distributed by the host side
+ * (torch.distributed broadcast). */
+#define QF_UNIQUE_ID_BYTES 128
+int qf_comm_get_unique_id(void *id_out);
+int qf_comm_init(qf_handle_t h, const void *unique_id, int rank, int nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUFLOW_B200_H */

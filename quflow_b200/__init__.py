@@ -1,0 +1,14 @@
+"""quflow_b200 — the isomp hot path of klasmodin/quflow on NVIDIA B200 (sm_100a).
+
+Public names follow the reference package (``import quflow as qf``):
+``qf.isomp`` / ``qf.isomp_fixedpoint`` (quflow/integrators/isospectral.py), ``qf.solve_poisson`` /
+``qf.laplace`` (quflow/laplacian/cpu.py), ``qf.hbar`` (quflow/geometry.py), ``qf.solve`` /
+``qf.QuSimulation`` (quflow/simulation.py).  Everything computes in the CUDA library
+``quflow_b200/_cuda/libquflow_b200.so``; there is no CPU fallback.
+"""
+from .geometry import hbar  # noqa: F401
+from .laplacian import solve_poisson, laplace, select_first  # noqa: F401
+from .integrators import isomp, isomp_fixedpoint, isomp_ensemble  # noqa: F401
+from . import integrators, _cuda  # noqa: F401
+
+__version__ = "0.1.0"

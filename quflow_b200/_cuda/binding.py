@@ -1,0 +1,254 @@
+"""ctypes binding of include/quflow_b200.h.
+
+This is the stub a quflow maintainer would add as ``quflow/_cuda/__init__.py``:
+plain pointers and sizes across the boundary; torch tensors are used on the Python side only to own
+device buffers and to provide the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBNAME = "libquflow_b200.so"
+
+QF_OK = 0
+QF_ERR_INVALID = -1
+QF_ERR_CUDA = -2
+QF_ERR_NONFINITE = -3
+QF_ERR_NCCL = -4
+QF_ERR_UNSUPPORTED = -5
+QF_FLAG_COMPSUM = 1
+QF_FLAG_REINITIALIZE = 2
+QF_UNIQUE_ID_BYTES = 128
+
+
+class QfError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"quflow_b200 error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class qf_stats(ctypes.Structure):
+    _fields_ = [("tol_used", ctypes.c_double), ("last_resnorm", ctypes.c_double),
+                ("total_iterations", ctypes.c_int64), ("number_of_maxit", ctypes.c_int64),
+                ("nonfinite", ctypes.c_int32), ("steps_done", ctypes.c_int32)]
+
+
+class qf_phase_times(ctypes.Structure):
+    _fields_ = [("poisson_ms", ctypes.c_float), ("gemm1_ms", ctypes.c_float), ("gemm2_ms", ctypes.c_float),
+                ("post_ms", ctypes.c_float), ("update_ms", ctypes.c_float)]
+
+
+_lib = None
+_lock = threading.Lock()
+
+# every symbol include/quflow_b200.h declares: (restype, argtypes)
+_vp, _i, _d, _u = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_uint
+SYMBOLS = {
+    "qf_device_count": (_i, []),
+    "qf_version": (ctypes.c_char_p, []),
+    "qf_last_error": (ctypes.c_char_p, []),
+    "qf_create": (_i, [_i, _i, _i, ctypes.POINTER(_vp)]),
+    "qf_destroy": (_i, [_vp]),
+    "qf_solve_poisson": (_i, [_vp, _vp, _vp, _vp]),
+    "qf_laplace": (_i, [_vp, _vp, _vp, _vp]),
+    "qf_norm_inf": (_i, [_vp, _vp, ctypes.POINTER(_d), _vp]),
+    "qf_zgemm": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "qf_isomp": (_i, [_vp, _vp, _d, _i, _d, _i, _i, _u, ctypes.POINTER(qf_stats), ctypes.POINTER(ctypes.c_int32), _vp]),
+    "qf_isomp_host": (_i, [_vp, _vp, _d, _i, _d, _i, _i, _u, ctypes.POINTER(qf_stats), ctypes.POINTER(ctypes.c_int32)]),
+    "qf_solve_poisson_host": (_i, [_vp, _vp, _vp]),
+    "qf_laplace_host": (_i, [_vp, _vp, _vp]),
+    "qf_launch_count": (ctypes.c_int64, [_vp]),
+    "qf_profile_iteration": (_i, [_vp, _vp, _d, _i, ctypes.POINTER(qf_phase_times), _vp]),
+    "qf_comm_get_unique_id": (_i, [_vp]),
+    "qf_comm_init": (_i, [_vp, _vp, _i, _i]),
+}
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, _LIBNAME)
+
+
+def library():
+    """Load libquflow_b200.so (no CUDA call is made by loading).  Fails loudly if it was not built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            path = library_path()
+            if not os.path.exists(path):
+                raise ImportError(
+                    f"{path} not found: the CUDA extension is not built. Run `python -c \"import __graft_entry__ as g; "
+                    f"g.build()\"` (or `python quflow_b200/_cuda/build.py`). quflow_b200 has no CPU fallback.")
+            lib = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc != QF_OK:
+        raise QfError(rc, library().qf_last_error().decode())
+
+
+def device_count() -> int:
+    n = library().qf_device_count()
+    return max(n, 0)
+
+
+def _dev_ptr(t):
+    """Device pointer of a contiguous complex128 torch CUDA tensor."""
+    import torch
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.complex128 and t.is_contiguous()):
+        raise TypeError("expected a contiguous complex128 CUDA tensor")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Handle:
+    """Owns one qf_handle_t: scratch matrices, Laplacian factors, graphs for (N, batch, device)."""
+
+    def __init__(self, N: int, batch: int = 1, device: int = 0):
+        lib = library()
+        if lib.qf_device_count() <= 0:
+            raise QfError(QF_ERR_CUDA, "no CUDA device available (quflow_b200 has no CPU fallback)")
+        self.N, self.batch, self.device = int(N), int(batch), int(device)
+        h = ctypes.c_void_p()
+        _check(lib.qf_create(self.N, self.batch, self.device, ctypes.byref(h)))
+        self._h = h
+        self._lib = lib
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.qf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers -----------------------------------------------------------------------
+    def _shape_ok(self, a):
+        shp = tuple(a.shape)
+        want2, want3 = (self.N, self.N), (self.batch, self.N, self.N)
+        if not (shp == want3 or (self.batch == 1 and shp == want2)):
+            raise ValueError(f"array of shape {shp} does not match handle (batch={self.batch}, N={self.N})")
+
+    @staticmethod
+    def _host_ptr(a):
+        if not (isinstance(a, np.ndarray) and a.dtype == np.complex128 and a.flags.c_contiguous):
+            raise TypeError("expected a C-contiguous complex128 numpy array")
+        return a.ctypes.data_as(ctypes.c_void_p)
+
+    def launch_count(self) -> int:
+        return int(self._lib.qf_launch_count(self._h))
+
+    # -- operators ---------------------------------------------------------------------
+    def solve_poisson(self, W, out=None):
+        self._shape_ok(W)
+        if isinstance(W, np.ndarray):
+            out = np.empty_like(W) if out is None else out
+            _check(self._lib.qf_solve_poisson_host(self._h, self._host_ptr(W), self._host_ptr(out)))
+            return out
+        import torch
+        out = torch.empty_like(W) if out is None else out
+        _check(self._lib.qf_solve_poisson(self._h, _dev_ptr(W), _dev_ptr(out), _stream_ptr()))
+        return out
+
+    def laplace(self, P, out=None):
+        self._shape_ok(P)
+        if isinstance(P, np.ndarray):
+            out = np.empty_like(P) if out is None else out
+            _check(self._lib.qf_laplace_host(self._h, self._host_ptr(P), self._host_ptr(out)))
+            return out
+        import torch
+        out = torch.empty_like(P) if out is None else out
+        _check(self._lib.qf_laplace(self._h, _dev_ptr(P), _dev_ptr(out), _stream_ptr()))
+        return out
+
+    def norm_inf(self, W):
+        self._shape_ok(W)
+        out = (ctypes.c_double * self.batch)()
+        _check(self._lib.qf_norm_inf(self._h, _dev_ptr(W), out, _stream_ptr()))
+        return np.array(out[:])
+
+    def zgemm(self, A, B, out=None):
+        import torch
+        self._shape_ok(A)
+        self._shape_ok(B)
+        out = torch.empty_like(A) if out is None else out
+        _check(self._lib.qf_zgemm(self._h, _dev_ptr(A), _dev_ptr(B), _dev_ptr(out), _stream_ptr()))
+        return out
+
+    def isomp(self, W, dt, steps, tol=-1.0, maxit=10, minit=1, compsum=False, reinitialize=False, want_iters=False):
+        """Advance W in place.  Returns (list of per-member stats dicts, iters array or None).
+
+        Raises ValueError on a non-finite residual (the reference raises it from scipy.linalg.norm).
+        """
+        self._shape_ok(W)
+        flags = (QF_FLAG_COMPSUM if compsum else 0) | (QF_FLAG_REINITIALIZE if reinitialize else 0)
+        stats = (qf_stats * self.batch)()
+        iters = np.zeros((self.batch, max(steps, 1)), dtype=np.int32) if want_iters else None
+        iters_p = iters.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)) if want_iters else None
+        if isinstance(W, np.ndarray):
+            rc = self._lib.qf_isomp_host(self._h, self._host_ptr(W), float(dt), int(steps), float(tol), int(maxit),
+                                         int(minit), flags, stats, iters_p)
+        else:
+            rc = self._lib.qf_isomp(self._h, _dev_ptr(W), float(dt), int(steps), float(tol), int(maxit), int(minit),
+                                    flags, stats, iters_p, _stream_ptr())
+        if rc == QF_ERR_NONFINITE:
+            raise ValueError("array must not contain infs or NaNs")
+        if rc == QF_ERR_INVALID:
+            raise AssertionError(self._lib.qf_last_error().decode())
+        _check(rc)
+        out = [dict(tol_used=s.tol_used, last_resnorm=s.last_resnorm, total_iterations=int(s.total_iterations),
+                    number_of_maxit=int(s.number_of_maxit), steps_done=int(s.steps_done)) for s in stats]
+        if want_iters:
+            iters = iters[:, :steps]
+        return out, iters
+
+    def profile_iteration(self, W, dt, reps=5):
+        pt = qf_phase_times()
+        _check(self._lib.qf_profile_iteration(self._h, _dev_ptr(W), float(dt), int(reps), ctypes.byref(pt), _stream_ptr()))
+        return {k: getattr(pt, k) for k, _ in qf_phase_times._fields_}
+
+    # -- multi-GPU -----------------------------------------------------------------------
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        buf = ctypes.create_string_buffer(unique_id, QF_UNIQUE_ID_BYTES)
+        _check(self._lib.qf_comm_init(self._h, buf, int(rank), int(nranks)))
+
+
+def comm_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(QF_UNIQUE_ID_BYTES)
+    _check(library().qf_comm_get_unique_id(buf))
+    return buf.raw
+
+
+_handles: dict = {}
+
+
+def get_handle(N: int, batch: int = 1, device: int | None = None) -> Handle:
+    """Module-level cache, mirroring the reference's per-N caches (quflow/laplacian/cpu.py:11-17)."""
+    if device is None:
+        try:
+            import torch
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        except Exception:
+            device = 0
+    key = (int(N), int(batch), int(device))
+    if key not in _handles:
+        _handles[key] = Handle(*key)
+    return _handles[key]

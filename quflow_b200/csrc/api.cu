@@ -1,0 +1,196 @@
+// C-ABI entry points (see include/quflow_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "qf_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void qf_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *qf_last_error(void) { return g_err; }
+extern "C" const char *qf_version(void) { return "quflow_b200 0.1.0 (sm_100a)"; }
+
+extern "C" int qf_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        qf_set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        return QF_ERR_CUDA;
+    }
+    return n;
+}
+
+static int alloc_mat(qf_handle_s *h, double2 **p)
+{
+    QF_CUDA(cudaMalloc(p, sizeof(double2) * h->mat_elems * h->batch));
+    QF_CUDA(cudaMemset(*p, 0, sizeof(double2) * h->mat_elems * h->batch));
+    return QF_OK;
+}
+
+extern "C" int qf_create(int N, int batch, int device, qf_handle_t *out)
+{
+    if (!out) { qf_set_error("qf_create: out is null"); return QF_ERR_INVALID; }
+    *out = nullptr;
+    if (N < 2 || N > 16384) { qf_set_error("qf_create: N=%d out of range [2, 16384]", N); return QF_ERR_INVALID; }
+    if (batch < 1) { qf_set_error("qf_create: batch must be >= 1"); return QF_ERR_INVALID; }
+    int ndev = qf_device_count();
+    if (ndev <= 0) {
+        if (ndev == 0) qf_set_error("qf_create: no CUDA device (quflow_b200 has no CPU fallback)");
+        return QF_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { qf_set_error("qf_create: device %d out of range (%d devices)", device, ndev); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    QF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        qf_set_error("qf_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return QF_ERR_UNSUPPORTED;
+    }
+    qf_handle_s *h = new qf_handle_s();
+    h->N = N;
+    h->batch = batch;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->mat_elems = (size_t)N * N;
+    h->nslots = (N + 31) / 32;
+    int rc = qf_build_tables(h);
+    if (rc == QF_OK) rc = alloc_mat(h, &h->dW);
+    if (rc == QF_OK) rc = alloc_mat(h, &h->Wh);
+    if (rc == QF_OK) rc = alloc_mat(h, &h->P);
+    if (rc == QF_OK) rc = alloc_mat(h, &h->A);
+    if (rc == QF_OK) rc = alloc_mat(h, &h->S);
+    if (rc == QF_OK) rc = alloc_mat(h, &h->scratch);
+    if (rc == QF_OK) rc = qf_gemm_create(h);
+    if (rc != QF_OK) { qf_destroy(h); return rc; }
+    const size_t rp = sizeof(double) * (size_t)batch * 2 * h->nslots * N;
+    QF_CUDA(cudaMalloc(&h->rowpart, rp));
+    QF_CUDA(cudaMemset(h->rowpart, 0, rp));
+    QF_CUDA(cudaMalloc(&h->trbuf, sizeof(double2) * batch));
+    QF_CUDA(cudaMalloc(&h->ctrl, sizeof(QfCtrl) * batch));
+    QF_CUDA(cudaMemset(h->ctrl, 0, sizeof(QfCtrl) * batch));
+    QF_CUDA(cudaMallocHost(&h->ctrl_host, sizeof(QfCtrl) * batch));
+    *out = h;
+    return QF_OK;
+}
+
+extern "C" int qf_destroy(qf_handle_t h)
+{
+    if (!h) return QF_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    qf_gemm_destroy(h);
+    void *ptrs[] = {h->tab_w, h->tab_iu, h->tab_o, h->dW, h->Wh, h->P, h->A, h->S, h->scratch, h->kahan_c,
+                    h->io, h->io2, h->rowpart, h->trbuf, h->ctrl, h->iters_dev};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
+    delete h;
+    return QF_OK;
+}
+
+extern "C" int64_t qf_launch_count(qf_handle_t h) { return h ? h->launches : 0; }
+
+extern "C" int qf_solve_poisson(qf_handle_t h, const void *W_dev, void *P_dev, void *stream)
+{
+    if (!h || !W_dev || !P_dev) { qf_set_error("qf_solve_poisson: null argument"); return QF_ERR_INVALID; }
+    if (W_dev == P_dev) { qf_set_error("qf_solve_poisson: W and P may not alias"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    const double2 *W = (const double2 *)W_dev;
+    // Wh == W: the solve reads W directly (no W + dW pass), eps = 1, not gated
+    return qf_launch_poisson(h, W, nullptr, const_cast<double2 *>(W), (double2 *)P_dev, 1.0, false, (cudaStream_t)stream);
+}
+
+extern "C" int qf_laplace(qf_handle_t h, const void *P_dev, void *W_dev, void *stream)
+{
+    if (!h || !W_dev || !P_dev) { qf_set_error("qf_laplace: null argument"); return QF_ERR_INVALID; }
+    if (W_dev == P_dev) { qf_set_error("qf_laplace: P and W may not alias"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    return qf_launch_laplace(h, (const double2 *)P_dev, (double2 *)W_dev, (cudaStream_t)stream);
+}
+
+extern "C" int qf_norm_inf(qf_handle_t h, const void *W_dev, double *out_host, void *stream)
+{
+    if (!h || !W_dev || !out_host) { qf_set_error("qf_norm_inf: null argument"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    QF_CHECK(qf_launch_norm_inf(h, (const double2 *)W_dev, st));
+    QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl) * h->batch, cudaMemcpyDeviceToHost, st));
+    QF_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < h->batch; ++b) out_host[b] = h->ctrl_host[b].norm0;
+    return QF_OK;
+}
+
+extern "C" int qf_zgemm(qf_handle_t h, const void *A_dev, const void *B_dev, void *C_dev, void *stream)
+{
+    if (!h || !A_dev || !B_dev || !C_dev) { qf_set_error("qf_zgemm: null argument"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    return qf_launch_zgemm(h, (const double2 *)A_dev, (const double2 *)B_dev, (double2 *)C_dev, false, false, 0, h->N,
+                           (cudaStream_t)stream);
+}
+
+// ---- host-buffer variants ---------------------------------------------------------------
+static int ensure_io(qf_handle_s *h, bool two)
+{
+    const size_t bytes = sizeof(double2) * h->mat_elems * h->batch;
+    if (!h->io) QF_CUDA(cudaMalloc(&h->io, bytes));
+    if (two && !h->io2) QF_CUDA(cudaMalloc(&h->io2, bytes));
+    return QF_OK;
+}
+
+extern "C" int qf_isomp_host(qf_handle_t h, void *W_host, double dt, int steps, double tol, int maxit, int minit,
+                             unsigned flags, qf_stats *stats, int32_t *iters_per_step)
+{
+    if (!h || !W_host) { qf_set_error("qf_isomp_host: null argument"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    QF_CHECK(ensure_io(h, false));
+    const size_t bytes = sizeof(double2) * h->mat_elems * h->batch;
+    QF_CUDA(cudaMemcpyAsync(h->io, W_host, bytes, cudaMemcpyHostToDevice, 0));
+    int rc = qf_isomp(h, h->io, dt, steps, tol, maxit, minit, flags, stats, iters_per_step, 0);
+    if (rc != QF_OK && rc != QF_ERR_NONFINITE) return rc;
+    QF_CUDA(cudaMemcpy(W_host, h->io, bytes, cudaMemcpyDeviceToHost));
+    return rc;
+}
+
+extern "C" int qf_solve_poisson_host(qf_handle_t h, const void *W_host, void *P_host)
+{
+    if (!h || !W_host || !P_host) { qf_set_error("qf_solve_poisson_host: null argument"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    QF_CHECK(ensure_io(h, true));
+    const size_t bytes = sizeof(double2) * h->mat_elems * h->batch;
+    QF_CUDA(cudaMemcpyAsync(h->io, W_host, bytes, cudaMemcpyHostToDevice, 0));
+    QF_CHECK(qf_solve_poisson(h, h->io, h->io2, 0));
+    QF_CUDA(cudaMemcpy(P_host, h->io2, bytes, cudaMemcpyDeviceToHost));
+    return QF_OK;
+}
+
+extern "C" int qf_laplace_host(qf_handle_t h, const void *P_host, void *W_host)
+{
+    if (!h || !W_host || !P_host) { qf_set_error("qf_laplace_host: null argument"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    QF_CHECK(ensure_io(h, true));
+    const size_t bytes = sizeof(double2) * h->mat_elems * h->batch;
+    QF_CUDA(cudaMemcpyAsync(h->io, P_host, bytes, cudaMemcpyHostToDevice, 0));
+    QF_CHECK(qf_laplace(h, h->io, h->io2, 0));
+    QF_CUDA(cudaMemcpy(W_host, h->io2, bytes, cudaMemcpyDeviceToHost));
+    return QF_OK;
+}
+
+// ---- multi-GPU (filled in by comm.cu when built with NCCL) --------------------------------
+extern "C" __attribute__((weak)) int qf_comm_get_unique_id(void *)
+{
+    qf_set_error("built without NCCL");
+    return QF_ERR_UNSUPPORTED;
+}
+extern "C" __attribute__((weak)) int qf_comm_init(qf_handle_t, const void *, int, int)
+{
+    qf_set_error("built without NCCL");
+    return QF_ERR_UNSUPPORTED;
+}

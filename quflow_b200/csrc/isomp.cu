@@ -1,0 +1,426 @@
+// The isospectral-midpoint fixed-point loop on the device.
+//
+// Replaces quflow/integrators/isospectral.py:338-613 (`isomp_fixedpoint`) for the default autonomous
+// Hamiltonian.  One fixed-point iteration (isospectral.py:475-536) is
+//     W~ = W + dW;  P~ = eps * Delta^{-1} W~          (poisson.cu)
+//     A  = P~ W~                                       (zgemm.cu)
+//     S  = A P~          (skew-Hermitian: only the column blocks touching the upper triangle are computed)
+//     dW_new = S + (A - A^H);  res = || dW_old - dW_new ||_inf       (k_post + k_control, this file)
+// and the step ends with  W += 2 (A - A^H)  (k_update; isospectral.py:547-596).
+// The stopping rule lives in a device-resident control block (QfCtrl): all kernels of the iterations that
+// follow convergence return immediately, so a whole step is enqueued without any host synchronisation.
+#include <math.h>
+
+#include "qf_common.cuh"
+
+namespace {
+
+constexpr int TS = 32;   // tile edge of the transpose-based kernels
+
+// ------------------------------------------------------------------------------- ||W||_inf
+__global__ void k_rowsum_abs(const double2 *__restrict__ W, int N, QfCtrl *ctrl)
+{
+    // one warp per row; max over rows through an order-independent atomicMax on the bit pattern (values >= 0)
+    const int b = blockIdx.y;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= N) return;
+    const double2 *R = W + (size_t)b * N * N + (size_t)row * N;
+    double s = 0.0;
+    for (int j = threadIdx.x & 31; j < N; j += 32) s += zabs(R[j]);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) {
+        if (!(s == s)) s = INFINITY;   // NaN -> propagate as inf
+        atomicMax(reinterpret_cast<unsigned long long *>(&ctrl[b].norm0), (unsigned long long)__double_as_longlong(s));
+    }
+}
+
+__global__ void k_call_begin(QfCtrl *ctrl, double tol, double tol_factor)
+{
+    QfCtrl &c = ctrl[blockIdx.x];
+    c.tol = (tol < 0.0) ? tol_factor * c.norm0 : tol;
+    c.resnorm = INFINITY;
+    c.resnorm_old = INFINITY;
+    c.total_it = 0;
+    c.n_maxit = 0;
+    c.active = 0;
+    c.it = 0;
+    c.nonfinite = 0;
+    c.steps_done = 0;
+}
+
+__global__ void k_step_begin(QfCtrl *ctrl)
+{
+    QfCtrl &c = ctrl[blockIdx.x];
+    c.it = 0;
+    c.resnorm = INFINITY;          // isospectral.py:470
+    c.active = c.nonfinite ? 0 : 1;
+}
+
+// zero dW of the members that are still alive (reinitialize=True, isospectral.py:471-472)
+__global__ void k_zero(double2 *X, size_t n2, const QfCtrl *__restrict__ ctrl)
+{
+    const int b = blockIdx.y;
+    if (ctrl[b].nonfinite) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
+        X[(size_t)b * n2 + i] = make_double2(0.0, 0.0);
+}
+
+// ------------------------------------------------------------------------------- post-GEMM
+// For the tile pair (bi <= bj):  c = A_ij - conj(A_ji),  d = S_ij + c,  r = |dW_ij - d|,
+// dW_ij = d, dW_ji = -conj(d);  deterministic partial row sums of r for the infinity norm:
+//   direct[bj][i] = sum_{j in tile, j >= i} r_ij      mirr[bi][j] = sum_{i in tile, i < j} r_ij
+__global__ void __launch_bounds__(256)
+k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *__restrict__ dWg, double *__restrict__ rowpart,
+       int N, int nslots, const QfCtrl *__restrict__ ctrl)
+{
+    const int b = blockIdx.z;
+    if (!ctrl[b].active) return;
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bi > bj) return;
+    __shared__ double2 T[TS][TS + 1];
+    __shared__ double2 D[TS][TS + 1];
+    __shared__ double R[TS][TS + 1];
+    const size_t off = (size_t)b * N * N;
+    const double2 *A = Ag + off;
+    const double2 *S = Sg + off;
+    double2 *dW = dWg + off;
+    double *direct = rowpart + ((size_t)b * 2 + 0) * nslots * N;
+    double *mirr = rowpart + ((size_t)b * 2 + 1) * nslots * N;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+
+    // A_ji tile, coalesced along i
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int jj = ty + 8 * q;
+        const int j = bj * TS + jj, i = bi * TS + tx;
+        T[jj][tx] = (j < N && i < N) ? A[(size_t)j * N + i] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int ii = ty + 8 * q;
+        const int i = bi * TS + ii, j = bj * TS + tx;
+        double r = 0.0;
+        double2 d = make_double2(0.0, 0.0);
+        if (i < N && j < N && i <= j) {
+            const size_t ij = (size_t)i * N + j;
+            const double2 c = zsub(A[ij], zconj(T[tx][ii]));          // isospectral.py:66-81
+            double2 s = S[ij];
+            if (i == j) s.x = 0.0;                                    // P W P is skew-Hermitian
+            d = zadd(s, c);                                           // :499,:509
+            const double2 old = dW[ij];
+            r = zabs(zsub(old, d));                                   // :526,:534
+            dW[ij] = d;
+        }
+        D[ii][tx] = d;
+        R[ii][tx] = r;
+        // direct row sum over the 32 columns of this tile (fixed shuffle tree => deterministic)
+        double s = r;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (tx == 0 && i < N) direct[(size_t)bj * N + i] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int jj = ty + 8 * q;
+        const int j = bj * TS + jj, i = bi * TS + tx;
+        if (j < N && i < N && i < j) {
+            const double2 d = D[tx][jj];
+            dW[(size_t)j * N + i] = make_double2(-d.x, d.y);
+        }
+        double s = (i < j) ? R[tx][jj] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (tx == 0 && j < N) mirr[(size_t)bi * N + j] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------- control
+__global__ void __launch_bounds__(256)
+k_control(const double *__restrict__ rowpart, int N, int nslots, QfCtrl *ctrl, int maxit, int minit)
+{
+    const int b = blockIdx.x;
+    QfCtrl &c = ctrl[b];
+    if (!c.active) return;
+    const double *direct = rowpart + ((size_t)b * 2 + 0) * nslots * N;
+    const double *mirr = rowpart + ((size_t)b * 2 + 1) * nslots * N;
+    __shared__ double red[8];
+    __shared__ int bad[8];
+    double best = 0.0;
+    int nan_seen = 0;
+    for (int r = threadIdx.x; r < N; r += blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < nslots; ++k) s += direct[(size_t)k * N + r] + mirr[(size_t)k * N + r];
+        if (!(s == s) || isinf(s)) nan_seen = 1;
+        best = fmax(best, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+        nan_seen |= __shfl_xor_sync(0xffffffffu, nan_seen, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = best; bad[threadIdx.x >> 5] = nan_seen; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { best = fmax(best, red[w]); nan_seen |= bad[w]; }
+        if (nan_seen) best = INFINITY;
+        c.it += 1;                                   // isospectral.py:478
+        c.total_it += 1;
+        int active = 1;
+        if (c.it >= minit) {                         // :523
+            c.resnorm_old = c.resnorm;               // :525
+            c.resnorm = best;
+            if (nan_seen) {                          // scipy.linalg.norm -> ValueError (:534)
+                c.nonfinite = 1;
+                active = 0;
+            } else if (best <= c.tol || best >= c.resnorm_old) {   // :535
+                active = 0;
+            }
+        }
+        if (active && c.it >= maxit) {               // for/else, :538-540
+            active = 0;
+            c.n_maxit += 1;
+        }
+        c.active = active;
+    }
+}
+
+// ------------------------------------------------------------------------------- update
+// W += 2 (A - A^H)   (isospectral.py:547, :592) or its Kahan-compensated form (:553-586).
+template <bool COMPSUM>
+__global__ void __launch_bounds__(256)
+k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__restrict__ Kg, int N, QfCtrl *ctrl,
+         int32_t *iters, int steps_cap)
+{
+    const int b = blockIdx.z;
+    QfCtrl &c = ctrl[b];
+    if (c.nonfinite) return;
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bi == 0 && bj == 0 && threadIdx.x == 0) {
+        if (iters && c.steps_done < steps_cap) iters[(size_t)b * steps_cap + c.steps_done] = c.it;
+        c.steps_done += 1;
+    }
+    if (bi > bj) return;
+    __shared__ double2 T[TS][TS + 1];
+    __shared__ double2 D[TS][TS + 1];
+    const size_t off = (size_t)b * N * N;
+    const double2 *A = Ag + off;
+    double2 *W = Wg + off;
+    double2 *K = COMPSUM ? Kg + off : nullptr;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int jj = ty + 8 * q;
+        const int j = bj * TS + jj, i = bi * TS + tx;
+        T[jj][tx] = (j < N && i < N) ? A[(size_t)j * N + i] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    double2 wv[4], kv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int ii = ty + 8 * q;
+        const int i = bi * TS + ii, j = bj * TS + tx;
+        double2 w = make_double2(0.0, 0.0), kc = make_double2(0.0, 0.0);
+        if (i < N && j < N && i <= j) {
+            const size_t ij = (size_t)i * N + j;
+            double2 cm = zsub(A[ij], zconj(T[tx][ii]));
+            cm = make_double2(2.0 * cm.x, 2.0 * cm.y);
+            w = W[ij];
+            if (COMPSUM) {
+                kc = K[ij];
+                const double2 y = zsub(cm, kc);          // :570-571
+                const double2 tt = zadd(w, y);           // :575-576
+                kc = zsub(zsub(tt, w), y);               // :580-583
+                w = tt;                                  // :586
+                K[ij] = kc;
+            } else {
+                w = zadd(w, cm);
+            }
+            W[ij] = w;
+        }
+        wv[q] = w;
+        kv[q] = kc;
+    }
+    __syncthreads();   // everyone is done reading T
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int ii = ty + 8 * q;
+        T[ii][tx] = wv[q];
+        if (COMPSUM) D[ii][tx] = kv[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int jj = ty + 8 * q;
+        const int j = bj * TS + jj, i = bi * TS + tx;
+        if (j < N && i < N && i < j) {
+            const double2 w = T[tx][jj];
+            W[(size_t)j * N + i] = make_double2(-w.x, w.y);
+            if (COMPSUM) {
+                const double2 kc = D[tx][jj];
+                K[(size_t)j * N + i] = make_double2(-kc.x, kc.y);
+            }
+        }
+    }
+}
+
+}   // namespace
+
+// ------------------------------------------------------------------------------- launchers
+int qf_launch_norm_inf(qf_handle_s *h, const double2 *W, cudaStream_t st)
+{
+    const int N = h->N;
+    for (int b = 0; b < h->batch; ++b)
+        QF_CUDA(cudaMemsetAsync(&h->ctrl[b].norm0, 0, sizeof(double), st));
+    dim3 g((N + 7) / 8, h->batch);
+    k_rowsum_abs<<<g, 256, 0, st>>>(W, N, h->ctrl);
+    h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
+static inline double qf_hbar(int N) { return 2.0 / sqrt((double)N * (double)N - 1.0); }   // quflow/geometry.py:7-9
+
+int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit, int minit, cudaStream_t st,
+                         cudaEvent_t *ev /* 5 events or null */)
+{
+    const int N = h->N;
+    if (ev) QF_CUDA(cudaEventRecord(ev[0], st));
+    QF_CHECK(qf_launch_poisson(h, W, h->dW, h->Wh, h->P, eps, true, st));
+    if (ev) QF_CUDA(cudaEventRecord(ev[1], st));
+    QF_CHECK(qf_launch_zgemm(h, h->P, h->Wh, h->A, false, true, 0, N, st));
+    if (ev) QF_CUDA(cudaEventRecord(ev[2], st));
+    QF_CHECK(qf_launch_zgemm(h, h->A, h->P, h->S, true, true, 0, N, st));
+    if (ev) QF_CUDA(cudaEventRecord(ev[3], st));
+    const int nb = (N + TS - 1) / TS;
+    dim3 g(nb, nb, h->batch);
+    k_post<<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl);
+    k_control<<<h->batch, 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit);
+    h->launches += 2;
+    if (ev) QF_CUDA(cudaEventRecord(ev[4], st));
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
+int qf_enqueue_update(qf_handle_s *h, double2 *W, bool compsum, cudaStream_t st)
+{
+    const int N = h->N;
+    const int nb = (N + TS - 1) / TS;
+    dim3 g(nb, nb, h->batch);
+    if (compsum)
+        k_update<true><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, h->iters_dev, h->steps_cap);
+    else
+        k_update<false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, h->iters_dev, h->steps_cap);
+    h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
+extern "C" int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double tol, int maxit, int minit, unsigned flags,
+                        qf_stats *stats, int32_t *iters_per_step, void *stream)
+{
+    if (!h || !W_dev) { qf_set_error("qf_isomp: null handle or pointer"); return QF_ERR_INVALID; }
+    if (minit < 1) { qf_set_error("minit must be at least 1."); return QF_ERR_INVALID; }       // isospectral.py:400
+    if (maxit < minit) { qf_set_error("maxit must be at minit."); return QF_ERR_INVALID; }     // isospectral.py:401
+    if (steps < 0) { qf_set_error("steps must be non-negative"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->N, B = h->batch;
+    const size_t n2 = h->mat_elems;
+    double2 *W = (double2 *)W_dev;
+    const bool compsum = (flags & QF_FLAG_COMPSUM) != 0;
+    const bool reinit = (flags & QF_FLAG_REINITIALIZE) != 0;
+
+    if (steps > h->steps_cap) {
+        if (h->iters_dev) QF_CUDA(cudaFree(h->iters_dev));
+        h->steps_cap = std::max(steps, 1024);
+        QF_CUDA(cudaMalloc(&h->iters_dev, sizeof(int32_t) * (size_t)B * h->steps_cap));
+    }
+    if (compsum && !h->kahan_c) QF_CUDA(cudaMalloc(&h->kahan_c, sizeof(double2) * n2 * B));
+
+    const double hb = qf_hbar(N);
+    const double eps = dt / (2.0 * hb);                                     // isospectral.py:436-437
+    double mach_eps = 2.220446049250313e-16;                                // np.finfo(complex128).eps
+    if (!compsum) mach_eps = sqrt(mach_eps);                                // :441-443
+    const double tol_factor = mach_eps * dt / hb;                           // :448
+
+    QF_CUDA(cudaMemsetAsync(h->dW, 0, sizeof(double2) * n2 * B, st));       // :430
+    if (compsum) QF_CUDA(cudaMemsetAsync(h->kahan_c, 0, sizeof(double2) * n2 * B, st));   // :457
+    QF_CHECK(qf_launch_norm_inf(h, W, st));
+    k_call_begin<<<B, 1, 0, st>>>(h->ctrl, tol, tol_factor);
+    h->launches++;
+
+    const dim3 gz((unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)h->sm_count * 8), B);
+    for (int k = 0; k < steps; ++k) {
+        k_step_begin<<<B, 1, 0, st>>>(h->ctrl);
+        h->launches++;
+        if (reinit) {
+            k_zero<<<gz, 256, 0, st>>>(h->dW, n2, h->ctrl);
+            h->launches++;
+        }
+        for (int i = 0; i < maxit; ++i) QF_CHECK(qf_enqueue_iteration(h, W, eps, maxit, minit, st, nullptr));
+        QF_CHECK(qf_enqueue_update(h, W, compsum, st));
+    }
+    QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl) * B, cudaMemcpyDeviceToHost, st));
+    if (iters_per_step && steps > 0) {
+        QF_CUDA(cudaMemcpy2DAsync(iters_per_step, sizeof(int32_t) * steps, h->iters_dev, sizeof(int32_t) * h->steps_cap,
+                                  sizeof(int32_t) * steps, B, cudaMemcpyDeviceToHost, st));
+    }
+    QF_CUDA(cudaStreamSynchronize(st));
+    int rc = QF_OK;
+    for (int b = 0; b < B; ++b) {
+        const QfCtrl &c = h->ctrl_host[b];
+        if (stats) {
+            stats[b].tol_used = c.tol;
+            stats[b].last_resnorm = c.resnorm;
+            stats[b].total_iterations = c.total_it;
+            stats[b].number_of_maxit = c.n_maxit;
+            stats[b].nonfinite = c.nonfinite;
+            stats[b].steps_done = c.steps_done;
+        }
+        if (c.nonfinite) {
+            qf_set_error("array must not contain infs or NaNs (member %d, step %d)", b, c.steps_done);
+            rc = QF_ERR_NONFINITE;
+        }
+    }
+    return rc;
+}
+
+extern "C" int qf_profile_iteration(qf_handle_t h, const void *W_dev, double dt, int reps, qf_phase_times *out, void *stream)
+{
+    if (!h || !W_dev || !out || reps < 1) { qf_set_error("qf_profile_iteration: bad arguments"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->N, B = h->batch;
+    const size_t n2 = h->mat_elems;
+    const double eps = dt / (2.0 * qf_hbar(N));
+    cudaEvent_t ev[7];
+    for (auto &e : ev) QF_CUDA(cudaEventCreate(&e));
+    if (!h->io) QF_CUDA(cudaMalloc(&h->io, sizeof(double2) * n2 * B));
+    QF_CUDA(cudaMemcpyAsync(h->io, W_dev, sizeof(double2) * n2 * B, cudaMemcpyDeviceToDevice, st));
+    QF_CUDA(cudaMemsetAsync(h->dW, 0, sizeof(double2) * n2 * B, st));
+    QF_CHECK(qf_launch_norm_inf(h, h->io, st));
+    k_call_begin<<<B, 1, 0, st>>>(h->ctrl, 0.0, 0.0);   // tol = 0: never converges by tolerance
+    float acc[5] = {0, 0, 0, 0, 0};
+    for (int r = -1; r < reps; ++r) {   // r = -1: warm-up
+        k_step_begin<<<B, 1, 0, st>>>(h->ctrl);
+        QF_CHECK(qf_enqueue_iteration(h, h->io, eps, 1 << 30, 1 << 30, st, ev));
+        QF_CUDA(cudaEventRecord(ev[5], st));
+        QF_CHECK(qf_enqueue_update(h, h->io, false, st));
+        QF_CUDA(cudaEventRecord(ev[6], st));
+        QF_CUDA(cudaStreamSynchronize(st));
+        if (r < 0) continue;
+        float ms;
+        for (int p = 0; p < 4; ++p) {
+            QF_CUDA(cudaEventElapsedTime(&ms, ev[p], ev[p + 1]));
+            acc[p] += ms;
+        }
+        QF_CUDA(cudaEventElapsedTime(&ms, ev[5], ev[6]));
+        acc[4] += ms;
+    }
+    out->poisson_ms = acc[0] / reps;
+    out->gemm1_ms = acc[1] / reps;
+    out->gemm2_ms = acc[2] / reps;
+    out->post_ms = acc[3] / reps;
+    out->update_ms = acc[4] / reps;
+    for (auto &e : ev) cudaEventDestroy(e);
+    return QF_OK;
+}

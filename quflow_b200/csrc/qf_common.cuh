@@ -1,0 +1,108 @@
+// Shared declarations for the quflow_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/quflow_b200.h"
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+void qf_set_error(const char *fmt, ...);
+
+#define QF_CUDA(call)                                                                             \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            qf_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return QF_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+#define QF_CHECK(expr)                  \
+    do {                                \
+        int _s = (expr);                \
+        if (_s != QF_OK) return _s;     \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// device-resident control block of one ensemble member (one per batch entry)
+// ---------------------------------------------------------------------------------------
+struct QfCtrl {
+    double tol;           // tolerance in use
+    double resnorm;       // residual of the last evaluated iteration (inf at step start)
+    double resnorm_old;
+    double norm0;         // ||W||_inf at call start (tol = factor * norm0)
+    long long total_it;
+    long long n_maxit;
+    int active;           // 1 while the fixed-point loop of the current step runs
+    int it;               // iterations executed in the current step
+    int nonfinite;        // sticky: residual was NaN/Inf -> everything becomes a no-op
+    int steps_done;
+};
+
+// double2 helpers: (x, y) = (re, im)
+__device__ __forceinline__ double2 zadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 zsub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 zconj(double2 a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ double2 zscale(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
+__device__ __forceinline__ double zabs(double2 a) { return hypot(a.x, a.y); }
+
+// ---------------------------------------------------------------------------------------
+// the handle
+// ---------------------------------------------------------------------------------------
+struct QfGemmPlan;   // zgemm.cu
+
+struct qf_handle_s {
+    int N = 0;
+    int batch = 1;
+    int device = 0;
+    int sm_count = 148;
+    size_t mat_elems = 0;      // N*N
+    // Poisson factors, all (N, N) float64 in matrix layout [k][k+m] (upper triangle used)
+    double *tab_w = nullptr;   // w_k   = o_k / u_{k-1}          (0 at k = 0)
+    double *tab_iu = nullptr;  // 1/u_k,  u_k = d_k - w_k o_k
+    double *tab_o = nullptr;   // o_k   (coupling to position k-1; quflow lap[...,1])
+    double *tab_d = nullptr;   // d_k   (quflow lap[...,0], bc=False) — for laplace()
+    // work matrices, batch * N * N complex128 each
+    double2 *dW = nullptr, *Wh = nullptr, *P = nullptr, *A = nullptr, *S = nullptr, *scratch = nullptr;
+    double2 *kahan_c = nullptr;   // compensation term (compsum), lazily allocated
+    double2 *io = nullptr;        // staging for the *_host entry points, lazily allocated
+    double2 *io2 = nullptr;
+    // residual partial row sums: [batch][2][nslots][N]
+    double *rowpart = nullptr;
+    double2 *trbuf = nullptr;     // [batch] mean of diag(W~)
+    int nslots = 0;
+    QfCtrl *ctrl = nullptr;       // [batch] device
+    int32_t *iters_dev = nullptr; // [batch * steps_cap]
+    int steps_cap = 0;
+    QfCtrl *ctrl_host = nullptr;  // pinned
+    long long launches = 0;
+    // multi-GPU
+    void *nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+    QfGemmPlan *gemm = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------
+// kernels' host launchers (each returns a qf_status)
+// ---------------------------------------------------------------------------------------
+// poisson.cu
+int qf_build_tables(qf_handle_s *h);
+// Wh = W (+ dW);  P = eps * Delta^{-1} Wh.  If ctrl != null the launch is skipped on device when !ctrl->active.
+int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, double2 *Wh, double2 *P, double eps,
+                      bool gated, cudaStream_t st);
+int qf_launch_laplace(qf_handle_s *h, const double2 *P, double2 *W, cudaStream_t st);
+
+// zgemm.cu
+int qf_gemm_create(qf_handle_s *h);
+void qf_gemm_destroy(qf_handle_s *h);
+// C = A * B.  upper_only: compute only the 64-wide column blocks that intersect the upper triangle
+// (used for S = A P~ which is skew-Hermitian).  row_begin/row_end: row range (multi-GPU sharding).
+int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 *C, bool upper_only, bool gated,
+                    int row_begin, int row_end, cudaStream_t st);
+
+// isomp.cu
+int qf_launch_norm_inf(qf_handle_s *h, const double2 *W, cudaStream_t st);   // -> ctrl[b].norm0

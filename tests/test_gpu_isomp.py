@@ -1,0 +1,176 @@
+"""GPU parity tests for the isomp fixed-point loop (through the C ABI).
+
+Bar (BASELINE.json north_star): relative Frobenius error <= 1e-10 after 100 steps against the
+reference on identical input, same tolerance and iteration cap; here we additionally require
+identical per-step iteration counts and Casimir drift no worse than the reference's.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden, unband, relfro
+
+pytestmark = pytest.mark.gpu
+
+TOL_100_STEPS = 1e-10    # north_star tolerance
+
+
+@pytest.fixture(scope="module")
+def qf(cuda_device):
+    import quflow_b200
+    return quflow_b200
+
+
+def run_gpu(qf, W0, dt, steps, **kw):
+    from quflow_b200._cuda import get_handle
+    W = W0.copy()
+    res, iters = get_handle(W0.shape[-1]).isomp(W, dt, steps, want_iters=True, **kw)
+    return W, res[0], iters[0]
+
+
+@pytest.mark.parametrize("N", [32, 64, 128])
+def test_isomp_random_vs_reference_golden(qf, N):
+    g = golden(f"isomp_R_N{N}.npz")
+    W0 = oracle.random_skewherm(N, 42)
+    steps = int(g["steps"]) if N < 128 else 100
+    W, st, iters = run_gpu(qf, W0, float(g["dt"]), steps)
+    assert st["tol_used"] == pytest.approx(float(g["tol_auto"]), rel=1e-13)
+    assert list(iters) == list(g["iterations"][:steps])
+    ref = g["Wfinal"] if N < 128 else g["W_step100"]
+    assert relfro(W, ref) < TOL_100_STEPS
+    assert np.abs(W + W.conj().T).max() == 0.0           # stays exactly skew-Hermitian
+    if N < 128:
+        # Casimir drift no worse than the reference's own (x2 for rounding luck) + absolute floor
+        c0 = g["casimirs0"]
+        drift_ref = np.abs(g["casimirs"] - c0)
+        drift = np.abs(oracle.casimirs(W) - c0)
+        assert np.all(drift <= 2 * drift_ref + 1e-13 * np.abs(c0))
+
+
+def test_isomp_config1_N128_1000_steps(qf):
+    """BASELINE config 1: R(128, 42), 1000 steps (the reference's CPU-runnable case)."""
+    g = golden("isomp_R_N128.npz")
+    W, st, iters = run_gpu(qf, oracle.random_skewherm(128, 42), float(g["dt"]), 1000)
+    assert list(iters) == list(g["iterations"])
+    assert relfro(W, g["Wfinal"]) < 1e-9                 # 10x the 100-step bar for 10x the steps
+    assert st["total_iterations"] / 1000 == float(g["mean_iterations"])
+
+
+def test_reference_golden_vector_head_semantics(qf):
+    """The reference's N=16 golden W0 (trace != 0) at HEAD semantics: compare with the reference's HEAD output."""
+    g = golden("ref_isomp_golden_N16.npz")
+    dt = qf.hbar(16) * float(g["stepsize"])
+    W = qf.isomp(g["W0"].copy(), dt, int(g["steps"]))
+    assert relfro(W, g["W_head"]) < 1e-10
+
+
+@pytest.mark.parametrize("tag,kw", [("compsum", dict(compsum=True)), ("tol1e-10", dict(tol=1e-10)),
+                                    ("reinit", dict(reinitialize=True)), ("minit3", dict(minit=3, maxit=5))])
+def test_isomp_option_variants(qf, tag, kw):
+    g = golden(f"isomp_R_N32_{tag}.npz")
+    W, st, iters = run_gpu(qf, oracle.random_skewherm(32, 42), float(g["dt"]), int(g["steps"]), **kw)
+    if tag != "tol1e-10":
+        # with tol far below the attainable residual the loop ends on the stagnation rule
+        # (resnorm >= resnorm_old), i.e. on rounding noise: counts may legitimately differ there
+        assert list(iters) == list(g["iterations"])
+        assert st["number_of_maxit"] / int(g["steps"]) == float(g["number_of_maxit"])
+    assert relfro(W, g["Wfinal"]) < TOL_100_STEPS
+
+
+def test_isomp_profile_mode(qf):
+    g = golden("isomp_R_N64_profile.npz")
+    W, st, iters = run_gpu(qf, oracle.random_skewherm(64, 42), float(g["dt"]), 5, minit=10, maxit=10)
+    assert list(iters) == [10] * 5
+    assert st["number_of_maxit"] / 5 == float(g["number_of_maxit"])
+    assert relfro(W, g["Wfinal"]) < 1e-12
+
+
+def test_isomp_smooth_N64(qf):
+    g = golden("isomp_S_N64.npz")
+    W, st, iters = run_gpu(qf, unband(g["W0_band"], 64), float(g["dt"]), 100)
+    assert list(iters) == list(g["iterations"])
+    assert relfro(W, g["Wfinal"]) < TOL_100_STEPS
+
+
+def test_isomp_config2_smooth_N512(qf):
+    """BASELINE config 2 (first 100 steps): S(512) against the reference's stored block / band / sample."""
+    g = golden("isomp_S_N512.npz")
+    N = 512
+    W, st, iters = run_gpu(qf, unband(g["W0_band"], N), float(g["dt"]), 100)
+    assert list(iters) == list(g["iterations"])
+    scale = float(g["normF"]) / N                        # rms entry magnitude
+    idx = g["sample_idx"]
+    assert np.abs(W[idx[:, 0], idx[:, 1]] - g["Wfinal_sample"]).max() < 1e-10 * scale * N
+    assert np.linalg.norm(W[:48, :48] - g["Wfinal_block"]) < 1e-10 * np.linalg.norm(g["Wfinal_block"])
+    assert np.linalg.norm(W) == pytest.approx(float(g["normF"]), rel=1e-12)
+    # and against the oracle run here on the same input: full-matrix relative Frobenius error
+    Wref = oracle.isomp(unband(g["W0_band"], N), float(g["dt"]), 100)
+    assert relfro(W, Wref) < TOL_100_STEPS
+
+
+@pytest.mark.parametrize("N", [5, 16, 61, 100, 130, 257])
+def test_isomp_odd_sizes_vs_oracle(qf, N):
+    W0 = oracle.random_skewherm(N, N)
+    dt = 0.2 * qf.hbar(N)
+    rec = {}
+    Wref = oracle.isomp(W0.copy(), dt, 20, record=rec)
+    W, st, iters = run_gpu(qf, W0, dt, 20)
+    assert list(iters) == rec["iterations"]
+    assert relfro(W, Wref) < 1e-12
+
+
+def test_python_api_semantics(qf):
+    import torch
+    N = 48
+    W0 = oracle.random_skewherm(N, 9)
+    dt = 0.25 * qf.hbar(N)
+    # numpy: in place + returned (reference semantics)
+    W = W0.copy()
+    stats = {'iterations': 0.0}
+    ret = qf.isomp(W, dt, steps=7, stats=stats, time=0.0, hamiltonian=qf.solve_poisson)
+    assert ret is W and not np.array_equal(W, W0)
+    assert set(stats) == {'iterations', 'tol_auto', 'number_of_maxit'}
+    ref_stats = {'iterations': 0.0}
+    Wref = oracle.isomp(W0.copy(), dt, 7, stats=ref_stats)
+    assert stats['iterations'] == ref_stats['iterations']
+    assert stats['tol_auto'] == pytest.approx(ref_stats['tol_auto'], rel=1e-13)
+    assert relfro(W, Wref) < 1e-13
+    # torch CUDA tensor: advanced in place on the device, same numbers
+    Wd = torch.from_numpy(W0).cuda()
+    assert qf.isomp(Wd, dt, steps=7) is Wd
+    assert np.array_equal(Wd.cpu().numpy(), W)
+    # an empty stats dict is ignored (`if stats:` in the reference)
+    empty = {}
+    qf.isomp(W0.copy(), dt, steps=1, stats=empty)
+    assert empty == {}
+    # chunked calls reset the warm start like the reference (dW re-zeroed per call, isospectral.py:430)
+    Wa = W0.copy(); qf.isomp(Wa, dt, 4); qf.isomp(Wa, dt, 3)
+    Wb = oracle.isomp(oracle.isomp(W0.copy(), dt, 4), dt, 3)
+    assert relfro(Wa, Wb) < 1e-13
+    with pytest.raises(AssertionError):
+        qf.isomp(W0.copy(), dt, 1, minit=0)
+    with pytest.raises(AssertionError):
+        qf.isomp(W0.copy(), dt, 1, minit=4, maxit=3)
+    with pytest.raises(NotImplementedError):
+        qf.isomp(W0.copy(), dt, 1, hamiltonian=lambda X: X)
+    with pytest.raises(NotImplementedError):
+        qf.isomp(W0.copy(), dt, 1, forcing=lambda P, X: X)
+    bad = W0.copy(); bad[3, 4] = np.nan; bad[4, 3] = np.nan
+    with pytest.raises(ValueError):
+        qf.isomp(bad, dt, 2)
+
+
+def test_isomp_ensemble_matches_independent_runs(qf):
+    """BASELINE config 5 in miniature: members converge independently."""
+    N, k = 64, 5
+    W0 = np.stack([oracle.random_skewherm(N, s) * (1.0 + 0.5 * s) for s in range(k)])
+    dt = 0.25 * qf.hbar(N)
+    W = W0.copy()
+    stats = []
+    _, iters = qf.isomp_ensemble(W, dt, steps=12, stats=stats, return_iterations=True)
+    for s in range(k):
+        rec, st = {}, {'iterations': 0.0}
+        Wref = oracle.isomp(W0[s].copy(), dt, 12, stats=st, record=rec)
+        assert list(iters[s]) == rec["iterations"]
+        assert stats[s]["tol_auto"] == pytest.approx(st["tol_auto"], rel=1e-13)
+        assert relfro(W[s], Wref) < 1e-12

@@ -1,0 +1,115 @@
+"""GPU parity tests for the operators on the hot path: solve_poisson, laplace, norm, ZGEMM.
+
+Every call goes through the C ABI (ctypes -> libquflow_b200.so).  Tolerances are floating-point
+tolerances, stated per test; the oracle is the CPU restatement pinned in tests/test_oracle.py.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden, relfro
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def qf(cuda_device):
+    import quflow_b200
+    return quflow_b200
+
+
+def to_dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to("cuda:0")
+
+
+@pytest.mark.parametrize("name,N", [("poisson_exact_N33_zt1", 33), ("poisson_exact_N33_zt0", 33),
+                                    ("poisson_exact_N64_zt1", 64), ("poisson_exact_N64_zt0", 64),
+                                    ("poisson_exact_N101_zt1", 101)])
+def test_solve_poisson_golden(qf, name, N):
+    g = golden(name + ".npz")
+    P = qf.solve_poisson(g["Wexact"])            # host path
+    np.testing.assert_allclose(P, g["Pexact"], atol=1e-14 * N ** 2, rtol=0)   # upstream tests/test_laplacian.py:252
+    assert relfro(P, g["P_ref"]) < 1e-13          # vs the reference's own output
+    Pd = qf.solve_poisson(to_dev(g["Wexact"])).cpu().numpy()                   # device path
+    assert np.array_equal(Pd, P)
+    assert np.abs(P + P.conj().T).max() == 0.0
+    assert abs(np.trace(P)) < 1e-12
+
+
+@pytest.mark.parametrize("N", [2, 3, 5, 16, 31, 32, 33, 64, 127, 128, 129, 200, 257, 512])
+def test_solve_poisson_vs_oracle(qf, N):
+    W = oracle.random_skewherm(N, seed=N)
+    P = qf.solve_poisson(W)
+    Pref = oracle.solve_poisson(W)
+    assert relfro(P, Pref) < 1e-13
+    # only the upper triangle of W is read (reference semantics): garbage below the diagonal is ignored
+    W2 = W.copy()
+    W2[np.tril_indices(N, -1)] = 7.0 + 3.0j
+    assert np.array_equal(qf.solve_poisson(W2), P)
+
+
+def test_solve_poisson_nonzero_trace_and_roundtrip(qf):
+    N = 96
+    W = oracle.random_skewherm(N, 3) + 0.3j * np.eye(N)
+    P = qf.solve_poisson(W)
+    assert relfro(P, oracle.solve_poisson(W)) < 1e-13
+    back = qf.laplace(P)
+    assert relfro(back, W - np.eye(N) * np.trace(W) / N) < 1e-11
+
+
+def test_solve_poisson_multistate_and_time_kwarg(qf):
+    N = 40
+    W = np.stack([oracle.random_skewherm(N, 1), oracle.random_skewherm(N, 2)])
+    P = qf.solve_poisson(W)                        # reduce=select_first, cpu.py:696-697
+    assert P.shape == (N, N)
+    assert np.array_equal(P, qf.solve_poisson(W[0]))
+    with pytest.raises(TypeError):                 # isomp's autonomy probe relies on this (isospectral.py:416-423)
+        qf.solve_poisson(W[0], time=0.0)
+
+
+@pytest.mark.parametrize("N", [2, 33, 65, 128, 300])
+def test_laplace(qf, N):
+    rng = np.random.RandomState(N)
+    P = rng.randn(N, N) + 1j * rng.randn(N, N)     # general (not skew-Hermitian) input
+    assert relfro(qf.laplace(P), oracle.laplace(P)) < 1e-15
+    if N in (33,):
+        g = golden("poisson_exact_N33_zt1.npz")
+        np.testing.assert_allclose(qf.laplace(g["Pexact"]), g["Wexact"], rtol=1e-7, atol=1e-9)   # upstream :152
+
+
+@pytest.mark.parametrize("N", [7, 64, 129, 500])
+def test_norm_inf(qf, N):
+    from quflow_b200._cuda import get_handle
+    W = oracle.random_skewherm(N, 11)
+    got = get_handle(N).norm_inf(to_dev(W))[0]
+    assert got == pytest.approx(np.linalg.norm(W, np.inf), rel=1e-14)
+
+
+@pytest.mark.parametrize("N", [8, 33, 64, 100, 128, 129, 192, 256, 333, 512])
+def test_zgemm_vs_numpy(qf, N):
+    """Complex FP64 DMMA GEMM against numpy (BLAS zgemm): both are fp64 dot products of length N, so the
+    difference is bounded by accumulation-order rounding, ~ sqrt(N) * eps relative to |A||B|."""
+    from quflow_b200._cuda import get_handle
+    rng = np.random.RandomState(N)
+    A = rng.randn(N, N) + 1j * rng.randn(N, N)
+    B = rng.randn(N, N) + 1j * rng.randn(N, N)
+    C = get_handle(N).zgemm(to_dev(A), to_dev(B)).cpu().numpy()
+    ref = A @ B
+    bound = np.abs(A) @ np.abs(B)
+    assert (np.abs(C - ref) / bound).max() < 4e-16 * np.sqrt(N) + 1e-15
+    # exactness on small integers: any summation order gives the same result
+    Ai = rng.randint(-3, 4, (N, N)) + 1j * rng.randint(-3, 4, (N, N))
+    Bi = rng.randint(-3, 4, (N, N)) + 1j * rng.randint(-3, 4, (N, N))
+    Ci = get_handle(N).zgemm(to_dev(Ai.astype(complex)), to_dev(Bi.astype(complex))).cpu().numpy()
+    assert np.array_equal(Ci, Ai @ Bi)
+
+
+def test_zgemm_batched(qf):
+    from quflow_b200._cuda import get_handle
+    N, k = 96, 3
+    rng = np.random.RandomState(0)
+    A = rng.randn(k, N, N) + 1j * rng.randn(k, N, N)
+    B = rng.randn(k, N, N) + 1j * rng.randn(k, N, N)
+    C = get_handle(N, k).zgemm(to_dev(A), to_dev(B)).cpu().numpy()
+    assert relfro(C, A @ B) < 1e-14
