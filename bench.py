@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — isomp steps/s on B200 (BASELINE.json metric), roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n 2048] [--mode natural|profile]
+
+Workload (config.workload): R(N, 42) — random skew-Hermitian trace-free complex128 vorticity normalised to
+norm_L2 = 1, N = 2048 by default (the size BASELINE.json's metric is quoted on; it fits one GPU),
+natural mode: dt = 0.25*hbar(N), tol='auto', maxit=10, minit=1 (about 3 fixed-point iterations per step).
+A "step" is one isospectral-midpoint time step.
+
+* ``value``  : steps/s with W resident in HBM, timed with CUDA events over exactly K steps (max over ranks).
+* ``e2e``    : the same metric through the public Python API with HOST buffers (numpy in pinned memory): every step
+               is one ``qf.isomp(W_host, dt, steps=1)`` call = H2D copy of W + one step + D2H copy of W.
+* ``roofline``: the dominant kernel (k_zgemm, FP64 DMMA) — executed flops per launch / CUDA-event launch time,
+               against the FP64 tensor peak measured on this pool (MEASURED_PEAKS.json has no FP64 entry; see
+               profiles/r01_fp64_pipes.txt).  ``roofline_poisson`` reports the HBM-bound Poisson solve against
+               MEASURED_PEAKS.json's copy bandwidth.
+* ``cpu_baseline`` / ``--impl reference``: the CPU oracle port of the reference path (numpy BLAS zgemm + OpenMP
+               Thomas, all host cores) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FP64_TENSOR_PEAK_TFLOPS = 37.15   # measured DMMA m8n8k4 issue peak, 148 SMs @ 1965 MHz (profiles/r01_fp64_pipes.txt)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def hbar(N):
+    return 2.0 / np.sqrt(float(N) ** 2 - 1.0)
+
+
+def workload(N, seed=42):
+    rng = np.random.RandomState(seed)
+    A = rng.randn(N, N) + 1j * rng.randn(N, N)
+    W = A - A.conj().T
+    W -= np.eye(N) * np.trace(W) / N
+    W /= np.linalg.norm(W) / np.sqrt(N)
+    return np.ascontiguousarray(W)
+
+
+def mode_kwargs(mode, N):
+    if mode == "profile":   # the reference's own protocol, profiling/run_profiling.py:124-127
+        return dict(dt=0.01 * hbar(N), maxit=10, minit=10)
+    return dict(dt=0.25 * hbar(N), maxit=10, minit=1)
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # median of the upper half = clocks under load (idle samples at the edges drag the plain median down)
+        s = sorted(sm)
+        return {"sm_mhz": float(np.median(s[len(s) // 2:])), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, all host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_threads():
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    return n
+
+
+def run_cpu_port(N, mode, steps, warmup):
+    """Time the CPU oracle (port of isospectral.py:338-613 + cpu.py:281-362) on `steps` steps."""
+    import oracle
+    kw = mode_kwargs(mode, N)
+    W = workload(N)
+    stats = {'iterations': 0.0}
+    if warmup > 0:
+        oracle.isomp(W, kw["dt"], steps=warmup, maxit=kw["maxit"], minit=kw["minit"])
+    t0 = time.perf_counter()
+    oracle.isomp(W, kw["dt"], steps=steps, maxit=kw["maxit"], minit=kw["minit"], stats=stats)
+    dt = time.perf_counter() - t0
+    return steps / dt, dt, stats['iterations']
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N = args.n
+    cores = cpu_threads()
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # bounded: at N=2048 one CPU step costs seconds; keep the whole run within a few minutes
+    warm = min(args.warmup, 1)
+    val, secs, its = run_cpu_port(N, args.mode, args.steps, warm)
+    sample = f"{args.steps} steps (+{warm} warm-up) of R({N},42), {args.mode} mode, {its:.2f} it/step, {secs:.1f} s"
+    kw = mode_kwargs(args.mode, N)
+    line = {
+        "impl": "reference", "metric": "isomp steps/sec", "value": val, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+        "config": workload_config(N, args.mode, kw, its),
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(N, mode, kw, its=None):
+    cfg = {"workload": f"isomp on R({N},42): random skew-Hermitian trace-free complex128, norm_L2=1; "
+                       f"{mode} mode dt={kw['dt'] / hbar(N):.2f}*hbar tol=auto maxit={kw['maxit']} minit={kw['minit']}",
+           "N": N, "mode": mode,
+           "l2": "working set (7 N^2 complex matrices + factor tables, > 500 MB at N=2048) exceeds the 126 MB L2; no flush needed"
+           if N >= 2048 else "working set partly L2-resident as in production use; see DESIGN.md"}
+    if its is not None:
+        cfg["iterations_per_step"] = its
+    return cfg
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import quflow_b200 as qf
+    from quflow_b200._cuda import get_handle
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (quflow_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    N, mode = args.n, args.mode
+    kw = mode_kwargs(mode, N)
+    W0 = workload(N)
+    handle = get_handle(N, 1, local_rank)
+    if world > 1:
+        from quflow_b200.distributed import attach_row_sharding
+        attach_row_sharding(handle, dist)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident -------------------------------------------------------------------
+    W = torch.from_numpy(W0).to(dev)
+    if args.warmup > 0:
+        handle.isomp(W, kw["dt"], args.warmup, maxit=kw["maxit"], minit=kw["minit"])
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = handle.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res, _ = handle.isomp(W, kw["dt"], args.steps, maxit=kw["maxit"], minit=kw["minit"])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = handle.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    its = res[0]["total_iterations"] / max(args.steps, 1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = args.steps / (ms * 1e-3)
+
+    # ---- e2e: public API, host buffers, one call per step ------------------------------------------
+    Wpin = torch.from_numpy(W0.copy()).pin_memory()
+    Wh = Wpin.numpy()
+    for _ in range(min(args.warmup, 2)):
+        qf.isomp(Wh, kw["dt"], steps=1, maxit=kw["maxit"], minit=kw["minit"])
+    barrier()
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        qf.isomp(Wh, kw["dt"], steps=1, maxit=kw["maxit"], minit=kw["minit"])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = e2e_steps / float(t.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (rank 0, single-GPU kernels) -------------------------------
+    hsolo = handle if world == 1 else get_handle(N, 1, local_rank)
+    ph = hsolo.profile_iteration(torch.from_numpy(W0).to(dev), kw["dt"], reps=5)
+    gemm1_tf = 8.0 * N ** 3 / (ph["gemm1_ms"] * 1e-3) / 1e12
+    # S = A P~ only computes the 64-wide column blocks that touch the upper triangle
+    nbm, nbn = (N + 127) // 128, (N + 63) // 64
+    tiles2 = sum(1 for i in range(nbm) for j in range(nbn) if j * 64 + 63 >= i * 128)
+    flops2 = 8.0 * N ** 3 * tiles2 / (nbm * nbn)
+    gemm2_tf = flops2 / (ph["gemm2_ms"] * 1e-3) / 1e12
+    peaks = measured_peaks()
+    hbm = peaks["hbm_gbs"] if peaks else 6650.0
+    pois_gbs = 32.0 * N * N / (ph["poisson_ms"] * 1e-3) / 1e9
+    iter_ms = ph["poisson_ms"] + ph["gemm1_ms"] + ph["gemm2_ms"] + ph["post_ms"]
+    roofline = {
+        "bound": "tensor", "kernel": "k_zgemm (A = P~ W~, 8 N^3 executed FP64 flop per launch)",
+        "achieved": gemm1_tf, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gemm1_tf / FP64_TENSOR_PEAK_TFLOPS,
+        "traffic": None,
+        "peak_source": "measured FP64 DMMA issue peak on this pool's B200 (profiles/r01_fp64_pipes.txt); "
+                       "MEASURED_PEAKS.json has no FP64 entry, datasheet ~37-40 TF/s",
+        "launch_ms": ph["gemm1_ms"],
+        "second_gemm": {"achieved": gemm2_tf, "frac": gemm2_tf / FP64_TENSOR_PEAK_TFLOPS, "launch_ms": ph["gemm2_ms"],
+                        "executed_flop": flops2, "note": "S = A P~ is skew-Hermitian: lower-triangle tiles skipped"},
+        "share_of_iteration": (ph["gemm1_ms"] + ph["gemm2_ms"]) / iter_ms,
+    }
+    roofline_poisson = {
+        "bound": "hbm", "kernel": "W~=W+dW, P~=eps*Laplace^-1 W~ (32 N^2 algorithmic bytes)", "achieved": pois_gbs,
+        "peak": hbm, "unit": "GB/s", "frac": pois_gbs / hbm, "traffic": None, "launch_ms": ph["poisson_ms"],
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "B200_PROFILING.md fallback 6.65 TB/s (of fallback)",
+    }
+
+    # ---- CPU baseline: bounded sample of the same workload on the host cores --------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = cpu_threads()
+        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        n_cpu = 3 if N >= 2048 else (6 if N >= 1024 else 20)
+        cval, secs, cits = run_cpu_port(N, mode, n_cpu, 1)
+        cpu = {"value": cval, "unit": "steps/s", "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} steps (+1 warm-up) of the same R({N},42) workload, {cits:.2f} it/step, {secs:.1f} s; "
+                         f"numpy BLAS zgemm + OpenMP Thomas (oracle/)"}
+
+    line = {
+        "metric": "isomp steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+        "config": workload_config(N, mode, kw, its),
+        "iterations_per_sec": value * its,
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": 16 * N * N, "d2h_bytes_per_step": 16 * N * N,
+                "note": "one qf.isomp(W_numpy_pinned, dt, steps=1) call per step; chunked calls reset the warm start "
+                        "like the reference (isospectral.py:430)"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "roofline_poisson": roofline_poisson,
+        "phase_ms": ph,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=2048)
+    ap.add_argument("--mode", default="natural", choices=["natural", "profile"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()
