@@ -46,6 +46,8 @@ __global__ void k_call_begin(QfCtrl *ctrl, double tol, double tol_factor)
     c.it = 0;
     c.nonfinite = 0;
     c.steps_done = 0;
+    c.resmax_bits = 0ull;
+    c.ticket = 0u;
 }
 
 __global__ void k_step_begin(QfCtrl *ctrl)
@@ -68,7 +70,7 @@ __global__ void k_zero(double2 *X, size_t n2, const QfCtrl *__restrict__ ctrl)
 // ------------------------------------------------------------------------------- post-GEMM
 // For the tile pair (bi <= bj):  c = A_ij - conj(A_ji),  d = S_ij + c,  r = |dW_ij - d|,
 // dW_ij = d, dW_ji = -conj(d);  deterministic partial row sums of r for the infinity norm:
-//   direct[bj][i] = sum_{j in tile, j >= i} r_ij      mirr[bi][j] = sum_{i in tile, i < j} r_ij
+//   direct[i][bj] = sum_{j in tile, j >= i} r_ij      mirr[j][bi] = sum_{i in tile, i < j} r_ij
 __global__ void __launch_bounds__(256)
 k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *__restrict__ dWg, double *__restrict__ rowpart,
        int N, int nslots, const QfCtrl *__restrict__ ctrl)
@@ -117,7 +119,7 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
         // direct row sum over the 32 columns of this tile (fixed shuffle tree => deterministic)
         double s = r;
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (tx == 0 && i < N) direct[(size_t)bj * N + i] = s;
+        if (tx == 0 && i < N) direct[(size_t)i * nslots + bj] = s;
     }
     __syncthreads();
 #pragma unroll
@@ -130,57 +132,61 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
         }
         double s = (i < j) ? R[tx][jj] : 0.0;
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (tx == 0 && j < N) mirr[(size_t)bi * N + j] = s;
+        if (tx == 0 && j < N) mirr[(size_t)j * nslots + bi] = s;
     }
 }
 
 // ------------------------------------------------------------------------------- control
+// Row sums of the residual (one warp per row, slots contiguous), max over rows through an order-independent
+// atomicMax, and the stopping rule evaluated by the last block to finish (ticket counter).
 __global__ void __launch_bounds__(256)
 k_control(const double *__restrict__ rowpart, int N, int nslots, QfCtrl *ctrl, int maxit, int minit)
 {
-    const int b = blockIdx.x;
+    const int b = blockIdx.y;
     QfCtrl &c = ctrl[b];
     if (!c.active) return;
     const double *direct = rowpart + ((size_t)b * 2 + 0) * nslots * N;
     const double *mirr = rowpart + ((size_t)b * 2 + 1) * nslots * N;
-    __shared__ double red[8];
-    __shared__ int bad[8];
-    double best = 0.0;
-    int nan_seen = 0;
-    for (int r = threadIdx.x; r < N; r += blockDim.x) {
-        double s = 0.0;
-        for (int k = 0; k < nslots; ++k) s += direct[(size_t)k * N + r] + mirr[(size_t)k * N + r];
-        if (!(s == s) || isinf(s)) nan_seen = 1;
-        best = fmax(best, s);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * 8 + warp;
+    double s = 0.0;
+    if (row < N) {
+        for (int k = lane; k < nslots; k += 32) s += direct[(size_t)row * nslots + k] + mirr[(size_t)row * nslots + k];
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
-        nan_seen |= __shfl_xor_sync(0xffffffffu, nan_seen, o);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ int last;
+    if (lane == 0 && row < N) {
+        if (!(s == s)) s = INFINITY;
+        atomicMax(&c.resmax_bits, (unsigned long long)__double_as_longlong(s));
     }
-    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = best; bad[threadIdx.x >> 5] = nan_seen; }
+    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) { best = fmax(best, red[w]); nan_seen |= bad[w]; }
-        if (nan_seen) best = INFINITY;
-        c.it += 1;                                   // isospectral.py:478
-        c.total_it += 1;
-        int active = 1;
-        if (c.it >= minit) {                         // :523
-            c.resnorm_old = c.resnorm;               // :525
-            c.resnorm = best;
-            if (nan_seen) {                          // scipy.linalg.norm -> ValueError (:534)
-                c.nonfinite = 1;
-                active = 0;
-            } else if (best <= c.tol || best >= c.resnorm_old) {   // :535
-                active = 0;
-            }
-        }
-        if (active && c.it >= maxit) {               // for/else, :538-540
+    if (threadIdx.x == 0) last = (atomicAdd(&c.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!last || threadIdx.x != 0) return;
+    __threadfence();
+    const double best = __longlong_as_double((long long)atomicExch(&c.resmax_bits, 0ull));
+    c.ticket = 0;
+    const int nan_seen = isinf(best) ? 1 : 0;
+    c.it += 1;                                   // isospectral.py:478
+    c.total_it += 1;
+    int active = 1;
+    if (c.it >= minit) {                         // :523
+        c.resnorm_old = c.resnorm;               // :525
+        c.resnorm = best;
+        if (nan_seen) {                          // scipy.linalg.norm -> ValueError (:534)
+            c.nonfinite = 1;
             active = 0;
-            c.n_maxit += 1;
+        } else if (best <= c.tol || best >= c.resnorm_old) {   // :535
+            active = 0;
         }
-        c.active = active;
     }
+    if (active && c.it >= maxit) {               // for/else, :538-540
+        active = 0;
+        c.n_maxit += 1;
+    }
+    __threadfence();
+    c.active = active;
 }
 
 // ------------------------------------------------------------------------------- update
@@ -293,7 +299,7 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
     const int nb = (N + TS - 1) / TS;
     dim3 g(nb, nb, h->batch);
     k_post<<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl);
-    k_control<<<h->batch, 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit);
+    k_control<<<dim3((N + 7) / 8, h->batch), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit);
     h->launches += 2;
     if (ev) QF_CUDA(cudaEventRecord(ev[4], st));
     QF_CUDA(cudaGetLastError());

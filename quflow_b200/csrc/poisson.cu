@@ -176,6 +176,219 @@ __global__ void k_fix_trace(double2 *P, int N, double eps, const QfCtrl *__restr
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// v2: chunked parallel solve.  One CTA owns GS = 4 adjacent diagonals m0..m0+3; thread (s, c) owns
+// positions [cL, (c+1)L) of system m0+s in registers.  With the LDL^T factors (w_k, 1/u_k) both sweeps
+// are first-order linear recurrences,
+//     forward   c_k = r_k - w_k c_{k-1}                 backward  x_k = c_k/u_k - w_{k+1} x_{k+1},
+// so each chunk is an affine map of its carry-in.  Pass 1 evaluates the chunk with carry-in 0 and the
+// map's slope (a running product), a warp-shuffle + shared-memory scan composes the maps across the
+// chunks of a system, pass 2 re-runs the chunk from its true carry-in.  Lanes s = 0..3 of a quad touch
+// 64 contiguous bytes of a matrix row, every thread has L independent 16-byte loads in flight, and the
+// per-CTA sequential depth is 4L FMAs + two log-depth scans instead of 2N.
+// HBM traffic: upper triangle of W~ (8 N^2 B) + w and 1/u tables (8 N^2 B) + full P (16 N^2 B) = 32 N^2 B.
+// ---------------------------------------------------------------------------------------
+constexpr int GS = 4;
+
+template <int L>
+__global__ void __launch_bounds__(512, 1)
+k_poisson_scan(const double2 *__restrict__ Wh, double2 *__restrict__ P, const double *__restrict__ tw,
+               const double *__restrict__ tiu, int N, double eps, const QfCtrl *__restrict__ ctrl, int gated)
+{
+    const int b = blockIdx.y;
+    if (gated && !ctrl[b].active) return;
+    __shared__ double totA[16][GS], totBx[16][GS], totBy[16][GS];
+    __shared__ double redx[16], redy[16];
+    __shared__ double2 bcast;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int s = tid & (GS - 1), c = tid >> 2;
+    const int m0 = blockIdx.x * GS;
+    const int m = m0 + s;
+    const int n = N - m;                 // length of this thread's system (<= 0: none)
+    const int k0 = c * L;
+    const size_t off = (size_t)b * N * N;
+    const double2 *R = Wh + off;
+    double2 *X = P + off;
+
+    double2 r[L];
+    double w[L + 1];                     // w[L] = w of the first position of the next chunk
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+        const int k = k0 + i;
+        const bool ok = k < n;
+        const size_t idx = (size_t)k * N + (k + m);
+        r[i] = ok ? R[idx] : make_double2(0.0, 0.0);
+        w[i] = ok ? __ldg(tw + idx) : 0.0;
+    }
+    {
+        const int k = k0 + L;
+        w[L] = (k < n) ? __ldg(tw + (size_t)k * N + (k + m)) : 0.0;
+    }
+
+    // ---- m = 0: remove the mean of the diagonal from the right-hand side (cpu.py:311-317,327-328)
+    if (m0 == 0) {
+        double sx = 0.0, sy = 0.0;
+        if (s == 0) {
+#pragma unroll
+            for (int i = 0; i < L; ++i) { sx += r[i].x; sy += r[i].y; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, o);
+            sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        }
+        if (lane == 0) { redx[warp] = sx; redy[warp] = sy; }
+        __syncthreads();
+        if (tid == 0) {
+            double ax = 0.0, ay = 0.0;
+            for (int q = 0; q < nwarps; ++q) { ax += redx[q]; ay += redy[q]; }
+            bcast = make_double2(ax / N, ay / N);
+        }
+        __syncthreads();
+        if (s == 0) {
+            const double2 tr = bcast;
+#pragma unroll
+            for (int i = 0; i < L; ++i)
+                if (k0 + i < n) { r[i].x -= tr.x; r[i].y -= tr.y; }
+        }
+        __syncthreads();
+    }
+
+    // ---- forward, pass 1: chunk map  c_out = A c_in + B
+    double A = 1.0;
+    double2 B = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+        B.x = r[i].x - w[i] * B.x;
+        B.y = r[i].y - w[i] * B.y;
+        A = -w[i] * A;
+    }
+    // inclusive scan over the 8 chunks of this warp (lanes with equal s are 4 apart)
+#pragma unroll
+    for (int d = GS; d < 32; d <<= 1) {
+        const double eA = __shfl_up_sync(0xffffffffu, A, d);
+        const double eBx = __shfl_up_sync(0xffffffffu, B.x, d);
+        const double eBy = __shfl_up_sync(0xffffffffu, B.y, d);
+        if (lane >= d) {
+            B.x = A * eBx + B.x;
+            B.y = A * eBy + B.y;
+            A = A * eA;
+        }
+    }
+    double xA = __shfl_up_sync(0xffffffffu, A, GS);
+    double xBx = __shfl_up_sync(0xffffffffu, B.x, GS);
+    double xBy = __shfl_up_sync(0xffffffffu, B.y, GS);
+    if (lane < GS) { xA = 1.0; xBx = 0.0; xBy = 0.0; }
+    if (lane >= 32 - GS) { totA[warp][s] = A; totBx[warp][s] = B.x; totBy[warp][s] = B.y; }
+    __syncthreads();
+    double2 carry;
+    {
+        double pBx = 0.0, pBy = 0.0;
+        for (int q = 0; q < warp; ++q) {
+            const double tA = totA[q][s];
+            pBx = tA * pBx + totBx[q][s];
+            pBy = tA * pBy + totBy[q][s];
+        }
+        carry.x = xA * pBx + xBx;
+        carry.y = xA * pBy + xBy;
+    }
+    // ---- forward, pass 2 from the true carry-in; r becomes z = c / u
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+        const int k = k0 + i;
+        carry.x = r[i].x - w[i] * carry.x;
+        carry.y = r[i].y - w[i] * carry.y;
+        const double iu = (k < n) ? __ldg(tiu + (size_t)k * N + (k + m)) : 0.0;
+        r[i].x = carry.x * iu;
+        r[i].y = carry.y * iu;
+    }
+    __syncthreads();   // tot* reused below
+
+    // ---- backward, pass 1: x_out = A x_in + B  (x_in = value just after the chunk)
+    A = 1.0;
+    B = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int i = L - 1; i >= 0; --i) {
+        B.x = r[i].x - w[i + 1] * B.x;
+        B.y = r[i].y - w[i + 1] * B.y;
+        A = -w[i + 1] * A;
+    }
+#pragma unroll
+    for (int d = GS; d < 32; d <<= 1) {
+        const double eA = __shfl_down_sync(0xffffffffu, A, d);
+        const double eBx = __shfl_down_sync(0xffffffffu, B.x, d);
+        const double eBy = __shfl_down_sync(0xffffffffu, B.y, d);
+        if (lane + d < 32) {
+            B.x = A * eBx + B.x;
+            B.y = A * eBy + B.y;
+            A = A * eA;
+        }
+    }
+    xA = __shfl_down_sync(0xffffffffu, A, GS);
+    xBx = __shfl_down_sync(0xffffffffu, B.x, GS);
+    xBy = __shfl_down_sync(0xffffffffu, B.y, GS);
+    if (lane >= 32 - GS) { xA = 1.0; xBx = 0.0; xBy = 0.0; }
+    if (lane < GS) { totA[warp][s] = A; totBx[warp][s] = B.x; totBy[warp][s] = B.y; }
+    __syncthreads();
+    {
+        double pBx = 0.0, pBy = 0.0;
+        for (int q = nwarps - 1; q > warp; --q) {
+            const double tA = totA[q][s];
+            pBx = tA * pBx + totBx[q][s];
+            pBy = tA * pBy + totBy[q][s];
+        }
+        carry.x = xA * pBx + xBx;
+        carry.y = xA * pBy + xBy;
+    }
+    // ---- backward, pass 2; r becomes x
+#pragma unroll
+    for (int i = L - 1; i >= 0; --i) {
+        carry.x = r[i].x - w[i + 1] * carry.x;
+        carry.y = r[i].y - w[i + 1] * carry.y;
+        r[i] = carry;
+    }
+
+    // ---- m = 0: remove the mean of diag(P) (cpu.py:342-352)
+    if (m0 == 0) {
+        double sx = 0.0, sy = 0.0;
+        if (s == 0) {
+#pragma unroll
+            for (int i = 0; i < L; ++i)
+                if (k0 + i < n) { sx += r[i].x; sy += r[i].y; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, o);
+            sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        }
+        __syncthreads();
+        if (lane == 0) { redx[warp] = sx; redy[warp] = sy; }
+        __syncthreads();
+        if (tid == 0) {
+            double ax = 0.0, ay = 0.0;
+            for (int q = 0; q < nwarps; ++q) { ax += redx[q]; ay += redy[q]; }
+            bcast = make_double2(ax / N, ay / N);
+        }
+        __syncthreads();
+        if (s == 0) {
+            const double2 tr = bcast;
+#pragma unroll
+            for (int i = 0; i < L; ++i) { r[i].x -= tr.x; r[i].y -= tr.y; }
+        }
+    }
+
+    // ---- store P = eps x and its skew-Hermitian mirror (cpu.py:334,340; isospectral.py:492)
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+        const int k = k0 + i;
+        if (k < n) {
+            const double2 v = make_double2(eps * r[i].x, eps * r[i].y);
+            X[(size_t)k * N + (k + m)] = v;
+            if (m != 0) X[(size_t)(k + m) * N + k] = make_double2(-v.x, v.y);
+        }
+    }
+}
+
 // W = Delta P for a general matrix (cpu.py:98-108); coefficients recomputed on the fly.
 __global__ void k_laplace(const double2 *__restrict__ P, double2 *__restrict__ W, int N)
 {
@@ -216,17 +429,27 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
 {
     const int N = h->N;
     const size_t n2 = h->mat_elems;
-    double2 *trbuf = h->trbuf;
+    const int g = gated ? 1 : 0;
     if (Wh != W) {
-        dim3 g((unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)h->sm_count * 8), h->batch);
-        k_whalf<<<g, 256, 0, st>>>(W, dW, Wh, n2, h->ctrl, gated ? 1 : 0);
+        dim3 gw((unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)h->sm_count * 8), h->batch);
+        k_whalf<<<gw, 256, 0, st>>>(W, dW, Wh, n2, h->ctrl, g);
         h->launches++;
     }
-    k_trace<<<h->batch, 256, 0, st>>>(Wh, N, h->ctrl, trbuf, gated ? 1 : 0);
-    dim3 gt((N + 63) / 64, h->batch);
-    k_thomas<<<gt, 64, 0, st>>>(Wh, P, h->scratch, h->tab_w, h->tab_iu, h->tab_o, N, eps, h->ctrl, trbuf, gated ? 1 : 0);
-    k_fix_trace<<<h->batch, 256, 0, st>>>(P, N, eps, h->ctrl, gated ? 1 : 0);
-    h->launches += 3;
+    if (N <= 2048) {
+        // chunked scan: 4 diagonals per CTA, 16 positions per thread
+        const int chunks = (N + 15) / 16;
+        const int threads = ((GS * chunks + 31) / 32) * 32;
+        dim3 grid((N + GS - 1) / GS, h->batch);
+        k_poisson_scan<16><<<grid, threads, 0, st>>>(Wh, P, h->tab_w, h->tab_iu, N, eps, h->ctrl, g);
+        h->launches++;
+    } else {
+        // large-N fallback: one thread per diagonal
+        k_trace<<<h->batch, 256, 0, st>>>(Wh, N, h->ctrl, h->trbuf, g);
+        dim3 gt((N + 63) / 64, h->batch);
+        k_thomas<<<gt, 64, 0, st>>>(Wh, P, h->scratch, h->tab_w, h->tab_iu, h->tab_o, N, eps, h->ctrl, h->trbuf, g);
+        k_fix_trace<<<h->batch, 256, 0, st>>>(P, N, eps, h->ctrl, g);
+        h->launches += 3;
+    }
     QF_CUDA(cudaGetLastError());
     return QF_OK;
 }

@@ -37,6 +37,8 @@ struct QfCtrl {
     double norm0;         // ||W||_inf at call start (tol = factor * norm0)
     long long total_it;
     long long n_maxit;
+    unsigned long long resmax_bits;   // running max of residual row sums (bit pattern of a non-negative double)
+    unsigned int ticket;              // blocks of k_control that have finished
     int active;           // 1 while the fixed-point loop of the current step runs
     int it;               // iterations executed in the current step
     int nonfinite;        // sticky: residual was NaN/Inf -> everything becomes a no-op

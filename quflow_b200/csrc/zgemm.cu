@@ -13,6 +13,9 @@
 // The K index inside an MMA is permuted (lane%4 = t uses k = 2t + s) so that the eight lanes of every
 // quarter-warp hit eight different chunks: all fragment loads are bank-conflict free.
 #include <algorithm>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
 
 #include "qf_common.cuh"
 
@@ -81,47 +84,19 @@ __device__ __forceinline__ void load_stage(uint32_t sA, uint32_t sB, const doubl
     }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-k_zgemm(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, double2 *__restrict__ Cg, int N, int row_begin,
-        int row_end, int upper_only, const QfCtrl *__restrict__ ctrl, int gated)
+// Accumulate k-tiles [kt_begin, kt_end) of the (row0, col0) tile into acc (cp.async 3-stage pipeline).
+__device__ __forceinline__ void gemm_mainloop(double (&acc_re)[4][4][2], double (&acc_im)[4][4][2], uint32_t smem_base,
+                                              const double2 *__restrict__ A, const double2 *__restrict__ B, int N, int row0,
+                                              int row_end, int col0, int kt_begin, int kt_end, int tid, int wm, int wn, int g, int t)
 {
-    const int b = blockIdx.z;
-    if (gated && !ctrl[b].active) return;
-    const int row0 = row_begin + blockIdx.y * BM;
-    const int col0 = blockIdx.x * BN;
-    if (upper_only && (col0 + BN - 1 < row0)) return;   // tile entirely below the diagonal
-
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
-
-    const size_t moff = (size_t)b * N * N;
-    const double2 *A = Ag + moff;
-    const double2 *B = Bg + moff;
-    double2 *C = Cg + moff;
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int wm = warp >> 1, wn = warp & 1;   // 4 x 2 warps
-    const int g = lane >> 2, t = lane & 3;
-
-    double acc_re[4][4][2], acc_im[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            acc_re[i][j][0] = acc_re[i][j][1] = 0.0;
-            acc_im[i][j][0] = acc_im[i][j][1] = 0.0;
-        }
-
-    const int KT = (N + BK - 1) / BK;
+    const int nkt = kt_end - kt_begin;
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < KT)
+        if (s < nkt)
             load_stage(smem_base + s * STAGE_BYTES, smem_base + s * STAGE_BYTES + A_STAGE_BYTES, A, B, N, row0, row_end, col0,
-                       s * BK, tid);
+                       (kt_begin + s) * BK, tid);
         cp_async_commit();
     }
-
     // per-thread fragment base offsets inside a stage (see file header for the k permutation)
     uint32_t a_off[2], b_off[2];
 #pragma unroll
@@ -130,15 +105,14 @@ k_zgemm(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, double2 
         a_off[s] = (wm * 32 + g) * 128 + ((kk ^ g) << 4);
         b_off[s] = A_STAGE_BYTES + wn * 4 * (BK * 128) + kk * 128 + ((g ^ kk) << 4);
     }
-
-    for (int kt = 0; kt < KT; ++kt) {
+    for (int kt = 0; kt < nkt; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         {
             const int nk = kt + STAGES - 1;
-            if (nk < KT) {
+            if (nk < nkt) {
                 const uint32_t sb = smem_base + (nk % STAGES) * STAGE_BYTES;
-                load_stage(sb, sb + A_STAGE_BYTES, A, B, N, row0, row_end, col0, nk * BK, tid);
+                load_stage(sb, sb + A_STAGE_BYTES, A, B, N, row0, row_end, col0, (kt_begin + nk) * BK, tid);
             }
             cp_async_commit();
         }
@@ -179,8 +153,14 @@ k_zgemm(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, double2 
         }
     }
     cp_async_wait<0>();
+    __syncthreads();   // all warps are done with shared memory: the next segment may refill it
+}
 
-    // epilogue: each thread owns, per 8x8 sub-tile, row g and the two adjacent columns 2t, 2t+1
+// each thread owns, per 8x8 sub-tile, row g and the two adjacent columns 2t, 2t+1
+__device__ __forceinline__ void gemm_store_tile(const double (&acc_re)[4][4][2], const double (&acc_im)[4][4][2],
+                                                double2 *__restrict__ C, int N, int row0, int row_end, int col0, int wm, int wn,
+                                                int g, int t)
+{
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = row0 + wm * 32 + i * 8 + g;
@@ -195,31 +175,212 @@ k_zgemm(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, double2 
     }
 }
 
+// ---- data-parallel kernel: one CTA per output tile (kept as the simple variant, QF_GEMM=tile) ----
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_zgemm(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, double2 *__restrict__ Cg, int N, int row_begin,
+        int row_end, int upper_only, const QfCtrl *__restrict__ ctrl, int gated)
+{
+    const int b = blockIdx.z;
+    if (gated && !ctrl[b].active) return;
+    const int row0 = row_begin + blockIdx.y * BM;
+    const int col0 = blockIdx.x * BN;
+    if (upper_only && (col0 + BN - 1 < row0)) return;   // tile entirely below the diagonal
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
+    const size_t moff = (size_t)b * N * N;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;   // 4 x 2 warps
+    const int g = lane >> 2, t = lane & 3;
+
+    double acc_re[4][4][2], acc_im[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc_re[i][j][0] = acc_re[i][j][1] = 0.0;
+            acc_im[i][j][0] = acc_im[i][j][1] = 0.0;
+        }
+    gemm_mainloop(acc_re, acc_im, smem_base, Ag + moff, Bg + moff, N, row0, row_end, col0, 0, (N + BK - 1) / BK, tid, wm, wn, g, t);
+    gemm_store_tile(acc_re, acc_im, Cg + moff, N, row0, row_end, col0, wm, wn, g, t);
+}
+
+// ---- stream-K kernel: persistent CTAs split the (tile, k) iteration space evenly --------------------
+// CTA c owns iterations [T c / G, T (c+1) / G) of the T = ntiles * KT k-tile iterations.  A tile whose k range is
+// split is finished by the CTA that computed its k = 0 part (at the END of that CTA's range); the CTAs that hold the
+// rest of the tile compute it FIRST in their own range, park the partial accumulators in their workspace slot and
+// raise a flag.  Waits therefore only ever target work that was started at kernel start: no dependency cycles.
+// Partials are added in CTA order, so the result is deterministic for a given (N, G).
+struct SkTile { int member, row0, col0, pad; };
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, double2 *__restrict__ Cg, int N, int row_end,
+           const SkTile *__restrict__ tiles, int ntiles, double2 *__restrict__ ws, int *__restrict__ flags,
+           const QfCtrl *__restrict__ ctrl, int gated)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int g = lane >> 2, t = lane & 3;
+    const int cta = blockIdx.x, G = gridDim.x;
+    const int KT = (N + BK - 1) / BK;
+    const long long T = (long long)ntiles * KT;
+    long long it = T * cta / G;
+    const long long it_end = T * (cta + 1) / G;
+
+    while (it < it_end) {
+        const int tile = (int)(it / KT);
+        const int ka = (int)(it - (long long)tile * KT);
+        const int kb = (int)min((long long)KT, ka + (it_end - it));
+        const SkTile ti = tiles[tile];
+        it += kb - ka;
+        if (gated && !ctrl[ti.member].active) continue;
+        const size_t moff = (size_t)ti.member * N * N;
+
+        double acc_re[4][4][2], acc_im[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc_re[i][j][0] = acc_re[i][j][1] = 0.0;
+                acc_im[i][j][0] = acc_im[i][j][1] = 0.0;
+            }
+        gemm_mainloop(acc_re, acc_im, smem_base, Ag + moff, Bg + moff, N, ti.row0, row_end, ti.col0, ka, kb, tid, wm, wn, g, t);
+
+        if (ka > 0) {
+            // contributor: park the partial tile in this CTA's slot ([reg][thread] layout: coalesced)
+            double2 *slot = ws + (size_t)cta * (32 * GEMM_THREADS);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    __stcg(slot + ((i * 4 + j) * 2 + 0) * GEMM_THREADS + tid, make_double2(acc_re[i][j][0], acc_re[i][j][1]));
+                    __stcg(slot + ((i * 4 + j) * 2 + 1) * GEMM_THREADS + tid, make_double2(acc_im[i][j][0], acc_im[i][j][1]));
+                }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicExch(flags + cta, 1);
+        } else {
+            if (kb < KT) {
+                // finisher: add the parts computed by the following CTAs, in CTA order
+                const long long tile_end = (long long)(tile + 1) * KT;
+                int peer = cta + 1;
+                long long covered = it_end;
+                while (covered < tile_end) {
+                    if (tid == 0) {
+                        while (atomicAdd(flags + peer, 0) == 0) __nanosleep(64);
+                        atomicExch(flags + peer, 0);   // consume: flags are all zero again when the kernel ends
+                    }
+                    __syncthreads();
+                    __threadfence();
+                    const double2 *slot = ws + (size_t)peer * (32 * GEMM_THREADS);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const double2 pr = __ldcg(slot + ((i * 4 + j) * 2 + 0) * GEMM_THREADS + tid);
+                            const double2 pi = __ldcg(slot + ((i * 4 + j) * 2 + 1) * GEMM_THREADS + tid);
+                            acc_re[i][j][0] += pr.x;
+                            acc_re[i][j][1] += pr.y;
+                            acc_im[i][j][0] += pi.x;
+                            acc_im[i][j][1] += pi.y;
+                        }
+                    covered = T * (peer + 1) / G;
+                    ++peer;
+                }
+            }
+            gemm_store_tile(acc_re, acc_im, Cg + moff, N, ti.row0, row_end, ti.col0, wm, wn, g, t);
+        }
+    }
+}
+
 }   // namespace
 
 struct QfGemmPlan {
-    int smem_bytes;
+    int smem_bytes = 0;
+    bool streamk = true;
+    int max_ctas = 0;
+    double2 *ws = nullptr;      // [max_ctas][32][256] partial tiles
+    int *flags = nullptr;       // [max_ctas]
+    // cached tile lists keyed by (upper_only, row_begin, row_end)
+    struct List { int upper, rb, re, ntiles; SkTile *dev; };
+    std::vector<List> lists;
 };
 
 int qf_gemm_create(qf_handle_s *h)
 {
-    h->gemm = new QfGemmPlan{GEMM_SMEM};
+    QfGemmPlan *p = new QfGemmPlan();
+    h->gemm = p;
+    p->smem_bytes = GEMM_SMEM;
+    const char *env = getenv("QF_GEMM");
+    p->streamk = !(env && strcmp(env, "tile") == 0);
+    p->max_ctas = h->sm_count;
     QF_CUDA(cudaFuncSetAttribute(k_zgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    QF_CUDA(cudaMalloc(&p->ws, sizeof(double2) * 32 * GEMM_THREADS * (size_t)p->max_ctas));
+    QF_CUDA(cudaMalloc(&p->flags, sizeof(int) * p->max_ctas));
+    QF_CUDA(cudaMemset(p->flags, 0, sizeof(int) * p->max_ctas));
     return QF_OK;
 }
 
 void qf_gemm_destroy(qf_handle_s *h)
 {
+    if (!h->gemm) return;
+    for (auto &l : h->gemm->lists) cudaFree(l.dev);
+    if (h->gemm->ws) cudaFree(h->gemm->ws);
+    if (h->gemm->flags) cudaFree(h->gemm->flags);
     delete h->gemm;
     h->gemm = nullptr;
+}
+
+static int get_tile_list(qf_handle_s *h, bool upper_only, int row_begin, int row_end, const SkTile **dev, int *ntiles)
+{
+    QfGemmPlan *p = h->gemm;
+    for (auto &l : p->lists)
+        if (l.upper == (int)upper_only && l.rb == row_begin && l.re == row_end) {
+            *dev = l.dev;
+            *ntiles = l.ntiles;
+            return QF_OK;
+        }
+    std::vector<SkTile> tl;
+    const int N = h->N;
+    for (int b = 0; b < h->batch; ++b)
+        for (int r0 = row_begin; r0 < row_end; r0 += BM)
+            for (int c0 = 0; c0 < N; c0 += BN) {
+                if (upper_only && (c0 + BN - 1 < r0)) continue;
+                tl.push_back(SkTile{b, r0, c0, 0});
+            }
+    QfGemmPlan::List l{(int)upper_only, row_begin, row_end, (int)tl.size(), nullptr};
+    QF_CUDA(cudaMalloc(&l.dev, sizeof(SkTile) * std::max<size_t>(tl.size(), 1)));
+    QF_CUDA(cudaMemcpy(l.dev, tl.data(), sizeof(SkTile) * tl.size(), cudaMemcpyHostToDevice));
+    p->lists.push_back(l);
+    *dev = l.dev;
+    *ntiles = l.ntiles;
+    return QF_OK;
 }
 
 int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 *C, bool upper_only, bool gated,
                     int row_begin, int row_end, cudaStream_t st)
 {
     const int N = h->N;
-    dim3 grid((N + BN - 1) / BN, (row_end - row_begin + BM - 1) / BM, h->batch);
-    k_zgemm<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(A, B, C, N, row_begin, row_end, upper_only ? 1 : 0, h->ctrl, gated ? 1 : 0);
+    QfGemmPlan *p = h->gemm;
+    if (!p->streamk) {
+        dim3 grid((N + BN - 1) / BN, (row_end - row_begin + BM - 1) / BM, h->batch);
+        k_zgemm<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(A, B, C, N, row_begin, row_end, upper_only ? 1 : 0, h->ctrl, gated ? 1 : 0);
+    } else {
+        const SkTile *tiles;
+        int ntiles;
+        QF_CHECK(get_tile_list(h, upper_only, row_begin, row_end, &tiles, &ntiles));
+        const int KT = (N + BK - 1) / BK;
+        const long long T = (long long)ntiles * KT;
+        // at least 8 k-iterations per CTA so that the fix-up traffic stays small
+        int G = (int)std::min<long long>(p->max_ctas, std::max<long long>(1, T / 8));
+        if (ntiles == 0) return QF_OK;
+        k_zgemm_sk<<<G, GEMM_THREADS, GEMM_SMEM, st>>>(A, B, C, N, row_end, tiles, ntiles, p->ws, p->flags, h->ctrl, gated ? 1 : 0);
+    }
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;
