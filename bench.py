@@ -249,7 +249,11 @@ def gpu_arm(args):
         return
 
     # ---- roofline of the dominant kernel (rank 0, single-GPU kernels) -------------------------------
-    hsolo = handle if world == 1 else get_handle(N, 1, local_rank)
+    if world == 1:
+        hsolo = handle
+    else:
+        from quflow_b200._cuda import Handle
+        hsolo = Handle(N, 1, local_rank)      # a fresh, unsharded handle: single-GPU kernels only
     ph = hsolo.profile_iteration(torch.from_numpy(W0).to(dev), kw["dt"], reps=5)
     gemm1_tf = 8.0 * N ** 3 / (ph["gemm1_ms"] * 1e-3) / 1e12
     # S = A P~ only computes the 64-wide column blocks that touch the upper triangle

@@ -135,6 +135,8 @@ int qf_profile_iteration(qf_handle_t h, const void *W_dev, double dt, int reps, 
 #define QF_UNIQUE_ID_BYTES 128
 int qf_comm_get_unique_id(void *id_out);
 int qf_comm_init(qf_handle_t h, const void *unique_id, int rank, int nranks);
+/* Test hook: run the row-sharded data path for `nranks` ranks on ONE GPU (all ranks' tiles, no communication). */
+int qf_set_emulated_ranks(qf_handle_t h, int nranks);
 
 #ifdef __cplusplus
 }

@@ -67,6 +67,7 @@ SYMBOLS = {
     "qf_profile_iteration": (_i, [_vp, _vp, _d, _i, ctypes.POINTER(qf_phase_times), _vp]),
     "qf_comm_get_unique_id": (_i, [_vp]),
     "qf_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "qf_set_emulated_ranks": (_i, [_vp, _i]),
 }
 
 
@@ -226,6 +227,9 @@ class Handle:
         return {k: getattr(pt, k) for k, _ in qf_phase_times._fields_}
 
     # -- multi-GPU -----------------------------------------------------------------------
+    def set_emulated_ranks(self, nranks: int):
+        _check(self._lib.qf_set_emulated_ranks(self._h, int(nranks)))
+
     def comm_init(self, unique_id: bytes, rank: int, nranks: int):
         buf = ctypes.create_string_buffer(unique_id, QF_UNIQUE_ID_BYTES)
         _check(self._lib.qf_comm_init(self._h, buf, int(rank), int(nranks)))

@@ -4,6 +4,8 @@
 
 #include "qf_common.cuh"
 
+void qf_comm_destroy(qf_handle_s *h);   // comm.cu
+
 static thread_local char g_err[512] = "";
 
 void qf_set_error(const char *fmt, ...)
@@ -87,6 +89,7 @@ extern "C" int qf_destroy(qf_handle_t h)
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     qf_gemm_destroy(h);
+    qf_comm_destroy(h);
     void *ptrs[] = {h->tab_w, h->tab_iu, h->tab_o, h->dW, h->Wh, h->P, h->A, h->S, h->scratch, h->kahan_c,
                     h->io, h->io2, h->rowpart, h->trbuf, h->ctrl, h->iters_dev};
     for (void *p : ptrs)
@@ -132,7 +135,7 @@ extern "C" int qf_zgemm(qf_handle_t h, const void *A_dev, const void *B_dev, voi
 {
     if (!h || !A_dev || !B_dev || !C_dev) { qf_set_error("qf_zgemm: null argument"); return QF_ERR_INVALID; }
     QF_CUDA(cudaSetDevice(h->device));
-    return qf_launch_zgemm(h, (const double2 *)A_dev, (const double2 *)B_dev, (double2 *)C_dev, false, false, 0, h->N,
+    return qf_launch_zgemm(h, (const double2 *)A_dev, (const double2 *)B_dev, (double2 *)C_dev, false, false, -1, 1, false,
                            (cudaStream_t)stream);
 }
 
@@ -183,14 +186,3 @@ extern "C" int qf_laplace_host(qf_handle_t h, const void *P_host, void *W_host)
     return QF_OK;
 }
 
-// ---- multi-GPU (filled in by comm.cu when built with NCCL) --------------------------------
-extern "C" __attribute__((weak)) int qf_comm_get_unique_id(void *)
-{
-    qf_set_error("built without NCCL");
-    return QF_ERR_UNSUPPORTED;
-}
-extern "C" __attribute__((weak)) int qf_comm_init(qf_handle_t, const void *, int, int)
-{
-    qf_set_error("built without NCCL");
-    return QF_ERR_UNSUPPORTED;
-}

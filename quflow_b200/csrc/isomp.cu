@@ -73,7 +73,7 @@ __global__ void k_zero(double2 *X, size_t n2, const QfCtrl *__restrict__ ctrl)
 //   direct[i][bj] = sum_{j in tile, j >= i} r_ij      mirr[j][bi] = sum_{i in tile, i < j} r_ij
 __global__ void __launch_bounds__(256)
 k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *__restrict__ dWg, double *__restrict__ rowpart,
-       int N, int nslots, const QfCtrl *__restrict__ ctrl)
+       int N, int nslots, const QfCtrl *__restrict__ ctrl, int hb, int G)
 {
     const int b = blockIdx.z;
     if (!ctrl[b].active) return;
@@ -95,7 +95,7 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
     for (int q = 0; q < 4; ++q) {
         const int jj = ty + 8 * q;
         const int j = bj * TS + jj, i = bi * TS + tx;
-        T[jj][tx] = (j < N && i < N) ? A[(size_t)j * N + i] : make_double2(0.0, 0.0);
+        T[jj][tx] = (j < N && i < N) ? A[(size_t)qf_prow(j, hb, G) * N + i] : make_double2(0.0, 0.0);
     }
     __syncthreads();
 #pragma unroll
@@ -106,8 +106,9 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
         double2 d = make_double2(0.0, 0.0);
         if (i < N && j < N && i <= j) {
             const size_t ij = (size_t)i * N + j;
-            const double2 c = zsub(A[ij], zconj(T[tx][ii]));          // isospectral.py:66-81
-            double2 s = S[ij];
+            const size_t pij = (size_t)qf_prow(i, hb, G) * N + j;     // A and S use the rank-permuted row layout
+            const double2 c = zsub(A[pij], zconj(T[tx][ii]));         // isospectral.py:66-81
+            double2 s = S[pij];
             if (i == j) s.x = 0.0;                                    // P W P is skew-Hermitian
             d = zadd(s, c);                                           // :499,:509
             const double2 old = dW[ij];
@@ -194,7 +195,7 @@ k_control(const double *__restrict__ rowpart, int N, int nslots, QfCtrl *ctrl, i
 template <bool COMPSUM>
 __global__ void __launch_bounds__(256)
 k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__restrict__ Kg, int N, QfCtrl *ctrl,
-         int32_t *iters, int steps_cap)
+         int32_t *iters, int steps_cap, int hb, int G)
 {
     const int b = blockIdx.z;
     QfCtrl &c = ctrl[b];
@@ -216,7 +217,7 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
     for (int q = 0; q < 4; ++q) {
         const int jj = ty + 8 * q;
         const int j = bj * TS + jj, i = bi * TS + tx;
-        T[jj][tx] = (j < N && i < N) ? A[(size_t)j * N + i] : make_double2(0.0, 0.0);
+        T[jj][tx] = (j < N && i < N) ? A[(size_t)qf_prow(j, hb, G) * N + i] : make_double2(0.0, 0.0);
     }
     __syncthreads();
     double2 wv[4], kv[4];
@@ -227,7 +228,7 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
         double2 w = make_double2(0.0, 0.0), kc = make_double2(0.0, 0.0);
         if (i < N && j < N && i <= j) {
             const size_t ij = (size_t)i * N + j;
-            double2 cm = zsub(A[ij], zconj(T[tx][ii]));
+            double2 cm = zsub(A[(size_t)qf_prow(i, hb, G) * N + j], zconj(T[tx][ii]));
             cm = make_double2(2.0 * cm.x, 2.0 * cm.y);
             w = W[ij];
             if (COMPSUM) {
@@ -289,16 +290,22 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
                          cudaEvent_t *ev /* 5 events or null */)
 {
     const int N = h->N;
+    const int G = h->nranks;
+    const bool real_comm = (G > 1 && h->nccl_comm != nullptr);
+    const int my = real_comm ? h->rank : -1;          // -1: compute every rank's blocks here (single GPU / emulation)
+    const int hb = qf_block_rows(N, G);
     if (ev) QF_CUDA(cudaEventRecord(ev[0], st));
     QF_CHECK(qf_launch_poisson(h, W, h->dW, h->Wh, h->P, eps, true, st));
     if (ev) QF_CUDA(cudaEventRecord(ev[1], st));
-    QF_CHECK(qf_launch_zgemm(h, h->P, h->Wh, h->A, false, true, 0, N, st));
+    QF_CHECK(qf_launch_zgemm(h, h->P, h->Wh, h->A, false, true, my, G, false, st));        // rows of A = P~ W~
+    if (real_comm) QF_CHECK(qf_comm_allgather_rows(h, h->A, st));
     if (ev) QF_CUDA(cudaEventRecord(ev[2], st));
-    QF_CHECK(qf_launch_zgemm(h, h->A, h->P, h->S, true, true, 0, N, st));
+    QF_CHECK(qf_launch_zgemm(h, h->A, h->P, h->S, true, true, my, G, true, st));          // rows of S = A P~ (A rows are local)
+    if (real_comm) QF_CHECK(qf_comm_allgather_rows(h, h->S, st));
     if (ev) QF_CUDA(cudaEventRecord(ev[3], st));
     const int nb = (N + TS - 1) / TS;
     dim3 g(nb, nb, h->batch);
-    k_post<<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl);
+    k_post<<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, G);
     k_control<<<dim3((N + 7) / 8, h->batch), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit);
     h->launches += 2;
     if (ev) QF_CUDA(cudaEventRecord(ev[4], st));
@@ -310,11 +317,12 @@ int qf_enqueue_update(qf_handle_s *h, double2 *W, bool compsum, cudaStream_t st)
 {
     const int N = h->N;
     const int nb = (N + TS - 1) / TS;
+    const int hb = qf_block_rows(N, h->nranks);
     dim3 g(nb, nb, h->batch);
     if (compsum)
-        k_update<true><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, h->iters_dev, h->steps_cap);
+        k_update<true><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks);
     else
-        k_update<false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, h->iters_dev, h->steps_cap);
+        k_update<false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks);
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;

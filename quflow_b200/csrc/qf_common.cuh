@@ -84,7 +84,7 @@ struct qf_handle_s {
     long long launches = 0;
     // multi-GPU
     void *nccl_comm = nullptr;
-    int rank = 0, nranks = 1;
+    int rank = 0, nranks = 1;     // nranks > 1 with nccl_comm == nullptr: all ranks emulated on this GPU (tests)
     QfGemmPlan *gemm = nullptr;
 };
 
@@ -102,9 +102,28 @@ int qf_launch_laplace(qf_handle_s *h, const double2 *P, double2 *W, cudaStream_t
 int qf_gemm_create(qf_handle_s *h);
 void qf_gemm_destroy(qf_handle_s *h);
 // C = A * B.  upper_only: compute only the 64-wide column blocks that intersect the upper triangle
-// (used for S = A P~ which is skew-Hermitian).  row_begin/row_end: row range (multi-GPU sharding).
+// (used for S = A P~ which is skew-Hermitian).  rank/nranks: row-block sharding (rank < 0: all blocks).
+// a_permuted: the A operand is itself stored in the rank-permuted row layout (an earlier GEMM's output).
 int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 *C, bool upper_only, bool gated,
-                    int row_begin, int row_end, cudaStream_t st);
+                    int rank, int nranks, bool a_permuted, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------
+// Row-block sharding across G ranks (multi-GPU).
+// The N rows are cut into 2G blocks of hb rows; rank r owns logical blocks r and 2G-1-r, which balances the
+// upper-triangular second GEMM.  GEMM outputs (A, S) are stored with rows PERMUTED so that each rank's two
+// blocks are contiguous: permuted row = (2r + slot) * hb + (i mod hb).  One in-place ncclAllGather then
+// completes the matrix on every rank.  G = 1 is the identity.
+// ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int qf_block_rows(int N, int G) { return G == 1 ? N : (N + 2 * G - 1) / (2 * G); }
+__host__ __device__ __forceinline__ int qf_prow(int i, int hb, int G)
+{
+    if (G == 1) return i;
+    const int blk = i / hb;
+    const int r = blk < G ? blk : 2 * G - 1 - blk;
+    const int slot = blk < G ? 0 : 1;
+    return (2 * r + slot) * hb + (i - blk * hb);
+}
+int qf_comm_allgather_rows(qf_handle_s *h, double2 *M, cudaStream_t st);   // comm.cu
 
 // isomp.cu
 int qf_launch_norm_inf(qf_handle_s *h, const double2 *W, cudaStream_t st);   // -> ctrl[b].norm0

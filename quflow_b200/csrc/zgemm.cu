@@ -161,6 +161,7 @@ __device__ __forceinline__ void gemm_store_tile(const double (&acc_re)[4][4][2],
                                                 double2 *__restrict__ C, int N, int row0, int row_end, int col0, int wm, int wn,
                                                 int g, int t)
 {
+    // row0 / row_end are in the OUTPUT row numbering here
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = row0 + wm * 32 + i * 8 + g;
@@ -212,10 +213,12 @@ k_zgemm(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, double2 
 // rest of the tile compute it FIRST in their own range, park the partial accumulators in their workspace slot and
 // raise a flag.  Waits therefore only ever target work that was started at kernel start: no dependency cycles.
 // Partials are added in CTA order, so the result is deterministic for a given (N, G).
-struct SkTile { int member, row0, col0, pad; };
+// One output tile: rows [a_row0, row_end) of the A operand (logical matrix rows) times columns [col0, col0+64) of B,
+// written to rows c_row0.. of C (C may use the rank-permuted row layout of the multi-GPU path, see qf_common.cuh).
+struct SkTile { int member, a_row0, c_row0, col0, row_end, op_row0, pad1, pad2; };   // op_row0: first row of the A operand in memory
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, double2 *__restrict__ Cg, int N, int row_end,
+k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, double2 *__restrict__ Cg, int N,
            const SkTile *__restrict__ tiles, int ntiles, double2 *__restrict__ ws, int *__restrict__ flags,
            const QfCtrl *__restrict__ ctrl, int gated)
 {
@@ -248,7 +251,10 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
                 acc_re[i][j][0] = acc_re[i][j][1] = 0.0;
                 acc_im[i][j][0] = acc_im[i][j][1] = 0.0;
             }
-        gemm_mainloop(acc_re, acc_im, smem_base, Ag + moff, Bg + moff, N, ti.row0, row_end, ti.col0, ka, kb, tid, wm, wn, g, t);
+        // the A operand may itself be stored in the rank-permuted row layout (second GEMM): shift the base pointer so that
+        // logical row a_row0 addresses memory row op_row0
+        gemm_mainloop(acc_re, acc_im, smem_base, Ag + moff + ((ptrdiff_t)ti.op_row0 - ti.a_row0) * N, Bg + moff, N, ti.a_row0, ti.row_end,
+                      ti.col0, ka, kb, tid, wm, wn, g, t);
 
         if (ka > 0) {
             // contributor: park the partial tile in this CTA's slot ([reg][thread] layout: coalesced)
@@ -292,7 +298,7 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
                     ++peer;
                 }
             }
-            gemm_store_tile(acc_re, acc_im, Cg + moff, N, ti.row0, row_end, ti.col0, wm, wn, g, t);
+            gemm_store_tile(acc_re, acc_im, Cg + moff, N, ti.c_row0, ti.c_row0 + (ti.row_end - ti.a_row0), ti.col0, wm, wn, g, t);
         }
     }
 }
@@ -305,8 +311,8 @@ struct QfGemmPlan {
     int max_ctas = 0;
     double2 *ws = nullptr;      // [max_ctas][32][256] partial tiles
     int *flags = nullptr;       // [max_ctas]
-    // cached tile lists keyed by (upper_only, row_begin, row_end)
-    struct List { int upper, rb, re, ntiles; SkTile *dev; };
+    // cached tile lists keyed by (upper_only, rank, nranks); rank < 0 = all ranks (single-GPU emulation)
+    struct List { int upper, rank, nranks, aperm, ntiles; SkTile *dev; };
     std::vector<List> lists;
 };
 
@@ -336,24 +342,34 @@ void qf_gemm_destroy(qf_handle_s *h)
     h->gemm = nullptr;
 }
 
-static int get_tile_list(qf_handle_s *h, bool upper_only, int row_begin, int row_end, const SkTile **dev, int *ntiles)
+static int get_tile_list(qf_handle_s *h, bool upper_only, int rank, int nranks, bool a_permuted, const SkTile **dev, int *ntiles)
 {
     QfGemmPlan *p = h->gemm;
     for (auto &l : p->lists)
-        if (l.upper == (int)upper_only && l.rb == row_begin && l.re == row_end) {
+        if (l.upper == (int)upper_only && l.rank == rank && l.nranks == nranks && l.aperm == (int)a_permuted) {
             *dev = l.dev;
             *ntiles = l.ntiles;
             return QF_OK;
         }
     std::vector<SkTile> tl;
     const int N = h->N;
+    const int hb = qf_block_rows(N, nranks);
     for (int b = 0; b < h->batch; ++b)
-        for (int r0 = row_begin; r0 < row_end; r0 += BM)
-            for (int c0 = 0; c0 < N; c0 += BN) {
-                if (upper_only && (c0 + BN - 1 < r0)) continue;
-                tl.push_back(SkTile{b, r0, c0, 0});
+        for (int r = 0; r < nranks; ++r) {
+            if (rank >= 0 && r != rank) continue;
+            // rank r owns logical row blocks r and 2G-1-r (balanced for the upper-triangular GEMM)
+            const int blocks[2] = {r, 2 * nranks - 1 - r};
+            for (int q = 0; q < (nranks == 1 ? 1 : 2); ++q) {
+                const int rb = (nranks == 1) ? 0 : blocks[q] * hb;
+                const int re = (nranks == 1) ? N : std::min(N, rb + hb);
+                for (int r0 = rb; r0 < re; r0 += BM)
+                    for (int c0 = 0; c0 < N; c0 += BN) {
+                        if (upper_only && (c0 + BN - 1 < r0)) continue;
+                        tl.push_back(SkTile{b, r0, qf_prow(r0, hb, nranks), c0, re, a_permuted ? qf_prow(r0, hb, nranks) : r0, 0, 0});
+                    }
             }
-    QfGemmPlan::List l{(int)upper_only, row_begin, row_end, (int)tl.size(), nullptr};
+        }
+    QfGemmPlan::List l{(int)upper_only, rank, nranks, (int)a_permuted, (int)tl.size(), nullptr};
     QF_CUDA(cudaMalloc(&l.dev, sizeof(SkTile) * std::max<size_t>(tl.size(), 1)));
     QF_CUDA(cudaMemcpy(l.dev, tl.data(), sizeof(SkTile) * tl.size(), cudaMemcpyHostToDevice));
     p->lists.push_back(l);
@@ -362,24 +378,25 @@ static int get_tile_list(qf_handle_s *h, bool upper_only, int row_begin, int row
     return QF_OK;
 }
 
+// rank/nranks select the row blocks (see qf_prow); rank < 0 computes every rank's blocks (emulation on one GPU).
 int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 *C, bool upper_only, bool gated,
-                    int row_begin, int row_end, cudaStream_t st)
+                    int rank, int nranks, bool a_permuted, cudaStream_t st)
 {
     const int N = h->N;
     QfGemmPlan *p = h->gemm;
-    if (!p->streamk) {
-        dim3 grid((N + BN - 1) / BN, (row_end - row_begin + BM - 1) / BM, h->batch);
-        k_zgemm<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(A, B, C, N, row_begin, row_end, upper_only ? 1 : 0, h->ctrl, gated ? 1 : 0);
+    if (!p->streamk && nranks == 1) {
+        dim3 grid((N + BN - 1) / BN, (N + BM - 1) / BM, h->batch);
+        k_zgemm<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(A, B, C, N, 0, N, upper_only ? 1 : 0, h->ctrl, gated ? 1 : 0);
     } else {
         const SkTile *tiles;
         int ntiles;
-        QF_CHECK(get_tile_list(h, upper_only, row_begin, row_end, &tiles, &ntiles));
+        QF_CHECK(get_tile_list(h, upper_only, rank, nranks, a_permuted, &tiles, &ntiles));
         const int KT = (N + BK - 1) / BK;
         const long long T = (long long)ntiles * KT;
-        // at least 8 k-iterations per CTA so that the fix-up traffic stays small
-        int G = (int)std::min<long long>(p->max_ctas, std::max<long long>(1, T / 8));
         if (ntiles == 0) return QF_OK;
-        k_zgemm_sk<<<G, GEMM_THREADS, GEMM_SMEM, st>>>(A, B, C, N, row_end, tiles, ntiles, p->ws, p->flags, h->ctrl, gated ? 1 : 0);
+        // at least 8 k-iterations per CTA so that the fix-up traffic stays small
+        const int G = (int)std::min<long long>(p->max_ctas, std::max<long long>(1, T / 8));
+        k_zgemm_sk<<<G, GEMM_THREADS, GEMM_SMEM, st>>>(A, B, C, N, tiles, ntiles, p->ws, p->flags, h->ctrl, gated ? 1 : 0);
     }
     h->launches++;
     QF_CUDA(cudaGetLastError());

@@ -1,0 +1,73 @@
+"""Multi-GPU host logic: one process per GPU, torch.distributed for the plumbing, NCCL inside the library.
+
+New functionality relative to the reference (which is single-process):
+
+* ``attach_row_sharding(handle, dist)`` — shard ONE large-N simulation by row blocks of the two GEMMs across the
+  ranks of the default process group.  The NCCL communicator lives inside libquflow_b200.so (so the all-gathers are
+  enqueued on the same stream as the kernels, with no Python in the loop); torch.distributed only carries the
+  128-byte ncclUniqueId from rank 0 to the other ranks.
+* ``member_slice(k, rank, world)`` / ``isomp_ensemble_sharded`` — shard an ensemble per member: no data-path
+  collective at all, one gather of the results at the end.
+"""
+import numpy as np
+
+from ._cuda import binding
+
+
+def row_blocks(N: int, world: int):
+    """Logical row ranges owned by each rank: blocks r and 2*world-1-r of N/(2*world) rows (balanced for the
+    upper-triangular second GEMM).  Mirrors qf_prow()/qf_block_rows() in csrc/qf_common.cuh."""
+    if world == 1:
+        return [[(0, N)]]
+    if N % (2 * world) != 0:
+        raise ValueError(f"row sharding needs N divisible by 2*world (N={N}, world={world})")
+    hb = N // (2 * world)
+    return [[(r * hb, (r + 1) * hb), ((2 * world - 1 - r) * hb, (2 * world - r) * hb)] for r in range(world)]
+
+
+def permuted_row(i: int, N: int, world: int) -> int:
+    """Row index of logical row i in the rank-permuted layout of the GEMM outputs."""
+    if world == 1:
+        return i
+    hb = N // (2 * world)
+    blk = i // hb
+    r, slot = (blk, 0) if blk < world else (2 * world - 1 - blk, 1)
+    return (2 * r + slot) * hb + (i - blk * hb)
+
+
+def broadcast_unique_id(dist, make_id=None) -> bytes:
+    """Rank 0 creates the ncclUniqueId; everybody receives it through the default process group (any backend)."""
+    import torch
+    rank = dist.get_rank()
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    buf = torch.zeros(binding.QF_UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        raw = (make_id or binding.comm_unique_id)()
+        buf.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+    dist.broadcast(buf, src=0)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def attach_row_sharding(handle, dist):
+    """Make ``handle`` (batch == 1) run its GEMMs row-sharded over the default process group."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world == 1:
+        return handle
+    row_blocks(handle.N, world)     # validates divisibility with a Python-level error
+    uid = broadcast_unique_id(dist)
+    handle.comm_init(uid, rank, world)
+    return handle
+
+
+def member_slice(k: int, rank: int, world: int) -> slice:
+    """Members of a k-member ensemble owned by ``rank`` (contiguous, sizes differ by at most one)."""
+    base, rem = divmod(k, world)
+    start = rank * base + min(rank, rem)
+    return slice(start, start + base + (1 if rank < rem else 0))
+
+
+def isomp_ensemble_sharded(W_local, dt, steps, dist=None, **kw):
+    """Advance this rank's members of an ensemble (``W_local``: (k_local, N, N)); no collective on the data path."""
+    from .integrators import isomp_ensemble
+    return isomp_ensemble(W_local, dt, steps, **kw)

@@ -1,0 +1,69 @@
+"""Multi-GPU parity check, launched by torchrun (one rank per GPU):
+row-sharded isomp over NCCL must reproduce the single-GPU result and the CPU oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import oracle  # noqa: E402
+import quflow_b200 as qf  # noqa: E402
+from quflow_b200._cuda import Handle  # noqa: E402
+from quflow_b200.distributed import attach_row_sharding, member_slice  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    for N, steps in ((256, 10), (1024, 6)):
+        W0 = oracle.random_skewherm(N, 42)
+        dt = 0.25 * qf.hbar(N)
+        solo = Handle(N, 1, local)
+        Ws = W0.copy()
+        rs, its_s = solo.isomp(Ws, dt, steps, want_iters=True)
+        shard = Handle(N, 1, local)
+        attach_row_sharding(shard, dist)
+        Wd = torch.from_numpy(W0).cuda()
+        rd, its_d = shard.isomp(Wd, dt, steps, want_iters=True)
+        Wm = Wd.cpu().numpy()
+        err = np.linalg.norm(Wm - Ws) / np.linalg.norm(Ws)
+        same_its = list(its_s[0]) == list(its_d[0])
+        # all ranks must hold bit-identical states (replicated control flow)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, Wm.tobytes())
+        identical = all(g == gathered[0] for g in gathered)
+        msg = f"rank {rank}: N={N} sharded-vs-solo rel.err={err:.2e} iterations equal={same_its} ranks identical={identical}"
+        if N <= 256:
+            rec = {}
+            Wref = oracle.isomp(W0.copy(), dt, steps, record=rec)
+            eo = np.linalg.norm(Wm - Wref) / np.linalg.norm(Wref)
+            msg += f" vs-oracle={eo:.2e}"
+            ok = ok and eo < 1e-12 and list(its_d[0]) == rec["iterations"]
+        print(msg, flush=True)
+        ok = ok and err < 1e-13 and same_its and identical
+        solo.close(); shard.close()
+    # ensemble sharded per member: no collective on the data path
+    k, N = 6, 64
+    W0 = np.stack([oracle.random_skewherm(N, s) for s in range(k)])
+    sl = member_slice(k, rank, world)
+    Wl = W0[sl].copy()
+    qf.isomp_ensemble(Wl, 0.25 * qf.hbar(N), steps=8)
+    for j, s in enumerate(range(k)[sl]):
+        Wref = oracle.isomp(W0[s].copy(), 0.25 * qf.hbar(N), 8)
+        ok = ok and np.linalg.norm(Wl[j] - Wref) / np.linalg.norm(Wref) < 1e-12
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MGPU_OK" if int(flag.item()) == 1 else "MGPU_FAIL", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

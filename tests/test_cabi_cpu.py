@@ -1,0 +1,94 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol include/*.h declares,
+the Python mirror keeps the reference's signatures, and the product path fails loudly without a GPU."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from quflow_b200._cuda import build, binding
+    build.build()                      # nvcc cross-compiles sm_100a without a GPU
+    return binding.library()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "quflow_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qf_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    from quflow_b200._cuda import binding
+    syms = declared_symbols()
+    assert len(syms) >= 18
+    for name in syms:
+        assert hasattr(lib, name), f"{name} declared in include/quflow_b200.h but not exported"
+        assert name in binding.SYMBOLS, f"{name} has no ctypes prototype in binding.py"
+
+
+def test_no_torch_types_in_the_abi():
+    text = open(os.path.join(ROOT, "include", "quflow_b200.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", text, flags=re.S)      # signatures only, comments stripped
+    assert "torch" not in code.lower() and "at::" not in code and "c10::" not in code and "std::" not in code
+    assert "#include <stdint.h>" in code and code.count("#include") == 1
+
+
+def test_library_reports_version_and_fails_loudly_without_gpu(lib):
+    import torch
+    assert b"quflow_b200" in lib.qf_version()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import quflow_b200 as qf
+    from quflow_b200._cuda import QfError
+    W = np.zeros((8, 8), dtype=np.complex128)
+    for call in (lambda: qf.solve_poisson(W), lambda: qf.laplace(W), lambda: qf.isomp(W, 0.1, 1)):
+        with pytest.raises(QfError, match="no CUDA device|no CPU fallback"):
+            call()
+
+
+def test_product_path_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "quflow_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+                assert "libqforacle" not in src
+
+
+def test_python_signatures_mirror_the_reference():
+    import quflow_b200 as qf
+    spec = inspect.getfullargspec(qf.isomp)
+    # quflow/integrators/isospectral.py:338-353
+    assert spec.args == ['W', 'dt', 'steps', 'hamiltonian', 'time', 'forcing', 'strang_splitting', 'stats', 'callback',
+                         'tol', 'maxit', 'minit', 'verbatim', 'compsum', 'reinitialize']
+    defaults = dict(zip(spec.args[-len(spec.defaults):], spec.defaults))
+    assert defaults['steps'] == 100 and defaults['tol'] == 'auto' and defaults['maxit'] == 10 and defaults['minit'] == 1
+    assert defaults['hamiltonian'] is qf.solve_poisson and defaults['compsum'] is False and defaults['reinitialize'] is False
+    assert qf.isomp is qf.isomp_fixedpoint                           # isospectral.py:617
+    assert 'stats' in spec.args                                      # qf.solve() passes stats only if it is listed (simulation.py:730)
+    assert inspect.getfullargspec(qf.solve_poisson).args == ['W', 'reduce']   # cpu.py:681; no `time` => autonomous probe
+    assert qf.hbar(512) == 2.0 / np.sqrt(512.0 ** 2 - 1)             # geometry.py:7-9
+
+
+def test_argument_validation_happens_before_any_device_work():
+    import quflow_b200 as qf
+    W = np.zeros((8, 8), dtype=np.complex128)
+    with pytest.raises(AssertionError, match="minit must be at least 1"):
+        qf.isomp(W, 0.1, 1, minit=0)
+    with pytest.raises(AssertionError, match="maxit must be at minit"):
+        qf.isomp(W, 0.1, 1, minit=5, maxit=2)
+    with pytest.raises(NotImplementedError):
+        qf.isomp(W, 0.1, 1, hamiltonian=lambda X: X)
+    with pytest.raises(NotImplementedError):
+        qf.isomp(W, 0.1, 1, forcing=lambda P, X: X)
+    with pytest.raises(TypeError):
+        qf.solve_poisson(W.astype(np.complex64))
+    with pytest.raises(TypeError):
+        qf.solve_poisson(W, time=0.0)
