@@ -1,5 +1,6 @@
 // C-ABI entry points (see include/quflow_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "qf_common.cuh"
@@ -63,6 +64,10 @@ extern "C" int qf_create(int N, int batch, int device, qf_handle_t *out)
     h->sm_count = prop.multiProcessorCount;
     h->mat_elems = (size_t)N * N;
     h->nslots = (N + 31) / 32;
+    {
+        const char *env = getenv("QF_GRAPH");
+        h->use_graph = !(env && env[0] == '0');
+    }
     int rc = qf_build_tables(h);
     if (rc == QF_OK) rc = alloc_mat(h, &h->dW);
     if (rc == QF_OK) rc = alloc_mat(h, &h->Wh);
@@ -88,6 +93,7 @@ extern "C" int qf_destroy(qf_handle_t h)
     if (!h) return QF_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    qf_graph_destroy(h);
     qf_gemm_destroy(h);
     qf_comm_destroy(h);
     void *ptrs[] = {h->tab_w, h->tab_iu, h->tab_o, h->dW, h->Wh, h->P, h->A, h->S, h->scratch, h->kahan_c,

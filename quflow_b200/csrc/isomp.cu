@@ -10,6 +10,7 @@
 // The stopping rule lives in a device-resident control block (QfCtrl): all kernels of the iterations that
 // follow convergence return immediately, so a whole step is enqueued without any host synchronisation.
 #include <math.h>
+#include <algorithm>
 
 #include "qf_common.cuh"
 
@@ -50,12 +51,26 @@ __global__ void k_call_begin(QfCtrl *ctrl, double tol, double tol_factor)
     c.ticket = 0u;
 }
 
-__global__ void k_step_begin(QfCtrl *ctrl)
+// Start of a step for every member (single thread; batch is small).  In graph mode it also arms the WHILE node.
+__global__ void k_step_begin(QfCtrl *ctrl, int batch, cudaGraphConditionalHandle cond, int use_cond)
 {
-    QfCtrl &c = ctrl[blockIdx.x];
-    c.it = 0;
-    c.resnorm = INFINITY;          // isospectral.py:470
-    c.active = c.nonfinite ? 0 : 1;
+    unsigned any = 0;
+    for (int b = 0; b < batch; ++b) {
+        QfCtrl &c = ctrl[b];
+        c.it = 0;
+        c.resnorm = INFINITY;          // isospectral.py:470
+        c.active = c.nonfinite ? 0 : 1;
+        any |= (unsigned)c.active;
+    }
+    if (use_cond) cudaGraphSetConditional(cond, any);
+}
+
+// End of the loop body in graph mode: keep iterating while any member is still active.
+__global__ void k_loop_cond(const QfCtrl *ctrl, int batch, cudaGraphConditionalHandle cond)
+{
+    unsigned any = 0;
+    for (int b = 0; b < batch; ++b) any |= (unsigned)ctrl[b].active;
+    cudaGraphSetConditional(cond, any);
 }
 
 // zero dW of the members that are still alive (reinitialize=True, isospectral.py:471-472)
@@ -328,6 +343,139 @@ int qf_enqueue_update(qf_handle_s *h, double2 *W, bool compsum, cudaStream_t st)
     return QF_OK;
 }
 
+// ------------------------------------------------------------------------------- step graph
+// One CUDA graph per step:  k_step_begin -> [k_zero] -> WHILE(any member active) { one fixed-point iteration } -> k_update.
+// The WHILE node is a CUDA conditional node whose handle is set on the device (k_step_begin / k_loop_cond), so the
+// number of iterations is decided by the GPU and no launch is wasted on iterations after convergence.
+struct QfStepGraph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphConditionalHandle cond = 0;
+    // key
+    const void *W = nullptr;
+    double eps = 0.0;
+    int maxit = 0, minit = 0, compsum = 0, reinit = 0, nranks = 0, rank = 0;
+    const void *iters = nullptr;
+    int steps_cap = 0;
+    const void *kahan = nullptr;
+    int kernels_per_iter = 0, kernels_per_step = 0;
+};
+
+static void free_step_graph(QfStepGraph *g)
+{
+    if (!g) return;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+}
+
+void qf_graph_destroy(qf_handle_s *h)
+{
+    free_step_graph(reinterpret_cast<QfStepGraph *>(h->step_graph));
+    h->step_graph = nullptr;
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    h->cap_stream = nullptr;
+}
+
+template <typename... Args>
+static cudaError_t add_kernel_node(cudaGraphNode_t *node, cudaGraph_t graph, const cudaGraphNode_t *deps, size_t ndeps,
+                                   void *func, dim3 grid, dim3 block, Args... args)
+{
+    void *argv[] = {(void *)&args...};
+    cudaKernelNodeParams p = {};
+    p.func = func;
+    p.gridDim = grid;
+    p.blockDim = block;
+    p.sharedMemBytes = 0;
+    p.kernelParams = argv;
+    p.extra = nullptr;
+    return cudaGraphAddKernelNode(node, graph, deps, ndeps, &p);
+}
+
+static int build_step_graph(qf_handle_s *h, double2 *W, double eps, int maxit, int minit, bool compsum, bool reinit,
+                            QfStepGraph **out)
+{
+    QfStepGraph *old = reinterpret_cast<QfStepGraph *>(h->step_graph);
+    if (old && old->W == W && old->eps == eps && old->maxit == maxit && old->minit == minit && old->compsum == (int)compsum &&
+        old->reinit == (int)reinit && old->nranks == h->nranks && old->rank == h->rank && old->iters == h->iters_dev &&
+        old->steps_cap == h->steps_cap && old->kahan == h->kahan_c) {
+        *out = old;
+        return QF_OK;
+    }
+    free_step_graph(old);
+    h->step_graph = nullptr;
+    if (!h->cap_stream) QF_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+
+    const int N = h->N, B = h->batch;
+    const size_t n2 = h->mat_elems;
+    QfStepGraph *g = new QfStepGraph();
+    g->W = W; g->eps = eps; g->maxit = maxit; g->minit = minit; g->compsum = compsum; g->reinit = reinit;
+    g->nranks = h->nranks; g->rank = h->rank; g->iters = h->iters_dev; g->steps_cap = h->steps_cap; g->kahan = h->kahan_c;
+#define QF_G(call)                                                                                \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            qf_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            free_step_graph(g);                                                                   \
+            return QF_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+    QF_G(cudaGraphCreate(&g->graph, 0));
+    QF_G(cudaGraphConditionalHandleCreate(&g->cond, g->graph, 1, cudaGraphCondAssignDefault));
+
+    cudaGraphNode_t n_begin, n_zero, n_while, n_update, last;
+    QfCtrl *ctrl = h->ctrl;
+    int use_cond = 1;
+    QF_G(add_kernel_node(&n_begin, g->graph, nullptr, 0, (void *)k_step_begin, dim3(1), dim3(1), ctrl, B, g->cond, use_cond));
+    last = n_begin;
+    g->kernels_per_step = 2;
+    if (reinit) {
+        const dim3 gz((unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)h->sm_count * 8), B);
+        double2 *dW = h->dW;
+        size_t n2v = n2;
+        const QfCtrl *cc = h->ctrl;
+        QF_G(add_kernel_node(&n_zero, g->graph, &last, 1, (void *)k_zero, gz, dim3(256), dW, n2v, cc));
+        last = n_zero;
+        g->kernels_per_step = 3;
+    }
+    cudaGraphNodeParams wp = {};
+    wp.type = cudaGraphNodeTypeConditional;
+    wp.conditional.handle = g->cond;
+    wp.conditional.type = cudaGraphCondTypeWhile;
+    wp.conditional.size = 1;
+    QF_G(cudaGraphAddNode(&n_while, g->graph, &last, 1, &wp));
+    cudaGraph_t body = wp.conditional.phGraph_out[0];
+
+    // loop body by stream capture (the launchers below are the same ones the eager path uses)
+    const long long l0 = h->launches;
+    QF_G(cudaStreamBeginCaptureToGraph(h->cap_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    int rc = qf_enqueue_iteration(h, W, eps, maxit, minit, h->cap_stream, nullptr);
+    if (rc == QF_OK) {
+        k_loop_cond<<<1, 1, 0, h->cap_stream>>>(h->ctrl, B, g->cond);
+        h->launches++;
+    }
+    cudaGraph_t captured = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &captured);
+    g->kernels_per_iter = (int)(h->launches - l0);
+    h->launches = l0;
+    if (rc != QF_OK) { free_step_graph(g); return rc; }
+    QF_G(ce);
+
+    const int nb = (N + TS - 1) / TS;
+    const dim3 gu(nb, nb, B);
+    const double2 *Ap = h->A;
+    double2 *Kp = h->kahan_c;
+    int32_t *iters = h->iters_dev;
+    int steps_cap = h->steps_cap, hb = qf_block_rows(N, h->nranks), G = h->nranks, Nv = N;
+    void *upd = compsum ? (void *)k_update<true> : (void *)k_update<false>;
+    QF_G(add_kernel_node(&n_update, g->graph, &n_while, 1, upd, gu, dim3(256), Ap, W, Kp, Nv, ctrl, iters, steps_cap, hb, G));
+    QF_G(cudaGraphInstantiate(&g->exec, g->graph, 0));
+#undef QF_G
+    h->step_graph = g;
+    *out = g;
+    return QF_OK;
+}
+
 extern "C" int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double tol, int maxit, int minit, unsigned flags,
                         qf_stats *stats, int32_t *iters_per_step, void *stream)
 {
@@ -363,15 +511,32 @@ extern "C" int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double
     h->launches++;
 
     const dim3 gz((unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)h->sm_count * 8), B);
-    for (int k = 0; k < steps; ++k) {
-        k_step_begin<<<B, 1, 0, st>>>(h->ctrl);
-        h->launches++;
-        if (reinit) {
-            k_zero<<<gz, 256, 0, st>>>(h->dW, n2, h->ctrl);
-            h->launches++;
+    QfStepGraph *sg = nullptr;
+    if (h->use_graph && steps > 0) {
+        // prepare everything that allocates (tile lists) before capturing
+        const bool real_comm = (h->nranks > 1 && h->nccl_comm != nullptr);
+        QF_CHECK(qf_gemm_prepare(h, real_comm ? h->rank : -1, h->nranks));
+        int rc = build_step_graph(h, W, eps, maxit, minit, compsum, reinit, &sg);
+        if (rc != QF_OK) {
+            if (!h->graph_warned) fprintf(stderr, "quflow_b200: step graph unavailable (%s); using eager launches\n", qf_last_error());
+            h->graph_warned = 1;
+            h->use_graph = 0;
+            sg = nullptr;
         }
-        for (int i = 0; i < maxit; ++i) QF_CHECK(qf_enqueue_iteration(h, W, eps, maxit, minit, st, nullptr));
-        QF_CHECK(qf_enqueue_update(h, W, compsum, st));
+    }
+    if (sg) {
+        for (int k = 0; k < steps; ++k) QF_CUDA(cudaGraphLaunch(sg->exec, st));
+    } else {
+        for (int k = 0; k < steps; ++k) {
+            k_step_begin<<<1, 1, 0, st>>>(h->ctrl, B, 0, 0);
+            h->launches++;
+            if (reinit) {
+                k_zero<<<gz, 256, 0, st>>>(h->dW, n2, h->ctrl);
+                h->launches++;
+            }
+            for (int i = 0; i < maxit; ++i) QF_CHECK(qf_enqueue_iteration(h, W, eps, maxit, minit, st, nullptr));
+            QF_CHECK(qf_enqueue_update(h, W, compsum, st));
+        }
     }
     QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl) * B, cudaMemcpyDeviceToHost, st));
     if (iters_per_step && steps > 0) {
@@ -379,6 +544,12 @@ extern "C" int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double
                                   sizeof(int32_t) * steps, B, cudaMemcpyDeviceToHost, st));
     }
     QF_CUDA(cudaStreamSynchronize(st));
+    if (sg) {
+        long long max_it = 0;
+        for (int b = 0; b < B; ++b) max_it = std::max(max_it, (long long)h->ctrl_host[b].total_it);
+        // kernels actually executed by the graphs: per step begin/update (+zero), per executed loop pass the body
+        h->launches += (long long)steps * sg->kernels_per_step + (B == 1 ? max_it : max_it) * sg->kernels_per_iter;
+    }
     int rc = QF_OK;
     for (int b = 0; b < B; ++b) {
         const QfCtrl &c = h->ctrl_host[b];
@@ -415,7 +586,7 @@ extern "C" int qf_profile_iteration(qf_handle_t h, const void *W_dev, double dt,
     k_call_begin<<<B, 1, 0, st>>>(h->ctrl, 0.0, 0.0);   // tol = 0: never converges by tolerance
     float acc[5] = {0, 0, 0, 0, 0};
     for (int r = -1; r < reps; ++r) {   // r = -1: warm-up
-        k_step_begin<<<B, 1, 0, st>>>(h->ctrl);
+        k_step_begin<<<1, 1, 0, st>>>(h->ctrl, B, 0, 0);
         QF_CHECK(qf_enqueue_iteration(h, h->io, eps, 1 << 30, 1 << 30, st, ev));
         QF_CUDA(cudaEventRecord(ev[5], st));
         QF_CHECK(qf_enqueue_update(h, h->io, false, st));

@@ -86,6 +86,11 @@ struct qf_handle_s {
     void *nccl_comm = nullptr;
     int rank = 0, nranks = 1;     // nranks > 1 with nccl_comm == nullptr: all ranks emulated on this GPU (tests)
     QfGemmPlan *gemm = nullptr;
+    // CUDA-graph execution of a step (isomp.cu)
+    void *step_graph = nullptr;
+    cudaStream_t cap_stream = nullptr;
+    int use_graph = 1;
+    int graph_warned = 0;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -124,6 +129,8 @@ __host__ __device__ __forceinline__ int qf_prow(int i, int hb, int G)
     return (2 * r + slot) * hb + (i - blk * hb);
 }
 int qf_comm_allgather_rows(qf_handle_s *h, double2 *M, cudaStream_t st);   // comm.cu
+int qf_gemm_prepare(qf_handle_s *h, int rank, int nranks);                  // zgemm.cu: build tile lists (allocates)
+void qf_graph_destroy(qf_handle_s *h);                                      // isomp.cu
 
 // isomp.cu
 int qf_launch_norm_inf(qf_handle_s *h, const double2 *W, cudaStream_t st);   // -> ctrl[b].norm0

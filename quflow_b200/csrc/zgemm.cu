@@ -378,6 +378,15 @@ static int get_tile_list(qf_handle_s *h, bool upper_only, int rank, int nranks, 
     return QF_OK;
 }
 
+int qf_gemm_prepare(qf_handle_s *h, int rank, int nranks)
+{
+    const SkTile *t;
+    int n;
+    QF_CHECK(get_tile_list(h, false, rank, nranks, false, &t, &n));
+    QF_CHECK(get_tile_list(h, true, rank, nranks, true, &t, &n));
+    return QF_OK;
+}
+
 // rank/nranks select the row blocks (see qf_prow); rank < 0 computes every rank's blocks (emulation on one GPU).
 int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 *C, bool upper_only, bool gated,
                     int rank, int nranks, bool a_permuted, cudaStream_t st)
