@@ -135,6 +135,12 @@ int qf_profile_iteration(qf_handle_t h, const void *W_dev, double dt, int reps, 
 #define QF_UNIQUE_ID_BYTES 128
 int qf_comm_get_unique_id(void *id_out);
 int qf_comm_init(qf_handle_t h, const void *unique_id, int rank, int nranks);
+/* Peer-memory data path (default): every rank exports a blob of CUDA IPC handles (its A/S buffers and flag array),
+ * the host side all-gathers the blobs (torch.distributed) and every rank imports all of them.  The per-iteration
+ * all-gathers then run as plain kernels that pull the peers' row blocks over NVLink, inside the step graph. */
+#define QF_P2P_BLOB_BYTES 256
+int qf_comm_p2p_export(qf_handle_t h, void *blob_out /* QF_P2P_BLOB_BYTES */);
+int qf_comm_p2p_import(qf_handle_t h, const void *blobs /* nranks * QF_P2P_BLOB_BYTES */, int rank, int nranks);
 /* Test hook: run the row-sharded data path for `nranks` ranks on ONE GPU (all ranks' tiles, no communication). */
 int qf_set_emulated_ranks(qf_handle_t h, int nranks);
 

@@ -24,6 +24,7 @@ QF_ERR_UNSUPPORTED = -5
 QF_FLAG_COMPSUM = 1
 QF_FLAG_REINITIALIZE = 2
 QF_UNIQUE_ID_BYTES = 128
+QF_P2P_BLOB_BYTES = 256
 
 
 class QfError(RuntimeError):
@@ -68,6 +69,8 @@ SYMBOLS = {
     "qf_comm_get_unique_id": (_i, [_vp]),
     "qf_comm_init": (_i, [_vp, _vp, _i, _i]),
     "qf_set_emulated_ranks": (_i, [_vp, _i]),
+    "qf_comm_p2p_export": (_i, [_vp, _vp]),
+    "qf_comm_p2p_import": (_i, [_vp, _vp, _i, _i]),
 }
 
 
@@ -229,6 +232,16 @@ class Handle:
     # -- multi-GPU -----------------------------------------------------------------------
     def set_emulated_ranks(self, nranks: int):
         _check(self._lib.qf_set_emulated_ranks(self._h, int(nranks)))
+
+    def p2p_export(self) -> bytes:
+        buf = ctypes.create_string_buffer(QF_P2P_BLOB_BYTES)
+        _check(self._lib.qf_comm_p2p_export(self._h, buf))
+        return buf.raw
+
+    def p2p_import(self, blobs, rank: int, nranks: int):
+        raw = b"".join(blobs)
+        assert len(raw) == nranks * QF_P2P_BLOB_BYTES
+        _check(self._lib.qf_comm_p2p_import(self._h, ctypes.create_string_buffer(raw, len(raw)), int(rank), int(nranks)))
 
     def comm_init(self, unique_id: bytes, rank: int, nranks: int):
         buf = ctypes.create_string_buffer(unique_id, QF_UNIQUE_ID_BYTES)

@@ -38,12 +38,15 @@ extern "C" int qf_comm_init(qf_handle_t h, const void *unique_id, int rank, int 
     if (h->nccl_comm) { ncclCommDestroy((ncclComm_t)h->nccl_comm); h->nccl_comm = nullptr; }
     h->rank = rank;
     h->nranks = nranks;
+    h->comm_mode = 0;
     if (nranks == 1) return QF_OK;
     ncclUniqueId id;
     memcpy(&id, unique_id, sizeof(id));
     ncclComm_t comm;
     QF_NCCL(ncclCommInitRank(&comm, nranks, id, rank));
     h->nccl_comm = comm;
+    h->comm_mode = 1;
+    h->use_graph = 0;   // NCCL nodes are not allowed inside a conditional (WHILE) graph body
     return QF_OK;
 }
 
@@ -69,11 +72,157 @@ int qf_comm_allgather_rows(qf_handle_s *, double2 *, cudaStream_t) { qf_set_erro
 void qf_comm_destroy(qf_handle_s *) {}
 #endif
 
+// ---------------------------------------------------------------------------------------
+// Peer-memory all-gather over NVLink (default data path for the row-sharded GEMM outputs).
+//
+// NCCL cannot live inside the body of a CUDA conditional (WHILE) node and cannot be gated by a device flag, so the
+// per-iteration gathers are done by a plain kernel that PULLS the peers' row blocks through P2P-mapped memory
+// (cudaIpc handles exchanged once by the host side).  Synchronisation is a monotone sequence number per source
+// rank written into every peer's flag array: a rank signals "my rows of gather #seq are complete" at the start of
+// its gather kernel (its GEMM finished earlier on the same stream) and every CTA waits until all sources reached
+// seq before copying.  Write-after-read safety needs no extra handshake: a rank can only start overwriting its
+// rows of A in iteration i+1 after it passed the S gather of iteration i, which required every peer's "S ready"
+// signal, which each peer raises only after its own A gather of iteration i has finished (stream order); the same
+// chain protects S.
+// ---------------------------------------------------------------------------------------
+struct QfP2P {
+    int nranks = 0, rank = 0;
+    unsigned long long *flags = nullptr;               // [MAXR] local, written by peers
+    double2 *peerA[QF_MAX_RANKS] = {}, *peerS[QF_MAX_RANKS] = {};
+    unsigned long long *peerFlags[QF_MAX_RANKS] = {};
+    // device copies of the pointer tables
+    double2 **peerA_dev = nullptr, **peerS_dev = nullptr;
+    unsigned long long **peerFlags_dev = nullptr;
+};
+
+struct QfP2PBlob {
+    cudaIpcMemHandle_t A, S, flags;
+};
+static_assert(sizeof(QfP2PBlob) <= QF_P2P_BLOB_BYTES, "blob too large");
+
+extern "C" int qf_comm_p2p_export(qf_handle_t h, void *blob_out)
+{
+    if (!h || !blob_out) { qf_set_error("qf_comm_p2p_export: null"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
+    if (!p) {
+        p = new QfP2P();
+        h->p2p = p;
+        QF_CUDA(cudaMalloc(&p->flags, sizeof(unsigned long long) * QF_MAX_RANKS));
+        QF_CUDA(cudaMemset(p->flags, 0, sizeof(unsigned long long) * QF_MAX_RANKS));
+    }
+    QfP2PBlob b;
+    memset(&b, 0, sizeof(b));
+    QF_CUDA(cudaIpcGetMemHandle(&b.A, h->A));
+    QF_CUDA(cudaIpcGetMemHandle(&b.S, h->S));
+    QF_CUDA(cudaIpcGetMemHandle(&b.flags, p->flags));
+    memset(blob_out, 0, QF_P2P_BLOB_BYTES);
+    memcpy(blob_out, &b, sizeof(b));
+    return QF_OK;
+}
+
+extern "C" int qf_comm_p2p_import(qf_handle_t h, const void *blobs, int rank, int nranks)
+{
+    if (!h || !blobs || nranks < 1 || nranks > QF_MAX_RANKS || rank < 0 || rank >= nranks) { qf_set_error("qf_comm_p2p_import: bad arguments"); return QF_ERR_INVALID; }
+    if (h->batch != 1) { qf_set_error("row sharding needs batch == 1"); return QF_ERR_INVALID; }
+    if (nranks > 1 && h->N % (2 * nranks) != 0) { qf_set_error("row sharding needs N divisible by 2*nranks (N=%d, nranks=%d)", h->N, nranks); return QF_ERR_INVALID; }
+    QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
+    if (!p) { qf_set_error("qf_comm_p2p_import: call qf_comm_p2p_export first"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    p->nranks = nranks;
+    p->rank = rank;
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) {
+            p->peerA[r] = h->A;
+            p->peerS[r] = h->S;
+            p->peerFlags[r] = p->flags;
+            continue;
+        }
+        QfP2PBlob b;
+        memcpy(&b, (const char *)blobs + (size_t)r * QF_P2P_BLOB_BYTES, sizeof(b));
+        QF_CUDA(cudaIpcOpenMemHandle((void **)&p->peerA[r], b.A, cudaIpcMemLazyEnablePeerAccess));
+        QF_CUDA(cudaIpcOpenMemHandle((void **)&p->peerS[r], b.S, cudaIpcMemLazyEnablePeerAccess));
+        QF_CUDA(cudaIpcOpenMemHandle((void **)&p->peerFlags[r], b.flags, cudaIpcMemLazyEnablePeerAccess));
+    }
+    QF_CUDA(cudaMalloc(&p->peerA_dev, sizeof(void *) * QF_MAX_RANKS));
+    QF_CUDA(cudaMalloc(&p->peerS_dev, sizeof(void *) * QF_MAX_RANKS));
+    QF_CUDA(cudaMalloc(&p->peerFlags_dev, sizeof(void *) * QF_MAX_RANKS));
+    QF_CUDA(cudaMemcpy(p->peerA_dev, p->peerA, sizeof(void *) * QF_MAX_RANKS, cudaMemcpyHostToDevice));
+    QF_CUDA(cudaMemcpy(p->peerS_dev, p->peerS, sizeof(void *) * QF_MAX_RANKS, cudaMemcpyHostToDevice));
+    QF_CUDA(cudaMemcpy(p->peerFlags_dev, p->peerFlags, sizeof(void *) * QF_MAX_RANKS, cudaMemcpyHostToDevice));
+    h->rank = rank;
+    h->nranks = nranks;
+    h->comm_mode = (nranks > 1) ? 2 : 0;
+    return QF_OK;
+}
+
+void qf_p2p_destroy(qf_handle_s *h)
+{
+    QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
+    if (!p) return;
+    for (int r = 0; r < p->nranks; ++r) {
+        if (r == p->rank) continue;
+        if (p->peerA[r]) cudaIpcCloseMemHandle(p->peerA[r]);
+        if (p->peerS[r]) cudaIpcCloseMemHandle(p->peerS[r]);
+        if (p->peerFlags[r]) cudaIpcCloseMemHandle(p->peerFlags[r]);
+    }
+    if (p->peerA_dev) cudaFree(p->peerA_dev);
+    if (p->peerS_dev) cudaFree(p->peerS_dev);
+    if (p->peerFlags_dev) cudaFree(p->peerFlags_dev);
+    if (p->flags) cudaFree(p->flags);
+    delete p;
+    h->p2p = nullptr;
+}
+
+// kind 0: gather of A, kind 1: gather of S.  seq = 2 * gseq + kind + 1 is monotone over the life of the handle.
+__global__ void __launch_bounds__(256)
+k_p2p_allgather(double2 *const *__restrict__ peers, unsigned long long *const *__restrict__ peer_flags,
+                volatile unsigned long long *my_flags, int rank, int nranks, size_t elems_per_rank, int kind,
+                const QfCtrl *__restrict__ ctrl, int gated)
+{
+    if (gated && !ctrl[0].active) return;
+    const unsigned long long seq = 2ull * ctrl[0].gseq + (unsigned long long)kind + 1ull;
+    if (blockIdx.x == 0 && threadIdx.x < nranks && threadIdx.x != rank) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(peer_flags[threadIdx.x] + rank) = seq;   // "my rows are ready"
+    }
+    if (threadIdx.x == 0) {
+        for (int p = 0; p < nranks; ++p) {
+            if (p == rank) continue;
+            while (my_flags[p] < seq) __nanosleep(200);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    double2 *mine = peers[rank];
+    // pull every peer's contiguous row region; blocks stride over the concatenation of the (nranks - 1) regions
+    const size_t total = elems_per_rank * (size_t)(nranks - 1);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int q = (int)(i / elems_per_rank);
+        const int src = q < rank ? q : q + 1;
+        const size_t off = (size_t)src * elems_per_rank + (i - (size_t)q * elems_per_rank);
+        mine[off] = __ldcg(peers[src] + off);
+    }
+}
+
+int qf_comm_p2p_allgather(qf_handle_s *h, int kind, bool gated, cudaStream_t st)
+{
+    QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
+    const int hb = qf_block_rows(h->N, h->nranks);
+    const size_t elems = (size_t)2 * hb * h->N;
+    k_p2p_allgather<<<h->sm_count * 2, 256, 0, st>>>(kind == 0 ? p->peerA_dev : p->peerS_dev, p->peerFlags_dev, p->flags,
+                                                     h->rank, h->nranks, elems, kind, h->ctrl, gated ? 1 : 0);
+    h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
 // Single-GPU emulation of G ranks (tests): same tile lists, same permuted layout, no communication.
 extern "C" int qf_set_emulated_ranks(qf_handle_t h, int nranks)
 {
     if (!h || nranks < 1) { qf_set_error("qf_set_emulated_ranks: bad arguments"); return QF_ERR_INVALID; }
-    if (h->nccl_comm) { qf_set_error("qf_set_emulated_ranks: handle already has a communicator"); return QF_ERR_INVALID; }
+    if (h->comm_mode != 0) { qf_set_error("qf_set_emulated_ranks: handle already has a communicator"); return QF_ERR_INVALID; }
     if (h->batch != 1) { qf_set_error("row sharding needs batch == 1"); return QF_ERR_INVALID; }
     if (nranks > 1 && h->N % (2 * nranks) != 0) { qf_set_error("row sharding needs N divisible by 2*nranks"); return QF_ERR_INVALID; }
     h->rank = 0;

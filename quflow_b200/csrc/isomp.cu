@@ -186,6 +186,7 @@ k_control(const double *__restrict__ rowpart, int N, int nslots, QfCtrl *ctrl, i
     const int nan_seen = isinf(best) ? 1 : 0;
     c.it += 1;                                   // isospectral.py:478
     c.total_it += 1;
+    c.gseq += 1;
     int active = 1;
     if (c.it >= minit) {                         // :523
         c.resnorm_old = c.resnorm;               // :525
@@ -306,17 +307,17 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
 {
     const int N = h->N;
     const int G = h->nranks;
-    const bool real_comm = (G > 1 && h->nccl_comm != nullptr);
+    const bool real_comm = (G > 1 && h->comm_mode != 0);
     const int my = real_comm ? h->rank : -1;          // -1: compute every rank's blocks here (single GPU / emulation)
     const int hb = qf_block_rows(N, G);
     if (ev) QF_CUDA(cudaEventRecord(ev[0], st));
     QF_CHECK(qf_launch_poisson(h, W, h->dW, h->Wh, h->P, eps, true, st));
     if (ev) QF_CUDA(cudaEventRecord(ev[1], st));
     QF_CHECK(qf_launch_zgemm(h, h->P, h->Wh, h->A, false, true, my, G, false, st));        // rows of A = P~ W~
-    if (real_comm) QF_CHECK(qf_comm_allgather_rows(h, h->A, st));
+    if (real_comm) QF_CHECK(h->comm_mode == 2 ? qf_comm_p2p_allgather(h, 0, true, st) : qf_comm_allgather_rows(h, h->A, st));
     if (ev) QF_CUDA(cudaEventRecord(ev[2], st));
     QF_CHECK(qf_launch_zgemm(h, h->A, h->P, h->S, true, true, my, G, true, st));          // rows of S = A P~ (A rows are local)
-    if (real_comm) QF_CHECK(qf_comm_allgather_rows(h, h->S, st));
+    if (real_comm) QF_CHECK(h->comm_mode == 2 ? qf_comm_p2p_allgather(h, 1, true, st) : qf_comm_allgather_rows(h, h->S, st));
     if (ev) QF_CUDA(cudaEventRecord(ev[3], st));
     const int nb = (N + TS - 1) / TS;
     dim3 g(nb, nb, h->batch);
@@ -514,7 +515,7 @@ extern "C" int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double
     QfStepGraph *sg = nullptr;
     if (h->use_graph && steps > 0) {
         // prepare everything that allocates (tile lists) before capturing
-        const bool real_comm = (h->nranks > 1 && h->nccl_comm != nullptr);
+        const bool real_comm = (h->nranks > 1 && h->comm_mode != 0);
         QF_CHECK(qf_gemm_prepare(h, real_comm ? h->rank : -1, h->nranks));
         int rc = build_step_graph(h, W, eps, maxit, minit, compsum, reinit, &sg);
         if (rc != QF_OK) {
@@ -522,6 +523,7 @@ extern "C" int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double
             h->graph_warned = 1;
             h->use_graph = 0;
             sg = nullptr;
+            cudaGetLastError();   // clear the error state left by the failed instantiation
         }
     }
     if (sg) {

@@ -37,6 +37,7 @@ struct QfCtrl {
     double norm0;         // ||W||_inf at call start (tol = factor * norm0)
     long long total_it;
     long long n_maxit;
+    unsigned long long gseq;          // executed iterations over the life of the handle (never reset)
     unsigned long long resmax_bits;   // running max of residual row sums (bit pattern of a non-negative double)
     unsigned int ticket;              // blocks of k_control that have finished
     int active;           // 1 while the fixed-point loop of the current step runs
@@ -56,6 +57,7 @@ __device__ __forceinline__ double zabs(double2 a) { return hypot(a.x, a.y); }
 // the handle
 // ---------------------------------------------------------------------------------------
 struct QfGemmPlan;   // zgemm.cu
+#define QF_MAX_RANKS 16
 
 struct qf_handle_s {
     int N = 0;
@@ -84,6 +86,8 @@ struct qf_handle_s {
     long long launches = 0;
     // multi-GPU
     void *nccl_comm = nullptr;
+    void *p2p = nullptr;          // QfP2P (comm.cu)
+    int comm_mode = 0;            // 0: none / emulated, 1: NCCL all-gather (eager only), 2: peer-memory pull kernel
     int rank = 0, nranks = 1;     // nranks > 1 with nccl_comm == nullptr: all ranks emulated on this GPU (tests)
     QfGemmPlan *gemm = nullptr;
     // CUDA-graph execution of a step (isomp.cu)
@@ -129,6 +133,8 @@ __host__ __device__ __forceinline__ int qf_prow(int i, int hb, int G)
     return (2 * r + slot) * hb + (i - blk * hb);
 }
 int qf_comm_allgather_rows(qf_handle_s *h, double2 *M, cudaStream_t st);   // comm.cu
+int qf_comm_p2p_allgather(qf_handle_s *h, int kind, bool gated, cudaStream_t st);   // comm.cu
+void qf_p2p_destroy(qf_handle_s *h);
 int qf_gemm_prepare(qf_handle_s *h, int rank, int nranks);                  // zgemm.cu: build tile lists (allocates)
 void qf_graph_destroy(qf_handle_s *h);                                      // isomp.cu
 

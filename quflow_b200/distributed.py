@@ -49,14 +49,28 @@ def broadcast_unique_id(dist, make_id=None) -> bytes:
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def attach_row_sharding(handle, dist):
-    """Make ``handle`` (batch == 1) run its GEMMs row-sharded over the default process group."""
+def attach_row_sharding(handle, dist, mode=None):
+    """Make ``handle`` (batch == 1) run its GEMMs row-sharded over the default process group.
+
+    mode "p2p" (default): peer-memory pull kernels over NVLink inside the step graph — torch.distributed (NCCL
+    backend) only all-gathers one 256-byte blob of CUDA IPC handles per rank.
+    mode "nccl": one in-place ncclAllGather per GEMM, issued by the library on the compute stream (eager launches;
+    NCCL cannot run inside the conditional graph body).  Select with QF_COMM=nccl.
+    """
+    import os
     world, rank = dist.get_world_size(), dist.get_rank()
     if world == 1:
         return handle
     row_blocks(handle.N, world)     # validates divisibility with a Python-level error
-    uid = broadcast_unique_id(dist)
-    handle.comm_init(uid, rank, world)
+    mode = mode or os.environ.get("QF_COMM", "p2p")
+    if mode == "nccl":
+        uid = broadcast_unique_id(dist)
+        handle.comm_init(uid, rank, world)
+    else:
+        blobs = [None] * world
+        dist.all_gather_object(blobs, handle.p2p_export())
+        handle.p2p_import(blobs, rank, world)
+        dist.barrier()              # every rank has mapped every peer before anybody starts signalling
     return handle
 
 

@@ -21,14 +21,14 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for N, steps in ((256, 10), (1024, 6)):
+    for N, steps, mode in ((256, 10, "p2p"), (256, 10, "nccl"), (1024, 6, "p2p")):
         W0 = oracle.random_skewherm(N, 42)
         dt = 0.25 * qf.hbar(N)
         solo = Handle(N, 1, local)
         Ws = W0.copy()
         rs, its_s = solo.isomp(Ws, dt, steps, want_iters=True)
         shard = Handle(N, 1, local)
-        attach_row_sharding(shard, dist)
+        attach_row_sharding(shard, dist, mode=mode)
         Wd = torch.from_numpy(W0).cuda()
         rd, its_d = shard.isomp(Wd, dt, steps, want_iters=True)
         Wm = Wd.cpu().numpy()
@@ -38,7 +38,7 @@ def main():
         gathered = [None] * world
         dist.all_gather_object(gathered, Wm.tobytes())
         identical = all(g == gathered[0] for g in gathered)
-        msg = f"rank {rank}: N={N} sharded-vs-solo rel.err={err:.2e} iterations equal={same_its} ranks identical={identical}"
+        msg = f"rank {rank}: N={N} mode={mode} sharded-vs-solo rel.err={err:.2e} iterations equal={same_its} ranks identical={identical}"
         if N <= 256:
             rec = {}
             Wref = oracle.isomp(W0.copy(), dt, steps, record=rec)
@@ -47,7 +47,9 @@ def main():
             ok = ok and eo < 1e-12 and list(its_d[0]) == rec["iterations"]
         print(msg, flush=True)
         ok = ok and err < 1e-13 and same_its and identical
+        dist.barrier()
         solo.close(); shard.close()
+        dist.barrier()
     # ensemble sharded per member: no collective on the data path
     k, N = 6, 64
     W0 = np.stack([oracle.random_skewherm(N, s) for s in range(k)])
