@@ -12,6 +12,8 @@
 // is stored at chunk c ^ (r & 7)); one LDS.128 per fragment delivers (re, im) of one complex element.
 // The K index inside an MMA is permuted (lane%4 = t uses k = 2t + s) so that the eight lanes of every
 // quarter-warp hit eight different chunks: all fragment loads are bank-conflict free.
+#include <cuda.h>
+
 #include <algorithm>
 #include <stdlib.h>
 #include <string.h>
@@ -57,6 +59,33 @@ __device__ __forceinline__ double2 lds128(uint32_t addr)
     return v;
 }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier primitives ---------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(phase)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
+
 // Load one K tile (k0 .. k0+15) of the A panel (rows row0 .. row0+127) and of the B panel (cols col0 .. col0+63).
 __device__ __forceinline__ void load_stage(uint32_t sA, uint32_t sB, const double2 *__restrict__ A,
                                            const double2 *__restrict__ B, int N, int row0, int row_end, int col0, int k0,
@@ -84,6 +113,57 @@ __device__ __forceinline__ void load_stage(uint32_t sA, uint32_t sB, const doubl
     }
 }
 
+// 64 DMMAs x 4 k-steps on one resident stage.
+__device__ __forceinline__ void gemm_compute_stage(double (&acc_re)[4][4][2], double (&acc_im)[4][4][2], uint32_t sb,
+                                                   const uint32_t (&a_off)[2], const uint32_t (&b_off)[2])
+{
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            double a_re[4], a_im[4], a_in[4], b_re[4], b_im[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double2 v = lds128(sb + a_off[s] + hh * (BM * 128) + i * 1024);
+                a_re[i] = v.x;
+                a_im[i] = v.y;
+                a_in[i] = flip_sign(v.y);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double2 v = lds128(sb + b_off[s] + hh * 1024 + j * (BK * 128));
+                b_re[j] = v.x;
+                b_im[j] = v.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dmma884(acc_re[i][j][0], acc_re[i][j][1], a_re[i], b_re[j]);
+                    dmma884(acc_im[i][j][0], acc_im[i][j][1], a_re[i], b_im[j]);
+                }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dmma884(acc_re[i][j][0], acc_re[i][j][1], a_in[i], b_im[j]);
+                    dmma884(acc_im[i][j][0], acc_im[i][j][1], a_im[i], b_re[j]);
+                }
+        }
+    }
+}
+
+__device__ __forceinline__ void gemm_frag_offsets(uint32_t (&a_off)[2], uint32_t (&b_off)[2], int wm, int wn, int g, int t)
+{
+    // per-thread fragment base offsets inside a stage (see file header for the k permutation)
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int kk = 2 * t + s;
+        a_off[s] = (wm * 32 + g) * 128 + ((kk ^ g) << 4);
+        b_off[s] = A_STAGE_BYTES + wn * 4 * (BK * 128) + kk * 128 + ((g ^ kk) << 4);
+    }
+}
+
 // Accumulate k-tiles [kt_begin, kt_end) of the (row0, col0) tile into acc (cp.async 3-stage pipeline).
 __device__ __forceinline__ void gemm_mainloop(double (&acc_re)[4][4][2], double (&acc_im)[4][4][2], uint32_t smem_base,
                                               const double2 *__restrict__ A, const double2 *__restrict__ B, int N, int row0,
@@ -97,14 +177,8 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc_re)[4][4][2], double 
                        (kt_begin + s) * BK, tid);
         cp_async_commit();
     }
-    // per-thread fragment base offsets inside a stage (see file header for the k permutation)
     uint32_t a_off[2], b_off[2];
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        const int kk = 2 * t + s;
-        a_off[s] = (wm * 32 + g) * 128 + ((kk ^ g) << 4);
-        b_off[s] = A_STAGE_BYTES + wn * 4 * (BK * 128) + kk * 128 + ((g ^ kk) << 4);
-    }
+    gemm_frag_offsets(a_off, b_off, wm, wn, g, t);
     for (int kt = 0; kt < nkt; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -116,44 +190,50 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc_re)[4][4][2], double 
             }
             cp_async_commit();
         }
-        const uint32_t sb = smem_base + (kt % STAGES) * STAGE_BYTES;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                double a_re[4], a_im[4], a_in[4], b_re[4], b_im[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const double2 v = lds128(sb + a_off[s] + hh * (BM * 128) + i * 1024);
-                    a_re[i] = v.x;
-                    a_im[i] = v.y;
-                    a_in[i] = flip_sign(v.y);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double2 v = lds128(sb + b_off[s] + hh * 1024 + j * (BK * 128));
-                    b_re[j] = v.x;
-                    b_im[j] = v.y;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        dmma884(acc_re[i][j][0], acc_re[i][j][1], a_re[i], b_re[j]);
-                        dmma884(acc_im[i][j][0], acc_im[i][j][1], a_re[i], b_im[j]);
-                    }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        dmma884(acc_re[i][j][0], acc_re[i][j][1], a_in[i], b_im[j]);
-                        dmma884(acc_im[i][j][0], acc_im[i][j][1], a_im[i], b_re[j]);
-                    }
-            }
-        }
+        gemm_compute_stage(acc_re, acc_im, smem_base + (kt % STAGES) * STAGE_BYTES, a_off, b_off);
     }
     cp_async_wait<0>();
     __syncthreads();   // all warps are done with shared memory: the next segment may refill it
+}
+
+// Same main loop fed by TMA: one elected thread issues 2 (A) + 8 (B) cp.async.bulk.tensor boxes of 128-byte rows per
+// stage into the SWIZZLE_128B layout; completion is tracked by one mbarrier per stage (expect_tx = 48 KiB).
+// `gk` counts the k-tiles this CTA has consumed since kernel start: stage = gk % STAGES, phase = (gk / STAGES) & 1.
+__device__ __forceinline__ void gemm_mainloop_tma(double (&acc_re)[4][4][2], double (&acc_im)[4][4][2], uint32_t smem_base,
+                                                  uint32_t bars, const CUtensorMap *tmA, const CUtensorMap *tmB, int member,
+                                                  int a_mem_row0, int col0, int kt_begin, int kt_end, uint32_t &gk, int tid,
+                                                  int wm, int wn, int g, int t)
+{
+    const int nkt = kt_end - kt_begin;
+    auto issue = [&](int i) {
+        const uint32_t idx = gk + (uint32_t)i;
+        const uint32_t stage = idx % STAGES;
+        const uint32_t sb = smem_base + stage * STAGE_BYTES;
+        const uint32_t bar = bars + 8 * stage;
+        const int k0 = (kt_begin + i) * BK;
+        mbar_arrive_expect_tx(bar, STAGE_BYTES);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) tma_load_3d(sb + hh * (BM * 128), tmA, 2 * (k0 + 8 * hh), a_mem_row0, member, bar);
+#pragma unroll
+        for (int c = 0; c < BN / 8; ++c) tma_load_3d(sb + A_STAGE_BYTES + c * (BK * 128), tmB, 2 * (col0 + 8 * c), k0, member, bar);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s)
+            if (s < nkt) issue(s);
+    }
+    uint32_t a_off[2], b_off[2];
+    gemm_frag_offsets(a_off, b_off, wm, wn, g, t);
+    for (int kt = 0; kt < nkt; ++kt) {
+        const uint32_t idx = gk + (uint32_t)kt;
+        const uint32_t stage = idx % STAGES;
+        __syncthreads();   // every warp finished k-tile kt-1: its stage may be refilled
+        if (tid == 0 && kt + STAGES - 1 < nkt) issue(kt + STAGES - 1);
+        mbar_wait(bars + 8 * stage, (idx / STAGES) & 1);
+        gemm_compute_stage(acc_re, acc_im, smem_base + stage * STAGE_BYTES, a_off, b_off);
+    }
+    gk += (uint32_t)nkt;
+    __syncthreads();
 }
 
 // each thread owns, per 8x8 sub-tile, row g and the two adjacent columns 2t, 2t+1
@@ -217,13 +297,26 @@ k_zgemm(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, double2 
 // written to rows c_row0.. of C (C may use the rank-permuted row layout of the multi-GPU path, see qf_common.cuh).
 struct SkTile { int member, a_row0, c_row0, col0, row_end, op_row0, pad1, pad2; };   // op_row0: first row of the A operand in memory
 
+template <bool TMA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, double2 *__restrict__ Cg, int N,
            const SkTile *__restrict__ tiles, int ntiles, double2 *__restrict__ ws, int *__restrict__ flags,
-           const QfCtrl *__restrict__ ctrl, int gated)
+           const QfCtrl *__restrict__ ctrl, int gated, const __grid_constant__ CUtensorMap tmA,
+           const __grid_constant__ CUtensorMap tmB)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
+    __shared__ __align__(8) unsigned long long mbar_storage[STAGES];
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(mbar_storage);
+    uint32_t gk = 0;
+    if (TMA) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) mbar_init(bars + 8 * s, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int wm = warp >> 1, wn = warp & 1;
@@ -253,8 +346,11 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
             }
         // the A operand may itself be stored in the rank-permuted row layout (second GEMM): shift the base pointer so that
         // logical row a_row0 addresses memory row op_row0
-        gemm_mainloop(acc_re, acc_im, smem_base, Ag + moff + ((ptrdiff_t)ti.op_row0 - ti.a_row0) * N, Bg + moff, N, ti.a_row0, ti.row_end,
-                      ti.col0, ka, kb, tid, wm, wn, g, t);
+        if (TMA)
+            gemm_mainloop_tma(acc_re, acc_im, smem_base, bars, &tmA, &tmB, ti.member, ti.op_row0, ti.col0, ka, kb, gk, tid, wm, wn, g, t);
+        else
+            gemm_mainloop(acc_re, acc_im, smem_base, Ag + moff + ((ptrdiff_t)ti.op_row0 - ti.a_row0) * N, Bg + moff, N, ti.a_row0,
+                          ti.row_end, ti.col0, ka, kb, tid, wm, wn, g, t);
 
         if (ka > 0) {
             // contributor: park the partial tile in this CTA's slot ([reg][thread] layout: coalesced)
@@ -305,9 +401,15 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
 
 }   // namespace
 
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
 struct QfGemmPlan {
     int smem_bytes = 0;
     bool streamk = true;
+    bool tma = true;
+    PFN_tmapEncodeTiled encode = nullptr;
     int max_ctas = 0;
     double2 *ws = nullptr;      // [max_ctas][32][256] partial tiles
     int *flags = nullptr;       // [max_ctas]
@@ -325,7 +427,20 @@ int qf_gemm_create(qf_handle_s *h)
     p->streamk = !(env && strcmp(env, "tile") == 0);
     p->max_ctas = h->sm_count;
     QF_CUDA(cudaFuncSetAttribute(k_zgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    {
+        const char *ld = getenv("QF_GEMM_LOAD");
+        p->tma = !(ld && strcmp(ld, "cpasync") == 0);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+            qres != cudaDriverEntryPointSuccess) {
+            p->tma = false;   // no TMA descriptor encoder in this driver: keep the cp.async loader
+            cudaGetLastError();
+        }
+        p->encode = (PFN_tmapEncodeTiled)fn;
+    }
     QF_CUDA(cudaMalloc(&p->ws, sizeof(double2) * 32 * GEMM_THREADS * (size_t)p->max_ctas));
     QF_CUDA(cudaMalloc(&p->flags, sizeof(int) * p->max_ctas));
     QF_CUDA(cudaMemset(p->flags, 0, sizeof(int) * p->max_ctas));
@@ -340,6 +455,25 @@ void qf_gemm_destroy(qf_handle_s *h)
     if (h->gemm->flags) cudaFree(h->gemm->flags);
     delete h->gemm;
     h->gemm = nullptr;
+}
+
+// 3-D tensor map over `batch` row-major N x N complex128 matrices seen as doubles: dims {2N, N, batch}, box {16, rows, 1}
+// (= 8 complex = one 128-byte swizzle span per row), SWIZZLE_128B, out-of-bounds elements read as zero.
+static int make_tmap(qf_handle_s *h, const double2 *base, int box_rows, CUtensorMap *out)
+{
+    const cuuint64_t N = (cuuint64_t)h->N;
+    cuuint64_t dims[3] = {2 * N, N, (cuuint64_t)h->batch};
+    cuuint64_t strides[2] = {16 * N, 16 * N * N};
+    cuuint32_t box[3] = {16, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = h->gemm->encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double2 *>(base), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        qf_set_error("cuTensorMapEncodeTiled failed with CUresult %d (N=%d)", (int)r, h->N);
+        return QF_ERR_CUDA;
+    }
+    return QF_OK;
 }
 
 static int get_tile_list(qf_handle_s *h, bool upper_only, int rank, int nranks, bool a_permuted, const SkTile **dev, int *ntiles)
@@ -405,7 +539,17 @@ int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 
         if (ntiles == 0) return QF_OK;
         // at least 8 k-iterations per CTA so that the fix-up traffic stays small
         const int G = (int)std::min<long long>(p->max_ctas, std::max<long long>(1, T / 8));
-        k_zgemm_sk<<<G, GEMM_THREADS, GEMM_SMEM, st>>>(A, B, C, N, tiles, ntiles, p->ws, p->flags, h->ctrl, gated ? 1 : 0);
+        // TMA needs 16-byte aligned rows (always true) and N >= 8 so that a 128-byte box fits the row pitch
+        if (p->tma && N >= 8) {
+            CUtensorMap tmA, tmB;
+            QF_CHECK(make_tmap(h, A, BM, &tmA));
+            QF_CHECK(make_tmap(h, B, BK, &tmB));
+            k_zgemm_sk<true><<<G, GEMM_THREADS, GEMM_SMEM, st>>>(A, B, C, N, tiles, ntiles, p->ws, p->flags, h->ctrl, gated ? 1 : 0, tmA, tmB);
+        } else {
+            CUtensorMap dummy;
+            memset(&dummy, 0, sizeof(dummy));
+            k_zgemm_sk<false><<<G, GEMM_THREADS, GEMM_SMEM, st>>>(A, B, C, N, tiles, ntiles, p->ws, p->flags, h->ctrl, gated ? 1 : 0, dummy, dummy);
+        }
     }
     h->launches++;
     QF_CUDA(cudaGetLastError());
