@@ -114,6 +114,10 @@ int qf_laplace_host(qf_handle_t h, const void *P_host, void *W_host);
 /* Introspection used by bench.py: number of kernels this library launched since creation
  * of the handle, and per-phase device time of the last qf_profile_iteration call. */
 int64_t qf_launch_count(qf_handle_t h);
+/* Real FP64 flops one GEMM launch EXECUTES on this handle (tiles * tile area * K * 6 or 8), full or upper-only
+ * variant, and whether the 3-multiplication (Karatsuba) complex arithmetic is active. For roofline accounting. */
+double qf_gemm_executed_flops(qf_handle_t h, int upper_only);
+int qf_gemm_is_3m(qf_handle_t h);
 
 typedef struct {
     float poisson_ms;   /* W~ = W + dW, P~ = eps * Delta^{-1} W~ */

@@ -65,6 +65,8 @@ SYMBOLS = {
     "qf_solve_poisson_host": (_i, [_vp, _vp, _vp]),
     "qf_laplace_host": (_i, [_vp, _vp, _vp]),
     "qf_launch_count": (ctypes.c_int64, [_vp]),
+    "qf_gemm_executed_flops": (_d, [_vp, _i]),
+    "qf_gemm_is_3m": (_i, [_vp]),
     "qf_profile_iteration": (_i, [_vp, _vp, _d, _i, ctypes.POINTER(qf_phase_times), _vp]),
     "qf_comm_get_unique_id": (_i, [_vp]),
     "qf_comm_init": (_i, [_vp, _vp, _i, _i]),
@@ -159,6 +161,11 @@ class Handle:
 
     def launch_count(self) -> int:
         return int(self._lib.qf_launch_count(self._h))
+
+    def gemm_info(self):
+        """(3M arithmetic active?, executed flops of the full GEMM, executed flops of the upper-only GEMM)."""
+        return (bool(self._lib.qf_gemm_is_3m(self._h)), float(self._lib.qf_gemm_executed_flops(self._h, 0)),
+                float(self._lib.qf_gemm_executed_flops(self._h, 1)))
 
     # -- operators ---------------------------------------------------------------------
     def solve_poisson(self, W, out=None):

@@ -86,9 +86,10 @@ __global__ void k_zero(double2 *X, size_t n2, const QfCtrl *__restrict__ ctrl)
 // For the tile pair (bi <= bj):  c = A_ij - conj(A_ji),  d = S_ij + c,  r = |dW_ij - d|,
 // dW_ij = d, dW_ji = -conj(d);  deterministic partial row sums of r for the infinity norm:
 //   direct[i][bj] = sum_{j in tile, j >= i} r_ij      mirr[j][bi] = sum_{i in tile, i < j} r_ij
+// It also writes the next iterate W~ = W + dW (both triangles), so no separate pass is needed before the Poisson solve.
 __global__ void __launch_bounds__(256)
 k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *__restrict__ dWg, double *__restrict__ rowpart,
-       int N, int nslots, const QfCtrl *__restrict__ ctrl, int hb, int G)
+       int N, int nslots, const QfCtrl *__restrict__ ctrl, int hb, int G, const double2 *__restrict__ Wg, double2 *__restrict__ Whg)
 {
     const int b = blockIdx.z;
     if (!ctrl[b].active) return;
@@ -101,6 +102,8 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
     const double2 *A = Ag + off;
     const double2 *S = Sg + off;
     double2 *dW = dWg + off;
+    const double2 *W = Wg + off;
+    double2 *Wh = Whg + off;
     double *direct = rowpart + ((size_t)b * 2 + 0) * nslots * N;
     double *mirr = rowpart + ((size_t)b * 2 + 1) * nslots * N;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -129,6 +132,7 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
             const double2 old = dW[ij];
             r = zabs(zsub(old, d));                                   // :526,:534
             dW[ij] = d;
+            Wh[ij] = zadd(W[ij], d);                                  // next iterate W~ = W + dW (:481-482)
         }
         D[ii][tx] = d;
         R[ii][tx] = r;
@@ -144,7 +148,9 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
         const int j = bj * TS + jj, i = bi * TS + tx;
         if (j < N && i < N && i < j) {
             const double2 d = D[tx][jj];
-            dW[(size_t)j * N + i] = make_double2(-d.x, d.y);
+            const double2 dm = make_double2(-d.x, d.y);
+            dW[(size_t)j * N + i] = dm;
+            Wh[(size_t)j * N + i] = zadd(W[(size_t)j * N + i], dm);
         }
         double s = (i < j) ? R[tx][jj] : 0.0;
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -207,11 +213,22 @@ k_control(const double *__restrict__ rowpart, int N, int nslots, QfCtrl *ctrl, i
 }
 
 // ------------------------------------------------------------------------------- update
-// W += 2 (A - A^H)   (isospectral.py:547, :592) or its Kahan-compensated form (:553-586).
+// W += 2 (A - A^H)   (isospectral.py:547, :592) or its Kahan-compensated form (:553-586).  Both triangles of W are
+// updated element by element (like the reference's full-matrix `W += PWcomm`), with the increment of the lower
+// triangle being the exact mirror -conj(.) of the upper one (isospectral.py:74).  The kernel also prepares the first
+// iterate of the next step, W~ = W_new + dW (or W_new when the iterate is re-initialised every step).
+__device__ __forceinline__ double2 kahan_add(double2 w, double2 inc, double2 &kc)
+{
+    const double2 y = zsub(inc, kc);          // :570-571
+    const double2 tt = zadd(w, y);            // :575-576
+    kc = zsub(zsub(tt, w), y);                // :580-583
+    return tt;                                // :586
+}
+
 template <bool COMPSUM>
 __global__ void __launch_bounds__(256)
 k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__restrict__ Kg, int N, QfCtrl *ctrl,
-         int32_t *iters, int steps_cap, int hb, int G)
+         int32_t *iters, int steps_cap, int hb, int G, const double2 *__restrict__ dWg, double2 *__restrict__ Whg, int reinit)
 {
     const int b = blockIdx.z;
     QfCtrl &c = ctrl[b];
@@ -223,11 +240,12 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
     }
     if (bi > bj) return;
     __shared__ double2 T[TS][TS + 1];
-    __shared__ double2 D[TS][TS + 1];
     const size_t off = (size_t)b * N * N;
     const double2 *A = Ag + off;
     double2 *W = Wg + off;
     double2 *K = COMPSUM ? Kg + off : nullptr;
+    const double2 *dW = dWg + off;
+    double2 *Wh = Whg + off;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -236,51 +254,51 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
         T[jj][tx] = (j < N && i < N) ? A[(size_t)qf_prow(j, hb, G) * N + i] : make_double2(0.0, 0.0);
     }
     __syncthreads();
-    double2 wv[4], kv[4];
+    double2 cv[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int ii = ty + 8 * q;
         const int i = bi * TS + ii, j = bj * TS + tx;
-        double2 w = make_double2(0.0, 0.0), kc = make_double2(0.0, 0.0);
+        double2 cm = make_double2(0.0, 0.0);
         if (i < N && j < N && i <= j) {
             const size_t ij = (size_t)i * N + j;
-            double2 cm = zsub(A[(size_t)qf_prow(i, hb, G) * N + j], zconj(T[tx][ii]));
-            cm = make_double2(2.0 * cm.x, 2.0 * cm.y);
-            w = W[ij];
+            cm = zsub(A[(size_t)qf_prow(i, hb, G) * N + j], zconj(T[tx][ii]));
+            cm = make_double2(2.0 * cm.x, 2.0 * cm.y);                 // :547
+            double2 w = W[ij];
             if (COMPSUM) {
-                kc = K[ij];
-                const double2 y = zsub(cm, kc);          // :570-571
-                const double2 tt = zadd(w, y);           // :575-576
-                kc = zsub(zsub(tt, w), y);               // :580-583
-                w = tt;                                  // :586
+                double2 kc = K[ij];
+                w = kahan_add(w, cm, kc);
                 K[ij] = kc;
             } else {
-                w = zadd(w, cm);
+                w = zadd(w, cm);                                       // :592
             }
             W[ij] = w;
+            Wh[ij] = reinit ? w : zadd(w, dW[ij]);
         }
-        wv[q] = w;
-        kv[q] = kc;
+        cv[q] = cm;
     }
     __syncthreads();   // everyone is done reading T
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int ii = ty + 8 * q;
-        T[ii][tx] = wv[q];
-        if (COMPSUM) D[ii][tx] = kv[q];
-    }
+    for (int q = 0; q < 4; ++q) T[ty + 8 * q][tx] = cv[q];
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int jj = ty + 8 * q;
         const int j = bj * TS + jj, i = bi * TS + tx;
         if (j < N && i < N && i < j) {
-            const double2 w = T[tx][jj];
-            W[(size_t)j * N + i] = make_double2(-w.x, w.y);
+            const size_t ji = (size_t)j * N + i;
+            const double2 cu = T[tx][jj];
+            const double2 cm = make_double2(-cu.x, cu.y);              // PWcomm[j,i] = -conj(PWcomm[i,j])
+            double2 w = W[ji];
             if (COMPSUM) {
-                const double2 kc = D[tx][jj];
-                K[(size_t)j * N + i] = make_double2(-kc.x, kc.y);
+                double2 kc = K[ji];
+                w = kahan_add(w, cm, kc);
+                K[ji] = kc;
+            } else {
+                w = zadd(w, cm);
             }
+            W[ji] = w;
+            Wh[ji] = reinit ? w : zadd(w, dW[ji]);
         }
     }
 }
@@ -311,7 +329,8 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
     const int my = real_comm ? h->rank : -1;          // -1: compute every rank's blocks here (single GPU / emulation)
     const int hb = qf_block_rows(N, G);
     if (ev) QF_CUDA(cudaEventRecord(ev[0], st));
-    QF_CHECK(qf_launch_poisson(h, W, h->dW, h->Wh, h->P, eps, true, st));
+    // W~ = W + dW was written by the previous k_post / k_update (or copied at call start): solve straight from it
+    QF_CHECK(qf_launch_poisson(h, h->Wh, nullptr, h->Wh, h->P, eps, true, st));
     if (ev) QF_CUDA(cudaEventRecord(ev[1], st));
     QF_CHECK(qf_launch_zgemm(h, h->P, h->Wh, h->A, false, true, my, G, false, st));        // rows of A = P~ W~
     if (real_comm) QF_CHECK(h->comm_mode == 2 ? qf_comm_p2p_allgather(h, 0, true, st) : qf_comm_allgather_rows(h, h->A, st));
@@ -321,7 +340,7 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
     if (ev) QF_CUDA(cudaEventRecord(ev[3], st));
     const int nb = (N + TS - 1) / TS;
     dim3 g(nb, nb, h->batch);
-    k_post<<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, G);
+    k_post<<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, G, W, h->Wh);
     k_control<<<dim3((N + 7) / 8, h->batch), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit);
     h->launches += 2;
     if (ev) QF_CUDA(cudaEventRecord(ev[4], st));
@@ -329,16 +348,16 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
     return QF_OK;
 }
 
-int qf_enqueue_update(qf_handle_s *h, double2 *W, bool compsum, cudaStream_t st)
+int qf_enqueue_update(qf_handle_s *h, double2 *W, bool compsum, bool reinit, cudaStream_t st)
 {
     const int N = h->N;
     const int nb = (N + TS - 1) / TS;
     const int hb = qf_block_rows(N, h->nranks);
     dim3 g(nb, nb, h->batch);
     if (compsum)
-        k_update<true><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks);
+        k_update<true><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks, h->dW, h->Wh, reinit ? 1 : 0);
     else
-        k_update<false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks);
+        k_update<false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks, h->dW, h->Wh, reinit ? 1 : 0);
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;
@@ -469,7 +488,10 @@ static int build_step_graph(qf_handle_s *h, double2 *W, double eps, int maxit, i
     int32_t *iters = h->iters_dev;
     int steps_cap = h->steps_cap, hb = qf_block_rows(N, h->nranks), G = h->nranks, Nv = N;
     void *upd = compsum ? (void *)k_update<true> : (void *)k_update<false>;
-    QF_G(add_kernel_node(&n_update, g->graph, &n_while, 1, upd, gu, dim3(256), Ap, W, Kp, Nv, ctrl, iters, steps_cap, hb, G));
+    const double2 *dWp = h->dW;
+    double2 *Whp = h->Wh;
+    int reinit_i = reinit ? 1 : 0;
+    QF_G(add_kernel_node(&n_update, g->graph, &n_while, 1, upd, gu, dim3(256), Ap, W, Kp, Nv, ctrl, iters, steps_cap, hb, G, dWp, Whp, reinit_i));
     QF_G(cudaGraphInstantiate(&g->exec, g->graph, 0));
 #undef QF_G
     h->step_graph = g;
@@ -506,6 +528,7 @@ extern "C" int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double
     const double tol_factor = mach_eps * dt / hb;                           // :448
 
     QF_CUDA(cudaMemsetAsync(h->dW, 0, sizeof(double2) * n2 * B, st));       // :430
+    QF_CUDA(cudaMemcpyAsync(h->Wh, W, sizeof(double2) * n2 * B, cudaMemcpyDeviceToDevice, st));   // W~ = W + 0
     if (compsum) QF_CUDA(cudaMemsetAsync(h->kahan_c, 0, sizeof(double2) * n2 * B, st));   // :457
     QF_CHECK(qf_launch_norm_inf(h, W, st));
     k_call_begin<<<B, 1, 0, st>>>(h->ctrl, tol, tol_factor);
@@ -537,7 +560,7 @@ extern "C" int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double
                 h->launches++;
             }
             for (int i = 0; i < maxit; ++i) QF_CHECK(qf_enqueue_iteration(h, W, eps, maxit, minit, st, nullptr));
-            QF_CHECK(qf_enqueue_update(h, W, compsum, st));
+            QF_CHECK(qf_enqueue_update(h, W, compsum, reinit, st));
         }
     }
     QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl) * B, cudaMemcpyDeviceToHost, st));
@@ -584,6 +607,7 @@ extern "C" int qf_profile_iteration(qf_handle_t h, const void *W_dev, double dt,
     if (!h->io) QF_CUDA(cudaMalloc(&h->io, sizeof(double2) * n2 * B));
     QF_CUDA(cudaMemcpyAsync(h->io, W_dev, sizeof(double2) * n2 * B, cudaMemcpyDeviceToDevice, st));
     QF_CUDA(cudaMemsetAsync(h->dW, 0, sizeof(double2) * n2 * B, st));
+    QF_CUDA(cudaMemcpyAsync(h->Wh, h->io, sizeof(double2) * n2 * B, cudaMemcpyDeviceToDevice, st));
     QF_CHECK(qf_launch_norm_inf(h, h->io, st));
     k_call_begin<<<B, 1, 0, st>>>(h->ctrl, 0.0, 0.0);   // tol = 0: never converges by tolerance
     float acc[5] = {0, 0, 0, 0, 0};
@@ -591,7 +615,7 @@ extern "C" int qf_profile_iteration(qf_handle_t h, const void *W_dev, double dt,
         k_step_begin<<<1, 1, 0, st>>>(h->ctrl, B, 0, 0);
         QF_CHECK(qf_enqueue_iteration(h, h->io, eps, 1 << 30, 1 << 30, st, ev));
         QF_CUDA(cudaEventRecord(ev[5], st));
-        QF_CHECK(qf_enqueue_update(h, h->io, false, st));
+        QF_CHECK(qf_enqueue_update(h, h->io, false, false, st));
         QF_CUDA(cudaEventRecord(ev[6], st));
         QF_CUDA(cudaStreamSynchronize(st));
         if (r < 0) continue;

@@ -11,6 +11,7 @@
 // the same [k][k+m] layout as the matrix, so a warp that walks "one system per lane" reads whole
 // rows: fully coalesced.
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 
@@ -188,10 +189,8 @@ __global__ void k_fix_trace(double2 *P, int N, double eps, const QfCtrl *__restr
 // per-CTA sequential depth is 4L FMAs + two log-depth scans instead of 2N.
 // HBM traffic: upper triangle of W~ (8 N^2 B) + w and 1/u tables (8 N^2 B) + full P (16 N^2 B) = 32 N^2 B.
 // ---------------------------------------------------------------------------------------
-constexpr int GS = 4;
-
-template <int L>
-__global__ void __launch_bounds__(512, 1)
+template <int L, int GS, int MAXT>
+__global__ void __launch_bounds__(MAXT, 512 / MAXT)
 k_poisson_scan(const double2 *__restrict__ Wh, double2 *__restrict__ P, const double *__restrict__ tw,
                const double *__restrict__ tiu, int N, double eps, const QfCtrl *__restrict__ ctrl, int gated)
 {
@@ -203,7 +202,8 @@ k_poisson_scan(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
-    const int s = tid & (GS - 1), c = tid >> 2;
+    constexpr int GSH = (GS == 4) ? 2 : 1;
+    const int s = tid & (GS - 1), c = tid >> GSH;
     const int m0 = blockIdx.x * GS;
     const int m = m0 + s;
     const int n = N - m;                 // length of this thread's system (<= 0: none)
@@ -436,11 +436,23 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
         h->launches++;
     }
     if (N <= 2048) {
-        // chunked scan: 4 diagonals per CTA, 16 positions per thread
+        // chunked scan: GS diagonals per CTA, 16 positions per thread (QF_POISSON_GS=2|4, default 2: two CTAs per SM
+        // overlap each other's load / solve / store phases)
         const int chunks = (N + 15) / 16;
-        const int threads = ((GS * chunks + 31) / 32) * 32;
-        dim3 grid((N + GS - 1) / GS, h->batch);
-        k_poisson_scan<16><<<grid, threads, 0, st>>>(Wh, P, h->tab_w, h->tab_iu, N, eps, h->ctrl, g);
+        static int gs = 0;
+        if (!gs) {
+            const char *env = getenv("QF_POISSON_GS");
+            gs = (env && env[0] == '4') ? 4 : 2;
+        }
+        if (gs == 4) {
+            const int threads = ((4 * chunks + 31) / 32) * 32;
+            dim3 grid((N + 3) / 4, h->batch);
+            k_poisson_scan<16, 4, 512><<<grid, threads, 0, st>>>(Wh, P, h->tab_w, h->tab_iu, N, eps, h->ctrl, g);
+        } else {
+            const int threads = ((2 * chunks + 31) / 32) * 32;
+            dim3 grid((N + 1) / 2, h->batch);
+            k_poisson_scan<16, 2, 256><<<grid, threads, 0, st>>>(Wh, P, h->tab_w, h->tab_iu, N, eps, h->ctrl, g);
+        }
         h->launches++;
     } else {
         // large-N fallback: one thread per diagonal

@@ -5,13 +5,19 @@
 // Replaces the two zgemm calls of the fixed-point iteration, np.matmul(Phalf, Whalf, out=PWcomm) and
 // np.matmul(PWcomm, Phalf, out=dW)  (quflow/integrators/isospectral.py:496,499).
 //
-// Layout.  CTA tile 128 x 64 complex, K step 16, 8 warps (4 along M x 2 along N), warp tile 32 x 32:
-// 4 x 4 sub-tiles of 8 x 8, each holding a real and an imaginary accumulator fragment (128 registers).
-// A complex product is four real DMMAs:  Cre += Are*Bre + (-Aim)*Bim,  Cim += Are*Bim + Aim*Bre.
+// Two arithmetic variants share all of the machinery below (template parameter M3):
+//   4M  CTA tile 128 x 64, 8 warps as 4 x 2, warp tile 32 x 32.  A complex product is four real DMMAs:
+//         Cre += Are*Bre + (-Aim)*Bim,  Cim += Are*Bim + Aim*Bre          (8 real flop per complex MAC)
+//   3M  CTA tile 64 x 64, 8 warps as 2 x 4, warp tile 32 x 16.  Karatsuba / "ZGEMM3M": three real DMMAs
+//         T1 += Are*Bre,  T2 += Aim*Bim,  T3 += (Are+Aim)*(Bre+Bim);   Cre = T1-T2,  Cim = T3-T1-T2   (6 real flop)
+//       25 % fewer FP64 tensor instructions for a normwise error of the same order.
+//
 // Operands sit in shared memory as 128-byte rows in the TMA SWIZZLE_128B pattern (16-byte chunk c of row r
 // is stored at chunk c ^ (r & 7)); one LDS.128 per fragment delivers (re, im) of one complex element.
 // The K index inside an MMA is permuted (lane%4 = t uses k = 2t + s) so that the eight lanes of every
 // quarter-warp hit eight different chunks: all fragment loads are bank-conflict free.
+// Tiles are fed by TMA (cp.async.bulk.tensor, one mbarrier per stage) with a cp.async fallback, and scheduled
+// stream-K: persistent CTAs split the (tile, k) iteration space evenly (see k_zgemm_sk).
 #include <cuda.h>
 
 #include <algorithm>
@@ -23,13 +29,29 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 16;
-constexpr int STAGES = 3;
-constexpr int A_STAGE_BYTES = BM * BK * 16;          // 32 KiB: 2 boxes [128 rows][128 B]
-constexpr int B_STAGE_BYTES = BK * BN * 16;          // 16 KiB: 8 boxes [16 rows][128 B]
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024;   // + slack for 1024-byte alignment
+constexpr int MI = 4;   // 8-row sub-tiles per warp (warp tile is 32 rows in both variants)
+
+template <bool M3>
+struct Cfg;
+template <>
+struct Cfg<false> {
+    static constexpr int BM = 128, BN = 64, BK = 16, WN = 2, NJ = 4, NACC = 2, STAGES = 3;
+};
+template <>
+struct Cfg<true> {
+    static constexpr int BM = 64, BN = 64, BK = 32, WN = 4, NJ = 2, NACC = 3, STAGES = 3;
+};
+template <bool M3>
+struct Geo {
+    using C = Cfg<M3>;
+    static constexpr int A_STAGE_BYTES = C::BM * C::BK * 16;   // BK/8 boxes [BM rows][128 B]
+    static constexpr int B_STAGE_BYTES = C::BK * C::BN * 16;   // BN/8 boxes [BK rows][128 B]
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int SMEM = C::STAGES * STAGE_BYTES + 1024;   // + slack for 1024-byte alignment
+    static constexpr int ACC_D2 = MI * C::NJ * C::NACC;           // double2 per thread in a partial tile
+};
+constexpr int WS_D2_PER_THREAD = 32;   // workspace slot = 32 double2 per thread (max over the variants)
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
@@ -86,15 +108,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
                  : "memory");
 }
 
-// Load one K tile (k0 .. k0+15) of the A panel (rows row0 .. row0+127) and of the B panel (cols col0 .. col0+63).
+// ---- cp.async loader (fallback when the driver has no tensor-map encoder, or QF_GEMM_LOAD=cpasync) --------
+template <bool M3>
 __device__ __forceinline__ void load_stage(uint32_t sA, uint32_t sB, const double2 *__restrict__ A,
                                            const double2 *__restrict__ B, int N, int row0, int row_end, int col0, int k0,
                                            int tid)
 {
+    constexpr int BM = Cfg<M3>::BM, BN = Cfg<M3>::BN, BK = Cfg<M3>::BK;
 #pragma unroll
     for (int q = 0; q < (BM * BK) / GEMM_THREADS; ++q) {
         const int idx = tid + q * GEMM_THREADS;
-        const int k = idx & (BK - 1), r = idx >> 4;
+        const int k = idx & (BK - 1), r = idx / BK;
         const int gr = row0 + r, gk = k0 + k;
         const bool ok = (gr < row_end) && (gk < N);
         const double2 *src = A + (ok ? ((size_t)gr * N + gk) : 0);
@@ -104,7 +128,7 @@ __device__ __forceinline__ void load_stage(uint32_t sA, uint32_t sB, const doubl
 #pragma unroll
     for (int q = 0; q < (BK * BN) / GEMM_THREADS; ++q) {
         const int idx = tid + q * GEMM_THREADS;
-        const int n = idx & (BN - 1), k = idx >> 6;
+        const int n = idx & (BN - 1), k = idx / BN;
         const int gk = k0 + k, gc = col0 + n;
         const bool ok = (gk < N) && (gc < N);
         const double2 *src = B + (ok ? ((size_t)gk * N + gc) : 0);
@@ -113,46 +137,65 @@ __device__ __forceinline__ void load_stage(uint32_t sA, uint32_t sB, const doubl
     }
 }
 
-// 64 DMMAs x 4 k-steps on one resident stage.
-__device__ __forceinline__ void gemm_compute_stage(double (&acc_re)[4][4][2], double (&acc_im)[4][4][2], uint32_t sb,
+// ---- the DMMA inner product over one resident stage (4 k-steps of 4) ---------------------------------------
+template <bool M3>
+__device__ __forceinline__ void gemm_compute_stage(double (&acc)[MI][Cfg<M3>::NJ][Cfg<M3>::NACC][2], uint32_t sb,
                                                    const uint32_t (&a_off)[2], const uint32_t (&b_off)[2])
 {
+    constexpr int BM = Cfg<M3>::BM, NJ = Cfg<M3>::NJ, BK = Cfg<M3>::BK;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
+    for (int hh = 0; hh < BK / 8; ++hh) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            double a_re[4], a_im[4], a_in[4], b_re[4], b_im[4];
+            double a_re[MI], a_im[MI], a_x[MI], b_re[NJ], b_im[NJ], b_x[NJ];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < MI; ++i) {
                 const double2 v = lds128(sb + a_off[s] + hh * (BM * 128) + i * 1024);
                 a_re[i] = v.x;
                 a_im[i] = v.y;
-                a_in[i] = flip_sign(v.y);
+                a_x[i] = M3 ? (v.x + v.y) : flip_sign(v.y);   // 3M: Are+Aim   4M: -Aim
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 const double2 v = lds128(sb + b_off[s] + hh * 1024 + j * (BK * 128));
                 b_re[j] = v.x;
                 b_im[j] = v.y;
+                b_x[j] = M3 ? (v.x + v.y) : 0.0;
             }
+            if (M3) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < MI; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    dmma884(acc_re[i][j][0], acc_re[i][j][1], a_re[i], b_re[j]);
-                    dmma884(acc_im[i][j][0], acc_im[i][j][1], a_re[i], b_im[j]);
-                }
+                    for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0][0], acc[i][j][0][1], a_re[i], b_re[j]);   // T1
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < MI; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    dmma884(acc_re[i][j][0], acc_re[i][j][1], a_in[i], b_im[j]);
-                    dmma884(acc_im[i][j][0], acc_im[i][j][1], a_im[i], b_re[j]);
-                }
+                    for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][1][0], acc[i][j][1][1], a_im[i], b_im[j]);   // T2
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][2][0], acc[i][j][2][1], a_x[i], b_x[j]);     // T3
+            } else {
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        dmma884(acc[i][j][0][0], acc[i][j][0][1], a_re[i], b_re[j]);
+                        dmma884(acc[i][j][1][0], acc[i][j][1][1], a_re[i], b_im[j]);
+                    }
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        dmma884(acc[i][j][0][0], acc[i][j][0][1], a_x[i], b_im[j]);
+                        dmma884(acc[i][j][1][0], acc[i][j][1][1], a_im[i], b_re[j]);
+                    }
+            }
         }
     }
 }
 
+template <bool M3>
 __device__ __forceinline__ void gemm_frag_offsets(uint32_t (&a_off)[2], uint32_t (&b_off)[2], int wm, int wn, int g, int t)
 {
     // per-thread fragment base offsets inside a stage (see file header for the k permutation)
@@ -160,25 +203,28 @@ __device__ __forceinline__ void gemm_frag_offsets(uint32_t (&a_off)[2], uint32_t
     for (int s = 0; s < 2; ++s) {
         const int kk = 2 * t + s;
         a_off[s] = (wm * 32 + g) * 128 + ((kk ^ g) << 4);
-        b_off[s] = A_STAGE_BYTES + wn * 4 * (BK * 128) + kk * 128 + ((g ^ kk) << 4);
+        b_off[s] = Geo<M3>::A_STAGE_BYTES + wn * Cfg<M3>::NJ * (Cfg<M3>::BK * 128) + kk * 128 + ((g ^ kk) << 4);
     }
 }
 
-// Accumulate k-tiles [kt_begin, kt_end) of the (row0, col0) tile into acc (cp.async 3-stage pipeline).
-__device__ __forceinline__ void gemm_mainloop(double (&acc_re)[4][4][2], double (&acc_im)[4][4][2], uint32_t smem_base,
+// Accumulate k-tiles [kt_begin, kt_end) of one output tile; cp.async multi-stage pipeline.
+template <bool M3>
+__device__ __forceinline__ void gemm_mainloop(double (&acc)[MI][Cfg<M3>::NJ][Cfg<M3>::NACC][2], uint32_t smem_base,
                                               const double2 *__restrict__ A, const double2 *__restrict__ B, int N, int row0,
                                               int row_end, int col0, int kt_begin, int kt_end, int tid, int wm, int wn, int g, int t)
 {
+    constexpr int STAGES = Cfg<M3>::STAGES, STAGE_BYTES = Geo<M3>::STAGE_BYTES, A_STAGE_BYTES = Geo<M3>::A_STAGE_BYTES;
+    constexpr int BK = Cfg<M3>::BK;
     const int nkt = kt_end - kt_begin;
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nkt)
-            load_stage(smem_base + s * STAGE_BYTES, smem_base + s * STAGE_BYTES + A_STAGE_BYTES, A, B, N, row0, row_end, col0,
-                       (kt_begin + s) * BK, tid);
+            load_stage<M3>(smem_base + s * STAGE_BYTES, smem_base + s * STAGE_BYTES + A_STAGE_BYTES, A, B, N, row0, row_end, col0,
+                           (kt_begin + s) * BK, tid);
         cp_async_commit();
     }
     uint32_t a_off[2], b_off[2];
-    gemm_frag_offsets(a_off, b_off, wm, wn, g, t);
+    gemm_frag_offsets<M3>(a_off, b_off, wm, wn, g, t);
     for (int kt = 0; kt < nkt; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -186,24 +232,27 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc_re)[4][4][2], double 
             const int nk = kt + STAGES - 1;
             if (nk < nkt) {
                 const uint32_t sb = smem_base + (nk % STAGES) * STAGE_BYTES;
-                load_stage(sb, sb + A_STAGE_BYTES, A, B, N, row0, row_end, col0, (kt_begin + nk) * BK, tid);
+                load_stage<M3>(sb, sb + A_STAGE_BYTES, A, B, N, row0, row_end, col0, (kt_begin + nk) * BK, tid);
             }
             cp_async_commit();
         }
-        gemm_compute_stage(acc_re, acc_im, smem_base + (kt % STAGES) * STAGE_BYTES, a_off, b_off);
+        gemm_compute_stage<M3>(acc, smem_base + (kt % STAGES) * STAGE_BYTES, a_off, b_off);
     }
     cp_async_wait<0>();
     __syncthreads();   // all warps are done with shared memory: the next segment may refill it
 }
 
-// Same main loop fed by TMA: one elected thread issues 2 (A) + 8 (B) cp.async.bulk.tensor boxes of 128-byte rows per
-// stage into the SWIZZLE_128B layout; completion is tracked by one mbarrier per stage (expect_tx = 48 KiB).
+// Same main loop fed by TMA: one elected thread issues 2 (A) + BN/8 (B) cp.async.bulk.tensor boxes of 128-byte rows
+// per stage into the SWIZZLE_128B layout; completion is tracked by one mbarrier per stage (expect_tx = stage bytes).
 // `gk` counts the k-tiles this CTA has consumed since kernel start: stage = gk % STAGES, phase = (gk / STAGES) & 1.
-__device__ __forceinline__ void gemm_mainloop_tma(double (&acc_re)[4][4][2], double (&acc_im)[4][4][2], uint32_t smem_base,
+template <bool M3>
+__device__ __forceinline__ void gemm_mainloop_tma(double (&acc)[MI][Cfg<M3>::NJ][Cfg<M3>::NACC][2], uint32_t smem_base,
                                                   uint32_t bars, const CUtensorMap *tmA, const CUtensorMap *tmB, int member,
                                                   int a_mem_row0, int col0, int kt_begin, int kt_end, uint32_t &gk, int tid,
                                                   int wm, int wn, int g, int t)
 {
+    constexpr int STAGES = Cfg<M3>::STAGES, STAGE_BYTES = Geo<M3>::STAGE_BYTES, A_STAGE_BYTES = Geo<M3>::A_STAGE_BYTES;
+    constexpr int BM = Cfg<M3>::BM, BN = Cfg<M3>::BN, BK = Cfg<M3>::BK;
     const int nkt = kt_end - kt_begin;
     auto issue = [&](int i) {
         const uint32_t idx = gk + (uint32_t)i;
@@ -213,7 +262,7 @@ __device__ __forceinline__ void gemm_mainloop_tma(double (&acc_re)[4][4][2], dou
         const int k0 = (kt_begin + i) * BK;
         mbar_arrive_expect_tx(bar, STAGE_BYTES);
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) tma_load_3d(sb + hh * (BM * 128), tmA, 2 * (k0 + 8 * hh), a_mem_row0, member, bar);
+        for (int hh = 0; hh < BK / 8; ++hh) tma_load_3d(sb + hh * (BM * 128), tmA, 2 * (k0 + 8 * hh), a_mem_row0, member, bar);
 #pragma unroll
         for (int c = 0; c < BN / 8; ++c) tma_load_3d(sb + A_STAGE_BYTES + c * (BK * 128), tmB, 2 * (col0 + 8 * c), k0, member, bar);
     };
@@ -223,68 +272,47 @@ __device__ __forceinline__ void gemm_mainloop_tma(double (&acc_re)[4][4][2], dou
             if (s < nkt) issue(s);
     }
     uint32_t a_off[2], b_off[2];
-    gemm_frag_offsets(a_off, b_off, wm, wn, g, t);
+    gemm_frag_offsets<M3>(a_off, b_off, wm, wn, g, t);
     for (int kt = 0; kt < nkt; ++kt) {
         const uint32_t idx = gk + (uint32_t)kt;
         const uint32_t stage = idx % STAGES;
         __syncthreads();   // every warp finished k-tile kt-1: its stage may be refilled
         if (tid == 0 && kt + STAGES - 1 < nkt) issue(kt + STAGES - 1);
         mbar_wait(bars + 8 * stage, (idx / STAGES) & 1);
-        gemm_compute_stage(acc_re, acc_im, smem_base + stage * STAGE_BYTES, a_off, b_off);
+        gemm_compute_stage<M3>(acc, smem_base + stage * STAGE_BYTES, a_off, b_off);
     }
     gk += (uint32_t)nkt;
     __syncthreads();
 }
 
-// each thread owns, per 8x8 sub-tile, row g and the two adjacent columns 2t, 2t+1
-__device__ __forceinline__ void gemm_store_tile(const double (&acc_re)[4][4][2], const double (&acc_im)[4][4][2],
-                                                double2 *__restrict__ C, int N, int row0, int row_end, int col0, int wm, int wn,
-                                                int g, int t)
+// each thread owns, per 8x8 sub-tile, row g and the two adjacent columns 2t, 2t+1 (row0 / row_end: OUTPUT rows)
+template <bool M3>
+__device__ __forceinline__ void gemm_store_tile(const double (&acc)[MI][Cfg<M3>::NJ][Cfg<M3>::NACC][2], double2 *__restrict__ C,
+                                                int N, int row0, int row_end, int col0, int wm, int wn, int g, int t)
 {
-    // row0 / row_end are in the OUTPUT row numbering here
+    constexpr int NJ = Cfg<M3>::NJ;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < MI; ++i) {
         const int r = row0 + wm * 32 + i * 8 + g;
         if (r >= row_end) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = col0 + wn * 32 + j * 8 + 2 * t;
+        for (int j = 0; j < NJ; ++j) {
+            const int c = col0 + wn * (8 * NJ) + j * 8 + 2 * t;
             double2 *dst = C + (size_t)r * N + c;
-            if (c < N) dst[0] = make_double2(acc_re[i][j][0], acc_im[i][j][0]);
-            if (c + 1 < N) dst[1] = make_double2(acc_re[i][j][1], acc_im[i][j][1]);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double re, im;
+                if (M3) {
+                    re = acc[i][j][0][e] - acc[i][j][1][e];
+                    im = (acc[i][j][2][e] - acc[i][j][0][e]) - acc[i][j][1][e];
+                } else {
+                    re = acc[i][j][0][e];
+                    im = acc[i][j][1][e];
+                }
+                if (c + e < N) dst[e] = make_double2(re, im);
+            }
         }
     }
-}
-
-// ---- data-parallel kernel: one CTA per output tile (kept as the simple variant, QF_GEMM=tile) ----
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-k_zgemm(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, double2 *__restrict__ Cg, int N, int row_begin,
-        int row_end, int upper_only, const QfCtrl *__restrict__ ctrl, int gated)
-{
-    const int b = blockIdx.z;
-    if (gated && !ctrl[b].active) return;
-    const int row0 = row_begin + blockIdx.y * BM;
-    const int col0 = blockIdx.x * BN;
-    if (upper_only && (col0 + BN - 1 < row0)) return;   // tile entirely below the diagonal
-
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
-    const size_t moff = (size_t)b * N * N;
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int wm = warp >> 1, wn = warp & 1;   // 4 x 2 warps
-    const int g = lane >> 2, t = lane & 3;
-
-    double acc_re[4][4][2], acc_im[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            acc_re[i][j][0] = acc_re[i][j][1] = 0.0;
-            acc_im[i][j][0] = acc_im[i][j][1] = 0.0;
-        }
-    gemm_mainloop(acc_re, acc_im, smem_base, Ag + moff, Bg + moff, N, row0, row_end, col0, 0, (N + BK - 1) / BK, tid, wm, wn, g, t);
-    gemm_store_tile(acc_re, acc_im, Cg + moff, N, row0, row_end, col0, wm, wn, g, t);
 }
 
 // ---- stream-K kernel: persistent CTAs split the (tile, k) iteration space evenly --------------------
@@ -293,17 +321,19 @@ k_zgemm(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, double2 
 // rest of the tile compute it FIRST in their own range, park the partial accumulators in their workspace slot and
 // raise a flag.  Waits therefore only ever target work that was started at kernel start: no dependency cycles.
 // Partials are added in CTA order, so the result is deterministic for a given (N, G).
-// One output tile: rows [a_row0, row_end) of the A operand (logical matrix rows) times columns [col0, col0+64) of B,
+//
+// One output tile: rows [a_row0, row_end) of the A operand (logical matrix rows) times columns [col0, col0+BN) of B,
 // written to rows c_row0.. of C (C may use the rank-permuted row layout of the multi-GPU path, see qf_common.cuh).
 struct SkTile { int member, a_row0, c_row0, col0, row_end, op_row0, pad1, pad2; };   // op_row0: first row of the A operand in memory
 
-template <bool TMA>
+template <bool M3, bool TMA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, double2 *__restrict__ Cg, int N,
            const SkTile *__restrict__ tiles, int ntiles, double2 *__restrict__ ws, int *__restrict__ flags,
            const QfCtrl *__restrict__ ctrl, int gated, const __grid_constant__ CUtensorMap tmA,
            const __grid_constant__ CUtensorMap tmB)
 {
+    constexpr int STAGES = Cfg<M3>::STAGES, NJ = Cfg<M3>::NJ, NACC = Cfg<M3>::NACC, WN = Cfg<M3>::WN;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
     __shared__ __align__(8) unsigned long long mbar_storage[STAGES];
@@ -319,9 +349,10 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
     }
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int wm = warp >> 1, wn = warp & 1;
+    const int wm = warp / WN, wn = warp % WN;
     const int g = lane >> 2, t = lane & 3;
     const int cta = blockIdx.x, G = gridDim.x;
+    constexpr int BK = Cfg<M3>::BK;
     const int KT = (N + BK - 1) / BK;
     const long long T = (long long)ntiles * KT;
     long long it = T * cta / G;
@@ -336,32 +367,31 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
         if (gated && !ctrl[ti.member].active) continue;
         const size_t moff = (size_t)ti.member * N * N;
 
-        double acc_re[4][4][2], acc_im[4][4][2];
+        double acc[MI][NJ][NACC][2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                acc_re[i][j][0] = acc_re[i][j][1] = 0.0;
-                acc_im[i][j][0] = acc_im[i][j][1] = 0.0;
-            }
-        // the A operand may itself be stored in the rank-permuted row layout (second GEMM): shift the base pointer so that
-        // logical row a_row0 addresses memory row op_row0
+            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                for (int c = 0; c < NACC; ++c) acc[i][j][c][0] = acc[i][j][c][1] = 0.0;
+
+        // the A operand may itself be stored in the rank-permuted row layout (second GEMM): op_row0 is its memory row
         if (TMA)
-            gemm_mainloop_tma(acc_re, acc_im, smem_base, bars, &tmA, &tmB, ti.member, ti.op_row0, ti.col0, ka, kb, gk, tid, wm, wn, g, t);
+            gemm_mainloop_tma<M3>(acc, smem_base, bars, &tmA, &tmB, ti.member, ti.op_row0, ti.col0, ka, kb, gk, tid, wm, wn, g, t);
         else
-            gemm_mainloop(acc_re, acc_im, smem_base, Ag + moff + ((ptrdiff_t)ti.op_row0 - ti.a_row0) * N, Bg + moff, N, ti.a_row0,
-                          ti.row_end, ti.col0, ka, kb, tid, wm, wn, g, t);
+            gemm_mainloop<M3>(acc, smem_base, Ag + moff + ((ptrdiff_t)ti.op_row0 - ti.a_row0) * N, Bg + moff, N, ti.a_row0,
+                              ti.row_end, ti.col0, ka, kb, tid, wm, wn, g, t);
 
         if (ka > 0) {
             // contributor: park the partial tile in this CTA's slot ([reg][thread] layout: coalesced)
-            double2 *slot = ws + (size_t)cta * (32 * GEMM_THREADS);
+            double2 *slot = ws + (size_t)cta * (WS_D2_PER_THREAD * GEMM_THREADS);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < MI; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    __stcg(slot + ((i * 4 + j) * 2 + 0) * GEMM_THREADS + tid, make_double2(acc_re[i][j][0], acc_re[i][j][1]));
-                    __stcg(slot + ((i * 4 + j) * 2 + 1) * GEMM_THREADS + tid, make_double2(acc_im[i][j][0], acc_im[i][j][1]));
-                }
+                for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                    for (int c = 0; c < NACC; ++c)
+                        __stcg(slot + ((i * NJ + j) * NACC + c) * GEMM_THREADS + tid, make_double2(acc[i][j][c][0], acc[i][j][c][1]));
             __threadfence();
             __syncthreads();
             if (tid == 0) atomicExch(flags + cta, 1);
@@ -378,23 +408,22 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
                     }
                     __syncthreads();
                     __threadfence();
-                    const double2 *slot = ws + (size_t)peer * (32 * GEMM_THREADS);
+                    const double2 *slot = ws + (size_t)peer * (WS_D2_PER_THREAD * GEMM_THREADS);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < MI; ++i)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const double2 pr = __ldcg(slot + ((i * 4 + j) * 2 + 0) * GEMM_THREADS + tid);
-                            const double2 pi = __ldcg(slot + ((i * 4 + j) * 2 + 1) * GEMM_THREADS + tid);
-                            acc_re[i][j][0] += pr.x;
-                            acc_re[i][j][1] += pr.y;
-                            acc_im[i][j][0] += pi.x;
-                            acc_im[i][j][1] += pi.y;
-                        }
+                        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                            for (int c = 0; c < NACC; ++c) {
+                                const double2 p = __ldcg(slot + ((i * NJ + j) * NACC + c) * GEMM_THREADS + tid);
+                                acc[i][j][c][0] += p.x;
+                                acc[i][j][c][1] += p.y;
+                            }
                     covered = T * (peer + 1) / G;
                     ++peer;
                 }
             }
-            gemm_store_tile(acc_re, acc_im, Cg + moff, N, ti.c_row0, ti.c_row0 + (ti.row_end - ti.a_row0), ti.col0, wm, wn, g, t);
+            gemm_store_tile<M3>(acc, Cg + moff, N, ti.c_row0, ti.c_row0 + (ti.row_end - ti.a_row0), ti.col0, wm, wn, g, t);
         }
     }
 }
@@ -406,29 +435,31 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuui
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct QfGemmPlan {
-    int smem_bytes = 0;
-    bool streamk = true;
+    bool m3 = true;             // 3M (Karatsuba) arithmetic; QF_GEMM_3M=0 selects the 4-multiplication variant
     bool tma = true;
     PFN_tmapEncodeTiled encode = nullptr;
     int max_ctas = 0;
     double2 *ws = nullptr;      // [max_ctas][32][256] partial tiles
     int *flags = nullptr;       // [max_ctas]
-    // cached tile lists keyed by (upper_only, rank, nranks); rank < 0 = all ranks (single-GPU emulation)
+    // cached tile lists keyed by (upper_only, rank, nranks, a_permuted); rank < 0 = all ranks (single-GPU emulation)
     struct List { int upper, rank, nranks, aperm, ntiles; SkTile *dev; };
     std::vector<List> lists;
+    int BM() const { return m3 ? Cfg<true>::BM : Cfg<false>::BM; }
+    int BN() const { return m3 ? Cfg<true>::BN : Cfg<false>::BN; }
+    int BK() const { return m3 ? Cfg<true>::BK : Cfg<false>::BK; }
 };
 
 int qf_gemm_create(qf_handle_s *h)
 {
     QfGemmPlan *p = new QfGemmPlan();
     h->gemm = p;
-    p->smem_bytes = GEMM_SMEM;
-    const char *env = getenv("QF_GEMM");
-    p->streamk = !(env && strcmp(env, "tile") == 0);
+    const char *env = getenv("QF_GEMM_3M");
+    p->m3 = !(env && env[0] == '0');
     p->max_ctas = h->sm_count;
-    QF_CUDA(cudaFuncSetAttribute(k_zgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<false>::SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<false>::SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM));
     {
         const char *ld = getenv("QF_GEMM_LOAD");
         p->tma = !(ld && strcmp(ld, "cpasync") == 0);
@@ -441,7 +472,7 @@ int qf_gemm_create(qf_handle_s *h)
         }
         p->encode = (PFN_tmapEncodeTiled)fn;
     }
-    QF_CUDA(cudaMalloc(&p->ws, sizeof(double2) * 32 * GEMM_THREADS * (size_t)p->max_ctas));
+    QF_CUDA(cudaMalloc(&p->ws, sizeof(double2) * WS_D2_PER_THREAD * GEMM_THREADS * (size_t)p->max_ctas));
     QF_CUDA(cudaMalloc(&p->flags, sizeof(int) * p->max_ctas));
     QF_CUDA(cudaMemset(p->flags, 0, sizeof(int) * p->max_ctas));
     return QF_OK;
@@ -455,6 +486,22 @@ void qf_gemm_destroy(qf_handle_s *h)
     if (h->gemm->flags) cudaFree(h->gemm->flags);
     delete h->gemm;
     h->gemm = nullptr;
+}
+
+extern "C" int qf_gemm_is_3m(qf_handle_t h) { return h && h->gemm && h->gemm->m3 ? 1 : 0; }
+
+// Executed real FP64 flops of one launch (for the roofline): tiles * BM * BN * N * (6 or 8).
+extern "C" double qf_gemm_executed_flops(qf_handle_t h, int upper_only)
+{
+    if (!h || !h->gemm) return 0.0;
+    const int N = h->N, BMv = h->gemm->BM(), BNv = h->gemm->BN();
+    long long tiles = 0;
+    for (int r0 = 0; r0 < N; r0 += BMv)
+        for (int c0 = 0; c0 < N; c0 += BNv)
+            if (!upper_only || c0 + BNv - 1 >= r0) ++tiles;
+    const int BK = h->gemm->BK();
+    const double kpad = (double)((N + BK - 1) / BK) * BK;
+    return (double)tiles * BMv * BNv * kpad * (h->gemm->m3 ? 6.0 : 8.0) * h->batch;
 }
 
 // 3-D tensor map over `batch` row-major N x N complex128 matrices seen as doubles: dims {2N, N, batch}, box {16, rows, 1}
@@ -486,7 +533,7 @@ static int get_tile_list(qf_handle_s *h, bool upper_only, int rank, int nranks, 
             return QF_OK;
         }
     std::vector<SkTile> tl;
-    const int N = h->N;
+    const int N = h->N, BMv = p->BM(), BNv = p->BN();
     const int hb = qf_block_rows(N, nranks);
     for (int b = 0; b < h->batch; ++b)
         for (int r = 0; r < nranks; ++r) {
@@ -496,10 +543,11 @@ static int get_tile_list(qf_handle_s *h, bool upper_only, int rank, int nranks, 
             for (int q = 0; q < (nranks == 1 ? 1 : 2); ++q) {
                 const int rb = (nranks == 1) ? 0 : blocks[q] * hb;
                 const int re = (nranks == 1) ? N : std::min(N, rb + hb);
-                for (int r0 = rb; r0 < re; r0 += BM)
-                    for (int c0 = 0; c0 < N; c0 += BN) {
-                        if (upper_only && (c0 + BN - 1 < r0)) continue;
-                        tl.push_back(SkTile{b, r0, qf_prow(r0, hb, nranks), c0, re, a_permuted ? qf_prow(r0, hb, nranks) : r0, 0, 0});
+                for (int r0 = rb; r0 < re; r0 += BMv)
+                    for (int c0 = 0; c0 < N; c0 += BNv) {
+                        if (upper_only && (c0 + BNv - 1 < r0)) continue;
+                        tl.push_back(SkTile{b, r0, qf_prow(r0, hb, nranks), c0, std::min(re, r0 + BMv),
+                                            a_permuted ? qf_prow(r0, hb, nranks) : r0, 0, 0});
                     }
             }
         }
@@ -521,36 +569,45 @@ int qf_gemm_prepare(qf_handle_s *h, int rank, int nranks)
     return QF_OK;
 }
 
+template <bool M3>
+static void launch_sk(qf_handle_s *h, bool tma, int G, const double2 *A, const double2 *B, double2 *C, const SkTile *tiles,
+                      int ntiles, int gated, const CUtensorMap &tmA, const CUtensorMap &tmB, cudaStream_t st)
+{
+    QfGemmPlan *p = h->gemm;
+    if (tma)
+        k_zgemm_sk<M3, true><<<G, GEMM_THREADS, Geo<M3>::SMEM, st>>>(A, B, C, h->N, tiles, ntiles, p->ws, p->flags, h->ctrl, gated, tmA, tmB);
+    else
+        k_zgemm_sk<M3, false><<<G, GEMM_THREADS, Geo<M3>::SMEM, st>>>(A, B, C, h->N, tiles, ntiles, p->ws, p->flags, h->ctrl, gated, tmA, tmB);
+}
+
 // rank/nranks select the row blocks (see qf_prow); rank < 0 computes every rank's blocks (emulation on one GPU).
 int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 *C, bool upper_only, bool gated,
                     int rank, int nranks, bool a_permuted, cudaStream_t st)
 {
     const int N = h->N;
     QfGemmPlan *p = h->gemm;
-    if (!p->streamk && nranks == 1) {
-        dim3 grid((N + BN - 1) / BN, (N + BM - 1) / BM, h->batch);
-        k_zgemm<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(A, B, C, N, 0, N, upper_only ? 1 : 0, h->ctrl, gated ? 1 : 0);
-    } else {
-        const SkTile *tiles;
-        int ntiles;
-        QF_CHECK(get_tile_list(h, upper_only, rank, nranks, a_permuted, &tiles, &ntiles));
-        const int KT = (N + BK - 1) / BK;
-        const long long T = (long long)ntiles * KT;
-        if (ntiles == 0) return QF_OK;
-        // at least 8 k-iterations per CTA so that the fix-up traffic stays small
-        const int G = (int)std::min<long long>(p->max_ctas, std::max<long long>(1, T / 8));
-        // TMA needs 16-byte aligned rows (always true) and N >= 8 so that a 128-byte box fits the row pitch
-        if (p->tma && N >= 8) {
-            CUtensorMap tmA, tmB;
-            QF_CHECK(make_tmap(h, A, BM, &tmA));
-            QF_CHECK(make_tmap(h, B, BK, &tmB));
-            k_zgemm_sk<true><<<G, GEMM_THREADS, GEMM_SMEM, st>>>(A, B, C, N, tiles, ntiles, p->ws, p->flags, h->ctrl, gated ? 1 : 0, tmA, tmB);
-        } else {
-            CUtensorMap dummy;
-            memset(&dummy, 0, sizeof(dummy));
-            k_zgemm_sk<false><<<G, GEMM_THREADS, GEMM_SMEM, st>>>(A, B, C, N, tiles, ntiles, p->ws, p->flags, h->ctrl, gated ? 1 : 0, dummy, dummy);
-        }
+    const SkTile *tiles;
+    int ntiles;
+    QF_CHECK(get_tile_list(h, upper_only, rank, nranks, a_permuted, &tiles, &ntiles));
+    if (ntiles == 0) return QF_OK;
+    const int BK = p->BK();
+    const int KT = (N + BK - 1) / BK;
+    const long long T = (long long)ntiles * KT;
+    // at least 128 k per CTA so that the fix-up traffic stays small
+    const int G = (int)std::min<long long>(p->max_ctas, std::max<long long>(1, T / (128 / BK)));
+    // TMA needs 16-byte aligned rows (always true) and N >= 8 so that a 128-byte box fits the row pitch
+    const bool tma = p->tma && N >= 8;
+    CUtensorMap tmA, tmB;
+    memset(&tmA, 0, sizeof(tmA));
+    memset(&tmB, 0, sizeof(tmB));
+    if (tma) {
+        QF_CHECK(make_tmap(h, A, p->BM(), &tmA));
+        QF_CHECK(make_tmap(h, B, BK, &tmB));   // B boxes: BK rows x 8 complex
     }
+    if (p->m3)
+        launch_sk<true>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st);
+    else
+        launch_sk<false>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st);
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;

@@ -89,7 +89,8 @@ def test_norm_inf(qf, N):
 @pytest.mark.parametrize("N", [8, 33, 64, 100, 128, 129, 192, 256, 333, 512])
 def test_zgemm_vs_numpy(qf, N):
     """Complex FP64 DMMA GEMM against numpy (BLAS zgemm): both are fp64 dot products of length N, so the
-    difference is bounded by accumulation-order rounding, ~ sqrt(N) * eps relative to |A||B|."""
+    difference is bounded by accumulation-order rounding, ~ sqrt(N) * eps relative to |A||B| (the default 3M
+    arithmetic forms the imaginary part as T3 - T1 - T2, which roughly doubles the constant)."""
     from quflow_b200._cuda import get_handle
     rng = np.random.RandomState(N)
     A = rng.randn(N, N) + 1j * rng.randn(N, N)
@@ -97,7 +98,7 @@ def test_zgemm_vs_numpy(qf, N):
     C = get_handle(N).zgemm(to_dev(A), to_dev(B)).cpu().numpy()
     ref = A @ B
     bound = np.abs(A) @ np.abs(B)
-    assert (np.abs(C - ref) / bound).max() < 4e-16 * np.sqrt(N) + 1e-15
+    assert (np.abs(C - ref) / bound).max() < 1e-15 * np.sqrt(N) + 2e-15
     # exactness on small integers: any summation order gives the same result
     Ai = rng.randint(-3, 4, (N, N)) + 1j * rng.randint(-3, 4, (N, N))
     Bi = rng.randint(-3, 4, (N, N)) + 1j * rng.randint(-3, 4, (N, N))
