@@ -242,6 +242,10 @@ def gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = e2e_steps / float(t.item())
 
+    ph_sharded = None
+    if world > 1:
+        # collective: per-phase device times of the SHARDED iteration (eager launches, gathers not overlapped)
+        ph_sharded = handle.profile_iteration(torch.from_numpy(W0).to(dev), kw["dt"], reps=5)
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -307,6 +311,7 @@ def gpu_arm(args):
         "roofline": roofline,
         "roofline_poisson": roofline_poisson,
         "phase_ms": ph,
+        "phase_ms_sharded": ph_sharded,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -174,10 +174,12 @@ void qf_p2p_destroy(qf_handle_s *h)
     h->p2p = nullptr;
 }
 
-// kind 0: gather of A, kind 1: gather of S.  seq = 2 * gseq + kind + 1 is monotone over the life of the handle.
+// kind 0: gather of A (full rows), kind 1: gather of S (only the columns at or right of the diagonal block are
+// needed by k_post).  seq = 2 * gseq + kind + 1 is monotone over the life of the handle.
+// One warp per pulled row, 8 independent 16-byte loads in flight per lane.
 __global__ void __launch_bounds__(256)
 k_p2p_allgather(double2 *const *__restrict__ peers, unsigned long long *const *__restrict__ peer_flags,
-                volatile unsigned long long *my_flags, int rank, int nranks, size_t elems_per_rank, int kind,
+                volatile unsigned long long *my_flags, int rank, int nranks, int N, int hb, int kind,
                 const QfCtrl *__restrict__ ctrl, int gated)
 {
     if (gated && !ctrl[0].active) return;
@@ -195,14 +197,33 @@ k_p2p_allgather(double2 *const *__restrict__ peers, unsigned long long *const *_
     }
     __syncthreads();
     double2 *mine = peers[rank];
-    // pull every peer's contiguous row region; blocks stride over the concatenation of the (nranks - 1) regions
-    const size_t total = elems_per_rank * (size_t)(nranks - 1);
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int q = (int)(i / elems_per_rank);
+    const int lane = threadIdx.x & 31;
+    const int rows_per_rank = 2 * hb;
+    const int total_rows = rows_per_rank * (nranks - 1);
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total_rows; w += warps) {
+        const int q = w / rows_per_rank;
         const int src = q < rank ? q : q + 1;
-        const size_t off = (size_t)src * elems_per_rank + (i - (size_t)q * elems_per_rank);
-        mine[off] = __ldcg(peers[src] + off);
+        const int lr = w - q * rows_per_rank;                 // row inside the source's permuted region
+        const int prow = src * rows_per_rank + lr;            // permuted row index
+        int c0 = 0;
+        if (kind == 1) {
+            // logical row of this permuted row: slot 0 -> block src, slot 1 -> block 2G-1-src
+            const int blk = lr < hb ? src : 2 * nranks - 1 - src;
+            c0 = ((blk * hb) / 64) * 64;                      // k_post reads S only at columns >= its row (64-aligned tiles)
+        }
+        const double2 *__restrict__ s = peers[src] + (size_t)prow * N;
+        double2 *__restrict__ d = mine + (size_t)prow * N;
+        // 8 independent 16-byte NVLink loads in flight per lane before the first store
+        for (int c = c0 + lane; c < N; c += 32 * 8) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (c + 32 * u < N) v[u] = __ldcg(s + c + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (c + 32 * u < N) d[c + 32 * u] = v[u];
+        }
     }
 }
 
@@ -210,9 +231,8 @@ int qf_comm_p2p_allgather(qf_handle_s *h, int kind, bool gated, cudaStream_t st)
 {
     QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
     const int hb = qf_block_rows(h->N, h->nranks);
-    const size_t elems = (size_t)2 * hb * h->N;
-    k_p2p_allgather<<<h->sm_count * 2, 256, 0, st>>>(kind == 0 ? p->peerA_dev : p->peerS_dev, p->peerFlags_dev, p->flags,
-                                                     h->rank, h->nranks, elems, kind, h->ctrl, gated ? 1 : 0);
+    k_p2p_allgather<<<h->sm_count * 2, 256, 0, st>>>(kind == 0 ? p->peerA_dev : p->peerS_dev, p->peerFlags_dev, p->flags, h->rank,
+                                                 h->nranks, h->N, hb, kind, h->ctrl, gated ? 1 : 0);
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;

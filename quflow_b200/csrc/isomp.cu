@@ -10,6 +10,7 @@
 // The stopping rule lives in a device-resident control block (QfCtrl): all kernels of the iterations that
 // follow convergence return immediately, so a whole step is enqueued without any host synchronisation.
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 
 #include "qf_common.cuh"
@@ -333,6 +334,7 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
     QF_CHECK(qf_launch_poisson(h, h->Wh, nullptr, h->Wh, h->P, eps, true, st));
     if (ev) QF_CUDA(cudaEventRecord(ev[1], st));
     QF_CHECK(qf_launch_zgemm(h, h->P, h->Wh, h->A, false, true, my, G, false, st));        // rows of A = P~ W~
+    // (An overlapped A gather on a forked stream was tried: no gain, and two spin-waiting kernels sharing SMs can deadlock.)
     if (real_comm) QF_CHECK(h->comm_mode == 2 ? qf_comm_p2p_allgather(h, 0, true, st) : qf_comm_allgather_rows(h, h->A, st));
     if (ev) QF_CUDA(cudaEventRecord(ev[2], st));
     QF_CHECK(qf_launch_zgemm(h, h->A, h->P, h->S, true, true, my, G, true, st));          // rows of S = A P~ (A rows are local)
@@ -395,6 +397,7 @@ void qf_graph_destroy(qf_handle_s *h)
     h->step_graph = nullptr;
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     h->cap_stream = nullptr;
+
 }
 
 template <typename... Args>

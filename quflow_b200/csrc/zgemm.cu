@@ -437,6 +437,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuui
 struct QfGemmPlan {
     bool m3 = true;             // 3M (Karatsuba) arithmetic; QF_GEMM_3M=0 selects the 4-multiplication variant
     bool tma = true;
+    bool cooperative = true;    // QF_GEMM_COOP=0 uses a plain launch
     PFN_tmapEncodeTiled encode = nullptr;
     int max_ctas = 0;
     double2 *ws = nullptr;      // [max_ctas][32][256] partial tiles
@@ -456,6 +457,12 @@ int qf_gemm_create(qf_handle_s *h)
     const char *env = getenv("QF_GEMM_3M");
     p->m3 = !(env && env[0] == '0');
     p->max_ctas = h->sm_count;
+    {
+        const char *c = getenv("QF_GEMM_COOP");
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+        p->cooperative = coop && !(c && c[0] == '0');
+    }
     QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<false>::SMEM));
     QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<false>::SMEM));
     QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM));
@@ -569,15 +576,33 @@ int qf_gemm_prepare(qf_handle_s *h, int rank, int nranks)
     return QF_OK;
 }
 
-template <bool M3>
-static void launch_sk(qf_handle_s *h, bool tma, int G, const double2 *A, const double2 *B, double2 *C, const SkTile *tiles,
-                      int ntiles, int gated, const CUtensorMap &tmA, const CUtensorMap &tmB, cudaStream_t st)
+// The stream-K CTAs wait on one another (finisher <- contributors), so they must all be resident at the same time:
+// the launch is cooperative, which makes the driver co-schedule the whole grid (grid <= #SMs, 1 CTA/SM).
+template <bool M3, bool TMA>
+static cudaError_t launch_sk_impl(qf_handle_s *h, int G, const double2 *A, const double2 *B, double2 *C, const SkTile *tiles,
+                                  int ntiles, int gated, const CUtensorMap &tmA, const CUtensorMap &tmB, cudaStream_t st)
 {
     QfGemmPlan *p = h->gemm;
-    if (tma)
-        k_zgemm_sk<M3, true><<<G, GEMM_THREADS, Geo<M3>::SMEM, st>>>(A, B, C, h->N, tiles, ntiles, p->ws, p->flags, h->ctrl, gated, tmA, tmB);
-    else
-        k_zgemm_sk<M3, false><<<G, GEMM_THREADS, Geo<M3>::SMEM, st>>>(A, B, C, h->N, tiles, ntiles, p->ws, p->flags, h->ctrl, gated, tmA, tmB);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Geo<M3>::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p->cooperative ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_zgemm_sk<M3, TMA>, A, B, C, h->N, tiles, ntiles, p->ws, p->flags,
+                              (const QfCtrl *)h->ctrl, gated, tmA, tmB);
+}
+
+template <bool M3>
+static cudaError_t launch_sk(qf_handle_s *h, bool tma, int G, const double2 *A, const double2 *B, double2 *C, const SkTile *tiles,
+                             int ntiles, int gated, const CUtensorMap &tmA, const CUtensorMap &tmB, cudaStream_t st)
+{
+    return tma ? launch_sk_impl<M3, true>(h, G, A, B, C, tiles, ntiles, gated, tmA, tmB, st)
+               : launch_sk_impl<M3, false>(h, G, A, B, C, tiles, ntiles, gated, tmA, tmB, st);
 }
 
 // rank/nranks select the row blocks (see qf_prow); rank < 0 computes every rank's blocks (emulation on one GPU).
@@ -604,10 +629,8 @@ int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 
         QF_CHECK(make_tmap(h, A, p->BM(), &tmA));
         QF_CHECK(make_tmap(h, B, BK, &tmB));   // B boxes: BK rows x 8 complex
     }
-    if (p->m3)
-        launch_sk<true>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st);
-    else
-        launch_sk<false>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st);
+    QF_CUDA(p->m3 ? launch_sk<true>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st)
+                  : launch_sk<false>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st));
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;
