@@ -9,6 +9,7 @@ Public names follow the reference package (``import quflow as qf``):
 from .geometry import hbar  # noqa: F401
 from .laplacian import solve_poisson, laplace, select_first  # noqa: F401
 from .integrators import isomp, isomp_fixedpoint, isomp_ensemble  # noqa: F401
-from . import integrators, _cuda  # noqa: F401
+from .simulation import solve, QuSimulation  # noqa: F401
+from . import integrators, simulation, _cuda  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,0 +1,323 @@
+"""Driver and persistence around the hot path — drop-in for ``quflow.solve`` / ``quflow.QuSimulation``.
+
+Reference: quflow/simulation.py — ``solve`` (:584-802) and ``QuSimulation`` (:49-478).  These are the callers on
+either side of the accelerated path: ``solve`` chunks the run into output intervals and
+calls ``integrator(W, dt, steps=n, **kwargs)`` (:788); ``QuSimulation`` is the HDF5 store used as its callback.
+
+What is kept identical: argument names and meaning of ``solve``; the bookkeeping of ``time``/``steps``/``steps_out``;
+what the callbacks receive (``cfun(W, delta_time=, delta_steps=, **stats)``, :794-798); the HDF5 layout (group
+attributes ``version``, ``created``, ``qutypes``, ``loggers``, ``N``; datasets ``mat`` (T,N,N) chunked (1,N,N) with
+attribute ``qutype``; ``time`` float64 (T,), ``step`` int (T,); ``tol_auto``, ``iterations``, ``number_of_maxit``,
+user fields and logger outputs; sub-group ``args/`` holding the solver arguments, callables pickled — :128-146,
+357-431, 433-478) so files written here open with the reference and vice versa.
+
+What is new: when the integrator is this package's ``isomp`` the state stays on the GPU for the whole run; every
+output interval costs one device→host copy into pinned memory for the callbacks instead of a round trip per chunk.
+
+Only the ``mat`` representation is written (``fun``/``shr``/``shc`` need the spherical-harmonic transforms, which are
+outside the hot path).  h5py is imported lazily: it is not part of this image, and nothing on the compute path needs it.
+"""
+import datetime
+import inspect
+import os
+import pickle
+import warnings
+
+import numpy as np
+
+from .geometry import hbar
+from .integrators import isomp
+from .laplacian import solve_poisson, _is_torch
+
+__all__ = ["solve", "QuSimulation"]
+
+_PICKLED_ARGS = ('qutypes', 'hamiltonian', 'forcing', 'integrator', 'callback', 'integrator_callback', 'strang_splitting')
+_STAT_FIELDS = ('tol_auto', 'iterations', 'number_of_maxit')          # simulation.py:409-412
+
+
+def _h5py():
+    try:
+        import h5py
+    except ImportError as e:       # pragma: no cover - depends on the environment
+        raise ImportError("QuSimulation needs h5py (not installed in this environment); "
+                          "the compute path of quflow_b200 does not") from e
+    return h5py
+
+
+class QuSimulation(object):
+    """HDF5-backed simulation record, usable as the ``callback`` of :func:`solve` (simulation.py:49-478)."""
+
+    def __init__(self, filename, qutypes=None, datapath="/", overwrite=False, loggers=None, state=None, time=None,
+                 **fields):
+        if datapath[-1] != "/":
+            raise ValueError("Datapath must end with /")                       # simulation.py:110-111
+        self.filename = filename
+        self.datapath = datapath
+        self.args_datapath = datapath + "args/"
+        self.loggers = dict(loggers) if loggers else {}
+        self.fieldnames = {}
+        if not os.path.exists(filename) or overwrite:
+            if state is None:
+                raise ValueError("At least `state` must be provided to initialize a QuSimulation.")
+            self.qutypes = {'mat': None} if qutypes is None else dict(qutypes)
+            unsupported = [q for q in self.qutypes if q != 'mat']
+            if unsupported:
+                raise NotImplementedError("quflow_b200.QuSimulation stores the 'mat' representation only "
+                                          f"(got {unsupported}); fun/shr/shc need the SHT layer of the reference")
+            self._create(np.asarray(state), 0.0 if time is None else float(time), fields)
+        else:
+            if state is not None:
+                raise ValueError(filename + " has already been initialized with W.")
+            if qutypes is not None:
+                raise ValueError(filename + " has already been initialized with qutypes.")
+            with _h5py().File(filename, "r") as f:
+                g = f[self.datapath]
+                self.qutypes = pickle.loads(bytes(g.attrs["qutypes"][0]))
+                if "loggers" in g.attrs:
+                    self.loggers = pickle.loads(bytes(g.attrs["loggers"][0]))
+        self._refresh_fieldnames()
+
+    # ------------------------------------------------------------------ creation
+    def _create(self, W, time, fields):
+        h5 = _h5py()
+        with h5.File(self.filename, "w") as f:
+            g = f if self.datapath == "/" else f.create_group(self.datapath)
+            g = f[self.datapath]
+            g.attrs["version"] = _version()
+            g.attrs["created"] = datetime.datetime.now().isoformat()
+            g.attrs["qutypes"] = np.array([pickle.dumps(self.qutypes)])
+            try:
+                g.attrs["loggers"] = np.array([pickle.dumps(self.loggers)])
+            except (AttributeError, pickle.PicklingError):
+                pass
+            f.create_group(self.args_datapath)
+            dtype = self.qutypes['mat'] or W.dtype
+            arr = W.astype(dtype)
+            ds = f.create_dataset(self.datapath + "mat", (1,) + arr.shape, dtype=arr.dtype, maxshape=(None,) + arr.shape,
+                                  chunks=(1,) + arr.shape)
+            ds[0, ...] = arr
+            ds.attrs["qutype"] = "mat"
+            g.attrs["N"] = W.shape[-1]
+            f.create_dataset(self.datapath + "time", (1,), dtype=np.float64, maxshape=(None,))[0] = time
+            f.create_dataset(self.datapath + "step", (1,), dtype=int, maxshape=(None,))[0] = 0
+            for name, logger in self.loggers.items():
+                self._new_series(f, name, logger(W))
+            fields = dict(fields)
+            for name in _STAT_FIELDS:
+                fields.setdefault(name, 0.0)
+            for name, value in fields.items():
+                if name in ("time", "step"):
+                    raise ValueError("{} is not a valid field name.".format(name))
+                self._new_series(f, name, value)
+
+    def _new_series(self, f, name, value):
+        arr = np.asarray(value)
+        ds = f.create_dataset(self.datapath + name, (1,) + arr.shape, dtype=arr.dtype, maxshape=(None,) + arr.shape)
+        ds[0, ...] = arr
+
+    def _refresh_fieldnames(self):
+        with _h5py().File(self.filename, "r") as f:
+            g = f[self.datapath]
+            for name in g.keys():
+                item = g[name]
+                if hasattr(item, "shape") and hasattr(item, "dtype"):
+                    self.fieldnames[name] = (tuple(item.shape), item.dtype)
+
+    # ------------------------------------------------------------------ callback protocol
+    def __call__(self, W, delta_time, delta_steps=1, **kwargs):
+        """Append one output record (simulation.py:433-478)."""
+        W = np.asarray(W)
+        with _h5py().File(self.filename, "r+") as f:
+            def push(name, value):
+                ds = f[self.datapath + name]
+                ds.resize(ds.shape[0] + 1, axis=0)
+                ds[-1, ...] = value
+                return ds
+
+            ds = f[self.datapath + "mat"]
+            push("mat", W.astype(ds.dtype))
+            t = f[self.datapath + "time"]
+            push("time", t[-1] + delta_time)
+            s = f[self.datapath + "step"]
+            push("step", s[-1] + delta_steps)
+            for name, value in kwargs.items():
+                if self.datapath + name in f and name not in self.loggers:
+                    push(name, value)
+            for name, logger in self.loggers.items():
+                push(name, logger(W))
+
+    # ------------------------------------------------------------------ access
+    def __setitem__(self, name, value):
+        with _h5py().File(self.filename, "r+") as f:
+            target = f[self.datapath] if name in ("prerun", "info") else f[self.args_datapath]
+            if value is None:
+                if name in target.attrs:
+                    del target.attrs[name]
+            elif name in _PICKLED_ARGS:
+                try:
+                    target.attrs[name] = np.array([pickle.dumps(value)])
+                except (AttributeError, pickle.PicklingError):
+                    target.attrs[name] = value.__name__
+            else:
+                target.attrs[name] = value
+
+    def __getitem__(self, key):
+        index = None
+        if isinstance(key, tuple) and isinstance(key[0], str):
+            index = key[1:] if len(key) > 2 else key[1]
+            key = key[0]
+        elif not isinstance(key, str):
+            index, key = key, "mat"
+        with _h5py().File(self.filename, "r") as f:
+            if self.datapath + key in f:
+                ds = f[self.datapath + key]
+                return ds[index] if index is not None else ds[:]
+            a = f[self.args_datapath].attrs
+            if key in a:
+                v = a[key]
+                if key in _PICKLED_ARGS:
+                    return _named(v) if isinstance(v, str) else pickle.loads(bytes(v[0]))
+                return v
+            g = f[self.datapath].attrs
+            if key in g:
+                return pickle.loads(bytes(g[key][0])) if key in ("qutypes", "loggers") else g[key]
+        raise KeyError("There is no dataset or attribute '{}'.".format(key))
+
+    def args(self):
+        with _h5py().File(self.filename, "r") as f:
+            names = list(f[self.args_datapath].attrs)
+        for name in names:
+            yield name, self[name]
+
+
+def _version():
+    from . import __version__
+    return __version__
+
+
+def _named(name):
+    """Resolve a callable stored by name (the reference evals the string, simulation.py:268)."""
+    import quflow_b200 as qf
+    return getattr(qf, name.split(".")[-1])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def solve(W,
+          dt=None,
+          stepsize=None,
+          steps=None,
+          simtime=None,
+          endtime=None,
+          steps_out=None,
+          dt_out=None,
+          integrator=None,
+          callback=None,
+          callback_kwargs=None,
+          integrator_callback=None,
+          progress_bar=True,
+          progress_file=None,
+          **kwargs):
+    """High-level solve loop (reference: quflow/simulation.py:584-802; same arguments and bookkeeping).
+
+    ``W`` is a (N, N) complex128 numpy array (updated in place, as with the reference's in-place integrators), a torch
+    CUDA tensor, or a :class:`QuSimulation` to continue from.  With this package's ``isomp`` (the default) the state
+    lives on the GPU between output intervals.
+    """
+    time = kwargs.get('time', 0.0)
+
+    # continue from a stored simulation (simulation.py:654-710)
+    if isinstance(W, QuSimulation):
+        sim = W
+        W = np.ascontiguousarray(sim['mat', -1])
+        time = float(sim['time', -1])
+        callback = sim if callback is None else (tuple(callback) if isinstance(callback, tuple) else (callback,)) + (sim,)
+        stored = dict(sim.args())
+        pick = lambda cur, *names: next((stored[n] for n in names if cur is None and n in stored), cur)   # noqa: E731
+        dt, stepsize, steps = pick(dt, 'dt'), pick(stepsize, 'stepsize'), pick(steps, 'steps')
+        simtime, endtime = pick(simtime, 'simtime'), pick(endtime, 'endtime')
+        steps_out, dt_out = pick(steps_out, 'steps_out', 'inner_steps'), pick(dt_out, 'dt_out', 'inner_time')
+        integrator = pick(integrator, 'integrator')
+        integrator_callback = pick(integrator_callback, 'integrator_callback', 'callback')
+        callback_kwargs = pick(callback_kwargs, 'callback_kwargs')
+        handled = {'dt', 'stepsize', 'steps', 'simtime', 'endtime', 'steps_out', 'inner_steps', 'dt_out', 'inner_time',
+                   'integrator', 'integrator_callback', 'callback', 'callback_kwargs', 'progress_bar', 'progress_file'}
+        for name, value in stored.items():
+            if name not in handled:
+                kwargs.setdefault(name, value)
+
+    N = W.shape[-1]
+    if dt is None:                                                        # simulation.py:716-719
+        if stepsize is None:
+            raise ValueError("Either `dt` or `stepsize` must be specified.")
+        dt = stepsize * hbar(N=N)
+    if integrator is None:                                                # :722-723
+        integrator = isomp
+
+    ikw = kwargs                                                          # :726-733
+    ikw['time'] = time
+    ikw.setdefault('hamiltonian', solve_poisson)
+    if 'stats' in inspect.getfullargspec(integrator).args:
+        ikw['stats'] = {'iterations': 0.0}
+    if integrator_callback is not None:
+        ikw['callback'] = integrator_callback
+
+    if sum(x is not None for x in (steps, simtime, endtime)) != 1:        # :736-737
+        warnings.warn("One, and only one, of `steps`, `simtime`, or `endtime` should be specified.")
+    if endtime is not None:
+        if endtime < time:
+            raise ValueError("Specified `endtime`={} is smaller than current `time`={}.".format(endtime, time))
+        simtime = endtime - time
+    if simtime is not None:
+        steps = round(simtime / np.abs(dt))                               # :745
+    if callback is not None and not isinstance(callback, tuple):
+        callback = (callback,)
+    if callback_kwargs is None:
+        callback_kwargs = dict()
+    if steps_out is None:                                                 # :752-758
+        steps_out = 100 if dt_out is None else round(dt_out / np.abs(dt))
+    steps_out = max(1, min(steps_out, steps)) if steps > 0 else 1         # :761-762
+
+    pbar = None
+    if progress_bar and not ikw.get('verbatim', False):                   # :765-779
+        try:
+            from tqdm import tqdm
+            pbar = tqdm(total=steps, unit=' steps', file=progress_file, ascii=progress_file is not None,
+                        mininterval=10.0 if progress_file is not None else 0.1)
+        except Exception:
+            pbar = None
+
+    # device-resident fast path: keep the state on the GPU across output intervals
+    host_out = None
+    Wdev = W
+    on_device = integrator is isomp and not _is_torch(W)
+    if on_device:
+        import torch
+        if not (isinstance(W, np.ndarray) and W.dtype == np.complex128 and W.flags.c_contiguous and W.ndim == 2):
+            on_device = False
+        else:
+            Wdev = torch.from_numpy(W).to("cuda", non_blocking=False)
+            host_out = torch.empty(W.shape, dtype=torch.complex128).pin_memory()
+
+    for k in range(0, steps, steps_out):                                  # :782
+        n = min(steps_out, steps - k)
+        Wdev = integrator(Wdev, dt, steps=n, **ikw)                       # :788
+        delta_time = n * dt
+        ikw['time'] += delta_time
+        if pbar is not None:
+            pbar.update(n)
+        if callback is not None:
+            if on_device:
+                host_out.copy_(Wdev)                                      # one D2H per output record
+                Wcb = host_out.numpy()
+            else:
+                Wcb = Wdev
+            if 'stats' in ikw:
+                callback_kwargs.update(ikw['stats'])                      # :796-797
+            for cfun in callback:
+                cfun(Wcb, delta_time=delta_time, delta_steps=n, **callback_kwargs)
+    if pbar is not None:
+        pbar.close()
+    if on_device:
+        W[...] = Wdev.cpu().numpy()                                       # the caller's array ends up advanced, as with the reference
+        return W
+    return Wdev
