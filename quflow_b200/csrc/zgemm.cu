@@ -137,60 +137,104 @@ __device__ __forceinline__ void load_stage(uint32_t sA, uint32_t sB, const doubl
     }
 }
 
-// ---- the DMMA inner product over one resident stage (4 k-steps of 4) ---------------------------------------
+// ---- the DMMA inner product over one resident stage (BK/4 k-steps of 4) -----------------------------------
+// Fragments are double-buffered in registers: the LDS.128 (and, for 3M, the DADDs forming Are+Aim / Bre+Bim) of
+// k-step ks+1 are issued before the DMMAs of k-step ks, so the tensor pipe never waits on shared-memory latency
+// inside a stage.
+template <bool M3>
+struct Frag {
+    double a_re[MI], a_im[MI], a_x[MI], b_re[Cfg<M3>::NJ], b_im[Cfg<M3>::NJ], b_x[Cfg<M3>::NJ];
+};
+
+template <bool M3>
+__device__ __forceinline__ void gemm_load_frag(Frag<M3> &f, uint32_t sb, const uint32_t (&a_off)[2], const uint32_t (&b_off)[2],
+                                               int ks)
+{
+    constexpr int BM = Cfg<M3>::BM, NJ = Cfg<M3>::NJ, BK = Cfg<M3>::BK;
+    const int hh = ks >> 1, s = ks & 1;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const double2 v = lds128(sb + a_off[s] + hh * (BM * 128) + i * 1024);
+        f.a_re[i] = v.x;
+        f.a_im[i] = v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const double2 v = lds128(sb + b_off[s] + hh * 1024 + j * (BK * 128));
+        f.b_re[j] = v.x;
+        f.b_im[j] = v.y;
+    }
+}
+
+// derived operands: 3M  Are+Aim, Bre+Bim (DADD on the FP64 pipe);  4M  -Aim (integer XOR)
+template <bool M3>
+__device__ __forceinline__ void gemm_finish_frag(Frag<M3> &f)
+{
+#pragma unroll
+    for (int i = 0; i < MI; ++i) f.a_x[i] = M3 ? (f.a_re[i] + f.a_im[i]) : flip_sign(f.a_im[i]);
+#pragma unroll
+    for (int j = 0; j < Cfg<M3>::NJ; ++j) f.b_x[j] = M3 ? (f.b_re[j] + f.b_im[j]) : 0.0;
+}
+
+template <bool M3>
+__device__ __forceinline__ void gemm_mma_frag(double (&acc)[MI][Cfg<M3>::NJ][Cfg<M3>::NACC][2], const Frag<M3> &f)
+{
+    constexpr int NJ = Cfg<M3>::NJ;
+    if (M3) {
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0][0], acc[i][j][0][1], f.a_re[i], f.b_re[j]);   // T1
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][1][0], acc[i][j][1][1], f.a_im[i], f.b_im[j]);   // T2
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][2][0], acc[i][j][2][1], f.a_x[i], f.b_x[j]);     // T3
+    } else {
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                dmma884(acc[i][j][0][0], acc[i][j][0][1], f.a_re[i], f.b_re[j]);
+                dmma884(acc[i][j][1][0], acc[i][j][1][1], f.a_re[i], f.b_im[j]);
+            }
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                dmma884(acc[i][j][0][0], acc[i][j][0][1], f.a_x[i], f.b_im[j]);
+                dmma884(acc[i][j][1][0], acc[i][j][1][1], f.a_im[i], f.b_re[j]);
+            }
+    }
+}
+
 template <bool M3>
 __device__ __forceinline__ void gemm_compute_stage(double (&acc)[MI][Cfg<M3>::NJ][Cfg<M3>::NACC][2], uint32_t sb,
                                                    const uint32_t (&a_off)[2], const uint32_t (&b_off)[2])
 {
-    constexpr int BM = Cfg<M3>::BM, NJ = Cfg<M3>::NJ, BK = Cfg<M3>::BK;
+    constexpr int KS = Cfg<M3>::BK / 4;
+    if (M3) {
+        // order per k-step: LDS(ks+1) -> DMMAs(ks) -> DADDs(ks+1): the in-order warp never waits on the LDS
+        Frag<M3> f[2];
+        gemm_load_frag<M3>(f[0], sb, a_off, b_off, 0);
+        gemm_finish_frag<M3>(f[0]);
 #pragma unroll
-    for (int hh = 0; hh < BK / 8; ++hh) {
+        for (int ks = 0; ks < KS; ++ks) {
+            if (ks + 1 < KS) gemm_load_frag<M3>(f[(ks + 1) & 1], sb, a_off, b_off, ks + 1);
+            gemm_mma_frag<M3>(acc, f[ks & 1]);
+            if (ks + 1 < KS) gemm_finish_frag<M3>(f[(ks + 1) & 1]);
+        }
+    } else {
+        // the 4M variant already runs at the register limit (128 accumulator registers): single-buffered fragments
+        Frag<M3> f;
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            double a_re[MI], a_im[MI], a_x[MI], b_re[NJ], b_im[NJ], b_x[NJ];
-#pragma unroll
-            for (int i = 0; i < MI; ++i) {
-                const double2 v = lds128(sb + a_off[s] + hh * (BM * 128) + i * 1024);
-                a_re[i] = v.x;
-                a_im[i] = v.y;
-                a_x[i] = M3 ? (v.x + v.y) : flip_sign(v.y);   // 3M: Are+Aim   4M: -Aim
-            }
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const double2 v = lds128(sb + b_off[s] + hh * 1024 + j * (BK * 128));
-                b_re[j] = v.x;
-                b_im[j] = v.y;
-                b_x[j] = M3 ? (v.x + v.y) : 0.0;
-            }
-            if (M3) {
-#pragma unroll
-                for (int i = 0; i < MI; ++i)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0][0], acc[i][j][0][1], a_re[i], b_re[j]);   // T1
-#pragma unroll
-                for (int i = 0; i < MI; ++i)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][1][0], acc[i][j][1][1], a_im[i], b_im[j]);   // T2
-#pragma unroll
-                for (int i = 0; i < MI; ++i)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][2][0], acc[i][j][2][1], a_x[i], b_x[j]);     // T3
-            } else {
-#pragma unroll
-                for (int i = 0; i < MI; ++i)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        dmma884(acc[i][j][0][0], acc[i][j][0][1], a_re[i], b_re[j]);
-                        dmma884(acc[i][j][1][0], acc[i][j][1][1], a_re[i], b_im[j]);
-                    }
-#pragma unroll
-                for (int i = 0; i < MI; ++i)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        dmma884(acc[i][j][0][0], acc[i][j][0][1], a_x[i], b_im[j]);
-                        dmma884(acc[i][j][1][0], acc[i][j][1][1], a_im[i], b_re[j]);
-                    }
-            }
+        for (int ks = 0; ks < KS; ++ks) {
+            gemm_load_frag<M3>(f, sb, a_off, b_off, ks);
+            gemm_finish_frag<M3>(f);
+            gemm_mma_frag<M3>(acc, f);
         }
     }
 }
@@ -428,6 +472,157 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
     }
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// ---- warp-specialised stream-K kernel (3M arithmetic, TMA) ------------------------------------------------------
+// Warp 8 is the producer: one lane walks the same (tile, k) segments as the consumers and keeps the STAGES-deep ring
+// full (wait `empty`, arm `full` with expect_tx, issue the TMA boxes).  Warps 0-7 are the DMMA consumers: wait `full`,
+// multiply, one arrive per warp on `empty`.  There is no CTA-wide barrier in the main loop, the producer runs ahead
+// across tile boundaries while the consumers do the stream-K fix-up / store, and only the 256 consumer threads meet
+// at the (named) barrier around the fix-up.
+constexpr int WS_THREADS = GEMM_THREADS + 32;
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, int ntiles, double2 *__restrict__ ws,
+             int *__restrict__ flags, const QfCtrl *__restrict__ ctrl, int gated, const __grid_constant__ CUtensorMap tmA,
+             const __grid_constant__ CUtensorMap tmB)
+{
+    constexpr bool M3 = true;
+    constexpr int STAGES = Cfg<M3>::STAGES, NJ = Cfg<M3>::NJ, NACC = Cfg<M3>::NACC, WN = Cfg<M3>::WN;
+    constexpr int BM = Cfg<M3>::BM, BN = Cfg<M3>::BN, BK = Cfg<M3>::BK;
+    constexpr int STAGE_BYTES = Geo<M3>::STAGE_BYTES, A_STAGE_BYTES = Geo<M3>::A_STAGE_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
+    __shared__ __align__(8) unsigned long long bar_full[STAGES], bar_empty[STAGES];
+    const uint32_t full = (uint32_t)__cvta_generic_to_shared(bar_full);
+    const uint32_t empty = (uint32_t)__cvta_generic_to_shared(bar_empty);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full + 8 * s, 1);
+            mbar_init(empty + 8 * s, GEMM_THREADS / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int cta = blockIdx.x, G = gridDim.x;
+    const int KT = (N + BK - 1) / BK;
+    const long long T = (long long)ntiles * KT;
+    long long it = T * cta / G;
+    const long long it_end = T * (cta + 1) / G;
+    uint32_t gk = 0;
+
+    if (warp == GEMM_THREADS / 32) {
+        // ===== producer =====
+        if (lane == 0) {
+            while (it < it_end) {
+                const int tile = (int)(it / KT);
+                const int ka = (int)(it - (long long)tile * KT);
+                const int kb = (int)min((long long)KT, ka + (it_end - it));
+                const SkTile ti = tiles[tile];
+                it += kb - ka;
+                if (gated && !ctrl[ti.member].active) continue;
+                for (int kt = ka; kt < kb; ++kt, ++gk) {
+                    const uint32_t stage = gk % STAGES;
+                    const uint32_t round = gk / STAGES;
+                    if (round > 0) mbar_wait(empty + 8 * stage, (round - 1) & 1);   // consumers released the previous fill
+                    const uint32_t sb = smem_base + stage * STAGE_BYTES;
+                    const uint32_t bar = full + 8 * stage;
+                    const int k0 = kt * BK;
+                    mbar_arrive_expect_tx(bar, STAGE_BYTES);
+#pragma unroll
+                    for (int hh = 0; hh < BK / 8; ++hh)
+                        tma_load_3d(sb + hh * (BM * 128), &tmA, 2 * (k0 + 8 * hh), ti.op_row0, ti.member, bar);
+#pragma unroll
+                    for (int c = 0; c < BN / 8; ++c)
+                        tma_load_3d(sb + A_STAGE_BYTES + c * (BK * 128), &tmB, 2 * (ti.col0 + 8 * c), k0, ti.member, bar);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int wm = warp / WN, wn = warp % WN;
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t a_off[2], b_off[2];
+    gemm_frag_offsets<M3>(a_off, b_off, wm, wn, g, t);
+    while (it < it_end) {
+        const int tile = (int)(it / KT);
+        const int ka = (int)(it - (long long)tile * KT);
+        const int kb = (int)min((long long)KT, ka + (it_end - it));
+        const SkTile ti = tiles[tile];
+        it += kb - ka;
+        if (gated && !ctrl[ti.member].active) continue;
+        const size_t moff = (size_t)ti.member * N * N;
+
+        double acc[MI][NJ][NACC][2];
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                for (int c = 0; c < NACC; ++c) acc[i][j][c][0] = acc[i][j][c][1] = 0.0;
+
+        for (int kt = ka; kt < kb; ++kt, ++gk) {
+            const uint32_t stage = gk % STAGES;
+            mbar_wait(full + 8 * stage, (gk / STAGES) & 1);
+            gemm_compute_stage<M3>(acc, smem_base + stage * STAGE_BYTES, a_off, b_off);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + 8 * stage);
+        }
+
+        if (ka > 0) {
+            double2 *slot = ws + (size_t)cta * (WS_D2_PER_THREAD * GEMM_THREADS);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                    for (int c = 0; c < NACC; ++c)
+                        __stcg(slot + ((i * NJ + j) * NACC + c) * GEMM_THREADS + tid, make_double2(acc[i][j][c][0], acc[i][j][c][1]));
+            __threadfence();
+            consumer_bar_sync();
+            if (tid == 0) atomicExch(flags + cta, 1);
+        } else {
+            if (kb < KT) {
+                const long long tile_end = (long long)(tile + 1) * KT;
+                int peer = cta + 1;
+                long long covered = it_end;
+                while (covered < tile_end) {
+                    if (tid == 0) {
+                        while (atomicAdd(flags + peer, 0) == 0) __nanosleep(64);
+                        atomicExch(flags + peer, 0);
+                    }
+                    consumer_bar_sync();
+                    __threadfence();
+                    const double2 *slot = ws + (size_t)peer * (WS_D2_PER_THREAD * GEMM_THREADS);
+#pragma unroll
+                    for (int i = 0; i < MI; ++i)
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                            for (int c = 0; c < NACC; ++c) {
+                                const double2 p = __ldcg(slot + ((i * NJ + j) * NACC + c) * GEMM_THREADS + tid);
+                                acc[i][j][c][0] += p.x;
+                                acc[i][j][c][1] += p.y;
+                            }
+                    covered = T * (peer + 1) / G;
+                    ++peer;
+                }
+            }
+            gemm_store_tile<M3>(acc, Cg + moff, N, ti.c_row0, ti.c_row0 + (ti.row_end - ti.a_row0), ti.col0, wm, wn, g, t);
+        }
+    }
+}
+
 }   // namespace
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -438,6 +633,7 @@ struct QfGemmPlan {
     bool m3 = true;             // 3M (Karatsuba) arithmetic; QF_GEMM_3M=0 selects the 4-multiplication variant
     bool tma = true;
     bool cooperative = true;    // QF_GEMM_COOP=0 uses a plain launch
+    bool warp_spec = true;      // QF_GEMM_WS=0: no producer warp (all 8 warps load through one elected thread)
     PFN_tmapEncodeTiled encode = nullptr;
     int max_ctas = 0;
     double2 *ws = nullptr;      // [max_ctas][32][256] partial tiles
@@ -467,6 +663,11 @@ int qf_gemm_create(qf_handle_s *h)
     QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<false>::SMEM));
     QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM));
     QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm3m_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM));
+    {
+        const char *w = getenv("QF_GEMM_WS");
+        p->warp_spec = !(w && w[0] == '0');
+    }
     {
         const char *ld = getenv("QF_GEMM_LOAD");
         p->tma = !(ld && strcmp(ld, "cpasync") == 0);
@@ -629,8 +830,23 @@ int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 
         QF_CHECK(make_tmap(h, A, p->BM(), &tmA));
         QF_CHECK(make_tmap(h, B, BK, &tmB));   // B boxes: BK rows x 8 complex
     }
-    QF_CUDA(p->m3 ? launch_sk<true>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st)
-                  : launch_sk<false>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st));
+    if (p->m3 && tma && p->warp_spec) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(G);
+        cfg.blockDim = dim3(WS_THREADS);
+        cfg.dynamicSmemBytes = Geo<true>::SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = p->cooperative ? 1 : 0;
+        QF_CUDA(cudaLaunchKernelEx(&cfg, k_zgemm3m_ws, C, N, tiles, ntiles, p->ws, p->flags, (const QfCtrl *)h->ctrl,
+                                   gated ? 1 : 0, tmA, tmB));
+    } else {
+        QF_CUDA(p->m3 ? launch_sk<true>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st)
+                      : launch_sk<false>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st));
+    }
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;
