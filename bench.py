@@ -11,7 +11,7 @@ A "step" is one isospectral-midpoint time step.
 * ``value``  : steps/s with W resident in HBM, timed with CUDA events over exactly K steps (max over ranks).
 * ``e2e``    : the same metric through the public Python API with HOST buffers (numpy in pinned memory): every step
                is one ``qf.isomp(W_host, dt, steps=1)`` call = H2D copy of W + one step + D2H copy of W.
-* ``roofline``: the dominant kernel (k_zgemm, FP64 DMMA) — executed flops per launch / CUDA-event launch time,
+* ``roofline``: the dominant kernel (k_zgemm3m_ws, FP64 DMMA) — EXECUTED flops per launch / CUDA-event launch time,
                against the FP64 tensor peak measured on this pool (MEASURED_PEAKS.json has no FP64 entry; see
                profiles/r01_fp64_pipes.txt).  ``roofline_poisson`` reports the HBM-bound Poisson solve against
                MEASURED_PEAKS.json's copy bandwidth.
@@ -54,6 +54,22 @@ def mode_kwargs(mode, N):
     if mode == "profile":   # the reference's own protocol, profiling/run_profiling.py:124-127
         return dict(dt=0.01 * hbar(N), maxit=10, minit=10)
     return dict(dt=0.25 * hbar(N), maxit=10, minit=1)
+
+
+def ncu_traffic(kernel_prefix, index=0):
+    """DRAM bytes (read + write) per launch of a kernel from the committed `ncu --set full` capture
+    (profiles/r01_ncu_full_kernels.json, N=2048); None for other sizes or when the file is missing."""
+    try:
+        rows = [r for r in json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_kernels.json")))
+                if r["kernel"].startswith(kernel_prefix)]
+        r = rows[index]
+
+        def to_bytes(txt):
+            val, unit = txt.split()
+            return float(val) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        return to_bytes(r["dram_read"]) + to_bytes(r["dram_write"])
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -271,7 +287,9 @@ def gpu_arm(args):
     roofline = {
         "bound": "tensor", "kernel": kname,
         "achieved": gemm1_tf, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gemm1_tf / FP64_TENSOR_PEAK_TFLOPS,
-        "traffic": None,
+        "traffic": ncu_traffic("k_zgemm3m_ws") if (N == 2048 and is3m) else None,
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full capture at N=2048 "
+                        "(profiles/r01_ncu_full_kernels.json); algorithmic operand bytes 3*16*N^2",
         "peak_source": "measured FP64 DMMA issue peak on this pool's B200 (profiles/r01_fp64_pipes.txt); "
                        "MEASURED_PEAKS.json has no FP64 entry, datasheet ~37-40 TF/s",
         "launch_ms": ph["gemm1_ms"],
@@ -282,7 +300,8 @@ def gpu_arm(args):
     }
     roofline_poisson = {
         "bound": "hbm", "kernel": "W~=W+dW, P~=eps*Laplace^-1 W~ (32 N^2 algorithmic bytes)", "achieved": pois_gbs,
-        "peak": hbm, "unit": "GB/s", "frac": pois_gbs / hbm, "traffic": None, "launch_ms": ph["poisson_ms"],
+        "peak": hbm, "unit": "GB/s", "frac": pois_gbs / hbm,
+        "traffic": ncu_traffic("k_poisson_scan") if N == 2048 else None, "launch_ms": ph["poisson_ms"],
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "B200_PROFILING.md fallback 6.65 TB/s (of fallback)",
     }
 

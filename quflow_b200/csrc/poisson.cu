@@ -214,18 +214,38 @@ k_poisson_scan(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
 
     double2 r[L];
     double w[L + 1];                     // w[L] = w of the first position of the next chunk
+    // Element (k, k+m) sits at flat index k (N+1) + m; its mirror (k+m, k) at k (N+1) + m N: both walk with stride N+1.
+    // N <= 2048 so flat indices fit 32 bits.
+    const unsigned stride = (unsigned)N + 1u;
+    const unsigned e0 = (unsigned)k0 * stride + (unsigned)m;
+    const int nvalid = min(L, max(0, n - k0));
+    extern __shared__ double iu_s[];     // [L][blockDim.x]: 1/u of this thread's chunk, prefetched while the forward sweep runs
+    const uint32_t iu_base = (uint32_t)__cvta_generic_to_shared(iu_s) + (uint32_t)tid * 8u;
+    const uint32_t iu_pitch = blockDim.x * 8u;
+    if (nvalid == L) {
+        const double2 *rp = R + e0;
+        const double *wp = tw + e0;
+        const double *up = tiu + e0;
 #pragma unroll
-    for (int i = 0; i < L; ++i) {
-        const int k = k0 + i;
-        const bool ok = k < n;
-        const size_t idx = (size_t)k * N + (k + m);
-        r[i] = ok ? R[idx] : make_double2(0.0, 0.0);
-        w[i] = ok ? __ldg(tw + idx) : 0.0;
+        for (int i = 0; i < L; ++i) {
+            r[i] = rp[(size_t)i * stride];
+            w[i] = __ldg(wp + (size_t)i * stride);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(iu_base + i * iu_pitch), "l"(up + (size_t)i * stride));
+        }
+        w[L] = (k0 + L < n) ? __ldg(wp + (size_t)L * stride) : 0.0;
+    } else {
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+            const bool ok = i < nvalid;
+            const unsigned idx = ok ? e0 + (unsigned)i * stride : 0u;
+            r[i] = ok ? R[idx] : make_double2(0.0, 0.0);
+            w[i] = ok ? __ldg(tw + idx) : 0.0;
+            const int sz = ok ? 8 : 0;       // src-size 0: zero fill
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(iu_base + i * iu_pitch), "l"(tiu + idx), "r"(sz));
+        }
+        w[L] = 0.0;
     }
-    {
-        const int k = k0 + L;
-        w[L] = (k < n) ? __ldg(tw + (size_t)k * N + (k + m)) : 0.0;
-    }
+    asm volatile("cp.async.commit_group;");
 
     // ---- m = 0: remove the mean of the diagonal from the right-hand side (cpu.py:311-317,327-328)
     if (m0 == 0) {
@@ -294,12 +314,12 @@ k_poisson_scan(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
         carry.y = xA * pBy + xBy;
     }
     // ---- forward, pass 2 from the true carry-in; r becomes z = c / u
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's own 1/u values (no cross-thread sharing)
 #pragma unroll
     for (int i = 0; i < L; ++i) {
-        const int k = k0 + i;
         carry.x = r[i].x - w[i] * carry.x;
         carry.y = r[i].y - w[i] * carry.y;
-        const double iu = (k < n) ? __ldg(tiu + (size_t)k * N + (k + m)) : 0.0;
+        const double iu = iu_s[i * blockDim.x + tid];
         r[i].x = carry.x * iu;
         r[i].y = carry.y * iu;
     }
@@ -378,13 +398,25 @@ k_poisson_scan(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
     }
 
     // ---- store P = eps x and its skew-Hermitian mirror (cpu.py:334,340; isospectral.py:492)
+    {
+        double2 *xp = X + e0;
+        double2 *xm = X + (unsigned)k0 * stride + (unsigned)m * (unsigned)N;
+        if (nvalid == L && m != 0) {
 #pragma unroll
-    for (int i = 0; i < L; ++i) {
-        const int k = k0 + i;
-        if (k < n) {
-            const double2 v = make_double2(eps * r[i].x, eps * r[i].y);
-            X[(size_t)k * N + (k + m)] = v;
-            if (m != 0) X[(size_t)(k + m) * N + k] = make_double2(-v.x, v.y);
+            for (int i = 0; i < L; ++i) {
+                const double2 v = make_double2(eps * r[i].x, eps * r[i].y);
+                xp[(size_t)i * stride] = v;
+                xm[(size_t)i * stride] = make_double2(-v.x, v.y);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < L; ++i) {
+                if (i < nvalid) {
+                    const double2 v = make_double2(eps * r[i].x, eps * r[i].y);
+                    xp[(size_t)i * stride] = v;
+                    if (m != 0) xm[(size_t)i * stride] = make_double2(-v.x, v.y);
+                }
+            }
         }
     }
 }
@@ -436,22 +468,27 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
         h->launches++;
     }
     if (N <= 2048) {
-        // chunked scan: GS diagonals per CTA, 16 positions per thread (QF_POISSON_GS=2|4, default 2: two CTAs per SM
-        // overlap each other's load / solve / store phases)
+        // chunked scan: GS diagonals per CTA, 16 positions per thread (QF_POISSON_GS=2|4, default 4)
         const int chunks = (N + 15) / 16;
+        static bool attr_done = false;
+        if (!attr_done) {
+            QF_CUDA(cudaFuncSetAttribute(k_poisson_scan<16, 4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 16 * 8));
+            QF_CUDA(cudaFuncSetAttribute(k_poisson_scan<16, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 16 * 8));
+            attr_done = true;
+        }
         static int gs = 0;
         if (!gs) {
             const char *env = getenv("QF_POISSON_GS");
-            gs = (env && env[0] == '4') ? 4 : 2;
+            gs = (env && env[0] == '2') ? 2 : 4;
         }
         if (gs == 4) {
             const int threads = ((4 * chunks + 31) / 32) * 32;
             dim3 grid((N + 3) / 4, h->batch);
-            k_poisson_scan<16, 4, 512><<<grid, threads, 0, st>>>(Wh, P, h->tab_w, h->tab_iu, N, eps, h->ctrl, g);
+            k_poisson_scan<16, 4, 512><<<grid, threads, threads * 16 * sizeof(double), st>>>(Wh, P, h->tab_w, h->tab_iu, N, eps, h->ctrl, g);
         } else {
             const int threads = ((2 * chunks + 31) / 32) * 32;
             dim3 grid((N + 1) / 2, h->batch);
-            k_poisson_scan<16, 2, 256><<<grid, threads, 0, st>>>(Wh, P, h->tab_w, h->tab_iu, N, eps, h->ctrl, g);
+            k_poisson_scan<16, 2, 256><<<grid, threads, threads * 16 * sizeof(double), st>>>(Wh, P, h->tab_w, h->tab_iu, N, eps, h->ctrl, g);
         }
         h->launches++;
     } else {
