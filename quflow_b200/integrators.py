@@ -109,6 +109,10 @@ def isomp_ensemble(W, dt, steps=100, stats=None, tol='auto', maxit=10, minit=1, 
         raise ValueError("isomp_ensemble expects a (k, N, N) array")
     Wc = _prepare(W)
     k, N = Wc.shape[0], Wc.shape[-1]
+    if k == 0:              # an empty member slice (more ranks than members) is a no-op
+        if stats is not None:
+            del stats[:]
+        return (W, np.zeros((0, steps), dtype=np.int32)) if return_iterations else W
     auto = (isinstance(tol, str) and tol == 'auto') or (not isinstance(tol, str) and tol < 0)
     handle = get_handle(N, k, Wc.device.index if _is_torch(Wc) else None)
     res, iters = handle.isomp(Wc, dt, steps, tol=-1.0 if auto else float(tol), maxit=maxit, minit=minit,
