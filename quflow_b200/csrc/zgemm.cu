@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "qf_common.cuh"
+#include "qf_tma.cuh"
 
 namespace {
 
@@ -79,33 +80,6 @@ __device__ __forceinline__ double2 lds128(uint32_t addr)
     double2 v;
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
-}
-
-// ---- TMA (cp.async.bulk.tensor) + mbarrier primitives ---------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase)
-{
-    uint32_t ok;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok)
-                     : "r"(bar), "r"(phase)
-                     : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-                 : "memory");
 }
 
 // ---- cp.async loader (fallback when the driver has no tensor-map encoder, or QF_GEMM_LOAD=cpasync) --------
@@ -472,10 +446,6 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
     }
 }
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ---- warp-specialised stream-K kernel (3M arithmetic, TMA) ------------------------------------------------------
@@ -625,9 +595,22 @@ k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, 
 
 }   // namespace
 
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_tmapEncodeTiled qf_tmap_encoder()
+{
+    static bool tried = false;
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && p &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
 
 struct QfGemmPlan {
     bool m3 = true;             // 3M (Karatsuba) arithmetic; QF_GEMM_3M=0 selects the 4-multiplication variant
@@ -671,14 +654,9 @@ int qf_gemm_create(qf_handle_s *h)
     {
         const char *ld = getenv("QF_GEMM_LOAD");
         p->tma = !(ld && strcmp(ld, "cpasync") == 0);
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
-            qres != cudaDriverEntryPointSuccess) {
-            p->tma = false;   // no TMA descriptor encoder in this driver: keep the cp.async loader
-            cudaGetLastError();
-        }
-        p->encode = (PFN_tmapEncodeTiled)fn;
+        PFN_tmapEncodeTiled fn = qf_tmap_encoder();
+        if (!fn) p->tma = false;   // no TMA descriptor encoder in this driver: keep the cp.async loader
+        p->encode = fn;
     }
     QF_CUDA(cudaMalloc(&p->ws, sizeof(double2) * WS_D2_PER_THREAD * GEMM_THREADS * (size_t)p->max_ctas));
     QF_CUDA(cudaMalloc(&p->flags, sizeof(int) * p->max_ctas));
