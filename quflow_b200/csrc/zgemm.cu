@@ -333,6 +333,49 @@ __device__ __forceinline__ void gemm_store_tile(const double (&acc)[MI][Cfg<M3>:
     }
 }
 
+// ---- work schedule of a persistent CTA: data-parallel waves, then a stream-K tail ---------------------------------
+// With G CTAs and ntiles tiles, the first floor(ntiles/G) "waves" are plain data-parallel: in wave w CTA c computes the
+// whole tile w*G + c.  The tiles of a wave are consecutive in the row-major tile list, so at any time the CTAs share
+// a few row panels of A and stream through B together: both stay L2-resident (handing every CTA a contiguous run of
+// tiles instead keeps ALL of A and B live at once, 134 MB at N=2048, and re-reads them ~5x from DRAM).
+// The remaining R < G tiles are split stream-K style: CTA c owns k-tile iterations [Tt c/G, Tt (c+1)/G) of Tt = R*KT.
+struct SkSched {
+    int G, cta, KT, nfull, w;
+    long long Tt, it, it_end;
+    int tail0;   // index of the first tail tile
+    __device__ __forceinline__ void init(int ntiles, int KT_, int cta_, int G_)
+    {
+        G = G_; cta = cta_; KT = KT_;
+        nfull = ntiles / G;
+        w = 0;
+        tail0 = nfull * G;
+        Tt = (long long)(ntiles - tail0) * KT;
+        it = Tt * cta / G;
+        it_end = Tt * (cta + 1) / G;
+    }
+    // next segment: tile index, k-tile range [ka, kb); tail_local >= 0 for tail tiles (index inside the tail)
+    __device__ __forceinline__ bool next(int &tile, int &ka, int &kb, int &tail_local)
+    {
+        if (w < nfull) {
+            tile = w * G + cta;
+            ka = 0;
+            kb = KT;
+            tail_local = -1;
+            ++w;
+            return true;
+        }
+        if (it < it_end) {
+            tail_local = (int)(it / KT);
+            tile = tail0 + tail_local;
+            ka = (int)(it - (long long)tail_local * KT);
+            kb = (int)min((long long)KT, ka + (it_end - it));
+            it += kb - ka;
+            return true;
+        }
+        return false;
+    }
+};
+
 // ---- stream-K kernel: persistent CTAs split the (tile, k) iteration space evenly --------------------
 // CTA c owns iterations [T c / G, T (c+1) / G) of the T = ntiles * KT k-tile iterations.  A tile whose k range is
 // split is finished by the CTA that computed its k = 0 part (at the END of that CTA's range); the CTAs that hold the
@@ -372,16 +415,12 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
     const int cta = blockIdx.x, G = gridDim.x;
     constexpr int BK = Cfg<M3>::BK;
     const int KT = (N + BK - 1) / BK;
-    const long long T = (long long)ntiles * KT;
-    long long it = T * cta / G;
-    const long long it_end = T * (cta + 1) / G;
+    SkSched sched;
+    sched.init(ntiles, KT, cta, G);
+    int tile, ka, kb, tail_local;
 
-    while (it < it_end) {
-        const int tile = (int)(it / KT);
-        const int ka = (int)(it - (long long)tile * KT);
-        const int kb = (int)min((long long)KT, ka + (it_end - it));
+    while (sched.next(tile, ka, kb, tail_local)) {
         const SkTile ti = tiles[tile];
-        it += kb - ka;
         if (gated && !ctrl[ti.member].active) continue;
         const size_t moff = (size_t)ti.member * N * N;
 
@@ -416,9 +455,9 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
         } else {
             if (kb < KT) {
                 // finisher: add the parts computed by the following CTAs, in CTA order
-                const long long tile_end = (long long)(tile + 1) * KT;
+                const long long tile_end = (long long)(tail_local + 1) * KT;
                 int peer = cta + 1;
-                long long covered = it_end;
+                long long covered = sched.it_end;
                 while (covered < tile_end) {
                     if (tid == 0) {
                         while (atomicAdd(flags + peer, 0) == 0) __nanosleep(64);
@@ -437,7 +476,7 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
                                 acc[i][j][c][0] += p.x;
                                 acc[i][j][c][1] += p.y;
                             }
-                    covered = T * (peer + 1) / G;
+                    covered = sched.Tt * (peer + 1) / G;
                     ++peer;
                 }
             }
@@ -484,20 +523,16 @@ k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, 
 
     const int cta = blockIdx.x, G = gridDim.x;
     const int KT = (N + BK - 1) / BK;
-    const long long T = (long long)ntiles * KT;
-    long long it = T * cta / G;
-    const long long it_end = T * (cta + 1) / G;
+    SkSched sched;
+    sched.init(ntiles, KT, cta, G);
+    int tile, ka, kb, tail_local;
     uint32_t gk = 0;
 
     if (warp == GEMM_THREADS / 32) {
         // ===== producer =====
         if (lane == 0) {
-            while (it < it_end) {
-                const int tile = (int)(it / KT);
-                const int ka = (int)(it - (long long)tile * KT);
-                const int kb = (int)min((long long)KT, ka + (it_end - it));
+            while (sched.next(tile, ka, kb, tail_local)) {
                 const SkTile ti = tiles[tile];
-                it += kb - ka;
                 if (gated && !ctrl[ti.member].active) continue;
                 for (int kt = ka; kt < kb; ++kt, ++gk) {
                     const uint32_t stage = gk % STAGES;
@@ -524,12 +559,8 @@ k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, 
     const int g = lane >> 2, t = lane & 3;
     uint32_t a_off[2], b_off[2];
     gemm_frag_offsets<M3>(a_off, b_off, wm, wn, g, t);
-    while (it < it_end) {
-        const int tile = (int)(it / KT);
-        const int ka = (int)(it - (long long)tile * KT);
-        const int kb = (int)min((long long)KT, ka + (it_end - it));
+    while (sched.next(tile, ka, kb, tail_local)) {
         const SkTile ti = tiles[tile];
-        it += kb - ka;
         if (gated && !ctrl[ti.member].active) continue;
         const size_t moff = (size_t)ti.member * N * N;
 
@@ -563,9 +594,9 @@ k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, 
             if (tid == 0) atomicExch(flags + cta, 1);
         } else {
             if (kb < KT) {
-                const long long tile_end = (long long)(tile + 1) * KT;
+                const long long tile_end = (long long)(tail_local + 1) * KT;
                 int peer = cta + 1;
-                long long covered = it_end;
+                long long covered = sched.it_end;
                 while (covered < tile_end) {
                     if (tid == 0) {
                         while (atomicAdd(flags + peer, 0) == 0) __nanosleep(64);
@@ -584,7 +615,7 @@ k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, 
                                 acc[i][j][c][0] += p.x;
                                 acc[i][j][c][1] += p.y;
                             }
-                    covered = T * (peer + 1) / G;
+                    covered = sched.Tt * (peer + 1) / G;
                     ++peer;
                 }
             }
@@ -729,12 +760,17 @@ static int get_tile_list(qf_handle_s *h, bool upper_only, int rank, int nranks, 
             for (int q = 0; q < (nranks == 1 ? 1 : 2); ++q) {
                 const int rb = (nranks == 1) ? 0 : blocks[q] * hb;
                 const int re = (nranks == 1) ? N : std::min(N, rb + hb);
-                for (int r0 = rb; r0 < re; r0 += BMv)
-                    for (int c0 = 0; c0 < N; c0 += BNv) {
-                        if (upper_only && (c0 + BNv - 1 < r0)) continue;
-                        tl.push_back(SkTile{b, r0, qf_prow(r0, hb, nranks), c0, std::min(re, r0 + BMv),
-                                            a_permuted ? qf_prow(r0, hb, nranks) : r0, 0, 0});
-                    }
+                // Tile order = L2 blocking.  Column groups of CG tile-columns, row-major inside a group: the B panel of a
+                // group (CG * BN columns, 33 MB at N=2048) stays L2-resident while the waves stream the A row panels past
+                // it, so A is read ncols/CG times and B once (all 32 tile-columns at once re-reads B every wave).
+                const int CG = 16 * BNv;
+                for (int cg = 0; cg < N; cg += CG)
+                    for (int r0 = rb; r0 < re; r0 += BMv)
+                        for (int c0 = cg; c0 < std::min(N, cg + CG); c0 += BNv) {
+                            if (upper_only && (c0 + BNv - 1 < r0)) continue;
+                            tl.push_back(SkTile{b, r0, qf_prow(r0, hb, nranks), c0, std::min(re, r0 + BMv),
+                                                a_permuted ? qf_prow(r0, hb, nranks) : r0, 0, 0});
+                        }
             }
         }
     QfGemmPlan::List l{(int)upper_only, rank, nranks, (int)a_permuted, (int)tl.size(), nullptr};
