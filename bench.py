@@ -339,6 +339,74 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
+def ensemble_arm(args):
+    """BASELINE config 5: independent N=256 members, `--members` per GPU, sharded per member with no data-path
+    collective (weak scaling).  value = member-steps/s over all ranks."""
+    import torch
+    import quflow_b200 as qf
+    from quflow_b200._cuda import get_handle
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    N = 256 if args.n == 2048 else args.n
+    k = args.members
+    kw = mode_kwargs(args.mode, N)
+    W0 = np.stack([workload(N, seed=1000 * rank + j) for j in range(k)])
+    handle = get_handle(N, k, local_rank)
+    W = torch.from_numpy(W0).to(dev)
+    handle.isomp(W, kw["dt"], args.warmup, maxit=kw["maxit"], minit=kw["minit"])
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = handle.launch_count()
+    e0.record()
+    res, _ = handle.isomp(W, kw["dt"], args.steps, maxit=kw["maxit"], minit=kw["minit"])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = handle.launch_count() - l0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # e2e: host buffers through the public API, one call per step
+    Wpin = torch.from_numpy(W0.copy()).pin_memory()
+    Wh = Wpin.numpy()
+    qf.isomp_ensemble(Wh, kw["dt"], steps=1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        qf.isomp_ensemble(Wh, kw["dt"], steps=1)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    if rank == 0:
+        its = float(np.mean([r["total_iterations"] for r in res])) / max(args.steps, 1)
+        line = {"metric": "isomp member-steps/sec (ensemble)", "value": world * k * args.steps / (ms * 1e-3), "unit": "member-steps/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)",
+                "data": "synthetic",
+                "config": {"workload": f"ensemble of {world * k} independent R({N},seed) members, {k} per GPU, {args.mode} mode, "
+                                       f"each with its own tolerance and convergence", "N": N, "members_per_gpu": k,
+                           "iterations_per_step": its},
+                "e2e": {"value": world * k * args.steps / e2e_s, "unit": "member-steps/s",
+                        "h2d_bytes_per_step": 16 * N * N * k, "d2h_bytes_per_step": 16 * N * N * k},
+                "gpu_launches": launches}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -348,8 +416,14 @@ def main():
     ap.add_argument("--n", type=int, default=2048)
     ap.add_argument("--mode", default="natural", choices=["natural", "profile"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="single", choices=["single", "ensemble"],
+                    help="single: one R(N,42) simulation (row-sharded across GPUs); ensemble: BASELINE config 5, "
+                         "--members independent N=256 simulations per GPU (weak scaling, no collective)")
+    ap.add_argument("--members", type=int, default=8)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "ensemble":
+        ensemble_arm(args)
+    elif args.impl == "reference":
         reference_arm(args)
     else:
         gpu_arm(args)
