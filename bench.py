@@ -192,7 +192,7 @@ def workload_config(N, mode, kw, its=None):
 def gpu_arm(args):
     import torch
     import quflow_b200 as qf
-    from quflow_b200._cuda import get_handle
+    from quflow_b200._cuda import Handle, get_handle
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -209,7 +209,7 @@ def gpu_arm(args):
     N, mode = args.n, args.mode
     kw = mode_kwargs(mode, N)
     W0 = workload(N)
-    handle = get_handle(N, 1, local_rank)
+    handle = Handle(N, 1, local_rank) if world > 1 else get_handle(N, 1, local_rank)
     if world > 1:
         from quflow_b200.distributed import attach_row_sharding
         attach_row_sharding(handle, dist)

@@ -261,11 +261,18 @@ def comm_unique_id() -> bytes:
     return buf.raw
 
 
-_handles: dict = {}
+from collections import OrderedDict  # noqa: E402
+
+_handles: "OrderedDict[tuple, Handle]" = OrderedDict()
+_MAX_CACHED_HANDLES = 8      # a handle owns ~8 N^2 complex matrices (0.55 GB at N=2048): keep the cache bounded
 
 
 def get_handle(N: int, batch: int = 1, device: int | None = None) -> Handle:
-    """Module-level cache, mirroring the reference's per-N caches (quflow/laplacian/cpu.py:11-17)."""
+    """Module-level LRU cache, mirroring the reference's per-N caches (quflow/laplacian/cpu.py:11-17).
+
+    Callers use the handle for the duration of one call; the least recently used one is destroyed when more than
+    ``_MAX_CACHED_HANDLES`` distinct (N, batch, device) combinations have been seen.  Hold your own ``Handle`` for
+    long-lived use (bench.py, multi-GPU sharding)."""
     if device is None:
         try:
             import torch
@@ -273,6 +280,11 @@ def get_handle(N: int, batch: int = 1, device: int | None = None) -> Handle:
         except Exception:
             device = 0
     key = (int(N), int(batch), int(device))
-    if key not in _handles:
-        _handles[key] = Handle(*key)
+    if key in _handles:
+        _handles.move_to_end(key)
+        return _handles[key]
+    while len(_handles) >= _MAX_CACHED_HANDLES:
+        _, old = _handles.popitem(last=False)
+        old.close()
+    _handles[key] = Handle(*key)
     return _handles[key]

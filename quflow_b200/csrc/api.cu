@@ -33,9 +33,8 @@ extern "C" int qf_device_count(void)
 
 static int alloc_mat(qf_handle_s *h, double2 **p)
 {
-    const size_t elems = h->mat_elems * h->batch + QF_SKEW_PAD(h->N);   // padding: see QF_SKEW_PAD
-    QF_CUDA(cudaMalloc(p, sizeof(double2) * elems));
-    QF_CUDA(cudaMemset(*p, 0, sizeof(double2) * elems));
+    QF_CUDA(cudaMalloc(p, sizeof(double2) * h->mat_elems * h->batch));
+    QF_CUDA(cudaMemset(*p, 0, sizeof(double2) * h->mat_elems * h->batch));
     return QF_OK;
 }
 
@@ -98,7 +97,7 @@ extern "C" int qf_destroy(qf_handle_t h)
     qf_gemm_destroy(h);
     qf_comm_destroy(h);
     qf_p2p_destroy(h);
-    void *ptrs[] = {h->tab_w, h->tab_iu, h->tab_o, h->tab_wu, h->dW, h->Wh, h->P, h->A, h->S, h->scratch, h->kahan_c,
+    void *ptrs[] = {h->tab_w, h->tab_iu, h->tab_o, h->dW, h->Wh, h->P, h->A, h->S, h->scratch, h->kahan_c,
                     h->io, h->io2, h->rowpart, h->trbuf, h->ctrl, h->iters_dev};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -115,9 +114,8 @@ extern "C" int qf_solve_poisson(qf_handle_t h, const void *W_dev, void *P_dev, v
     if (W_dev == P_dev) { qf_set_error("qf_solve_poisson: W and P may not alias"); return QF_ERR_INVALID; }
     QF_CUDA(cudaSetDevice(h->device));
     const double2 *W = (const double2 *)W_dev;
-    // the input is staged into the handle's own (padded) W~ buffer: the TMA kernel reads a skewed view that runs a few
-    // rows past the end of the matrix; eps = 1, not gated
-    return qf_launch_poisson(h, W, nullptr, h->Wh, (double2 *)P_dev, 1.0, false, (cudaStream_t)stream);
+    // Wh == W: the solve reads W directly (no W + dW pass), eps = 1, not gated
+    return qf_launch_poisson(h, W, nullptr, const_cast<double2 *>(W), (double2 *)P_dev, 1.0, false, (cudaStream_t)stream);
 }
 
 extern "C" int qf_laplace(qf_handle_t h, const void *P_dev, void *W_dev, void *stream)

@@ -16,7 +16,6 @@
 #include <vector>
 
 #include "qf_common.cuh"
-#include "qf_tma.cuh"
 
 // ---------------------------------------------------------------------------------------
 // host: coefficient / factor tables
@@ -52,14 +51,6 @@ int qf_build_tables(qf_handle_s *h)
     QF_CUDA(cudaMemcpy(h->tab_w, tw.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
     QF_CUDA(cudaMemcpy(h->tab_iu, tiu.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
     QF_CUDA(cudaMemcpy(h->tab_o, to.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
-    // interleaved (w, 1/u) pairs for the TMA kernel; padded because the skewed view (row pitch N+1) of the last rows
-    // reaches up to N-2 elements past the end of the matrix
-    {
-        std::vector<double2> wu(n2 + QF_SKEW_PAD(N), make_double2(0.0, 0.0));
-        for (size_t i = 0; i < n2; ++i) wu[i] = make_double2(tw[i], tiu[i]);
-        QF_CUDA(cudaMalloc(&h->tab_wu, wu.size() * sizeof(double2)));
-        QF_CUDA(cudaMemcpy(h->tab_wu, wu.data(), wu.size() * sizeof(double2), cudaMemcpyHostToDevice));
-    }
     return QF_OK;
 }
 
@@ -430,326 +421,6 @@ k_poisson_scan(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// v3 (experimental, QF_POISSON_TMA=1): the same chunked affine-scan solve, fed by TMA through the SKEWED view of the matrix.
-//
-// With a row pitch of (N+1) elements instead of N, element (k, k+m) of the matrix is element (k, m) of a dense 2-D
-// tensor: a group of 4 adjacent diagonals x 256 positions is one TMA box of 256 rows x 64 bytes.  The same view over
-// the interleaved (w, 1/u) table delivers the factors.  (Positions past the end of a diagonal wrap into the next matrix
-// row: they are masked by the consumers; the buffers carry N elements of padding for the last rows.)
-//
-// The kernel is persistent and warp-specialised: warp 16 is the producer (one lane issues the boxes of the CTA's
-// diagonal groups, in order, into a 3-slot ring of 32 KiB, paced by full/empty mbarriers); the 512 consumer threads
-// unpack a box as soon as it lands (right-hand side -> registers, factors -> a per-thread [i][thread] shared array),
-// release the slot, and run the two sweeps exactly as k_poisson_scan does.  While the consumers scan / store group g,
-// the producer is already streaming group g+1, so global-load latency is off the critical path and the consumers do
-// no address arithmetic for loads at all.
-// ---------------------------------------------------------------------------------------
-constexpr int PT_GS = 4;                 // diagonals per group
-constexpr int PT_L = 16;                 // positions per thread
-constexpr int PT_ROWS = 256;             // positions per TMA box
-constexpr int PT_SLOTS = 3;
-constexpr int PT_CONS = 512;             // consumer threads: 4 diagonals x 128 chunks (N <= 2048)
-constexpr int PT_THREADS = PT_CONS + 32;
-constexpr int PT_SLOT_BYTES = 2 * PT_ROWS * 64;                       // R box + table box
-constexpr int PT_SMEM = PT_SLOTS * PT_SLOT_BYTES + PT_L * PT_CONS * 16 + 1024;
-
-__device__ __forceinline__ void pt_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-
-__global__ void __launch_bounds__(PT_THREADS, 1)
-k_poisson_tma(double2 *__restrict__ P, const double2 *__restrict__ tab_wu, int N, int NG, double eps,
-              const QfCtrl *__restrict__ ctrl, int gated, const __grid_constant__ CUtensorMap tmR,
-              const __grid_constant__ CUtensorMap tmT)
-{
-    constexpr int L = PT_L, GS = PT_GS;
-    const int b = blockIdx.y;
-    if (gated && !ctrl[b].active) return;
-    extern __shared__ uint8_t pt_raw[];
-    const uint32_t base = ((uint32_t)__cvta_generic_to_shared(pt_raw) + 1023u) & ~1023u;
-    const uint32_t ring = base;                                           // [slot][R 16 KiB | T 16 KiB]
-    const uint32_t priv = base + PT_SLOTS * PT_SLOT_BYTES;                // [i][thread] (w, 1/u)
-    __shared__ __align__(8) unsigned long long bar_full[PT_SLOTS], bar_empty[PT_SLOTS];
-    // issued[q] = number of boxes the producer has armed in slot q so far.  A box is unpacked by its own two warps only,
-    // so a warp may reach the 2nd, 3rd ... use of a slot without having seen the earlier ones; mbarrier parity alone cannot
-    // tell "round r not armed yet" from "round r complete", the counter can.
-    __shared__ volatile unsigned issued[PT_SLOTS];
-    __shared__ double totA[16][GS], totBx[16][GS], totBy[16][GS];
-    __shared__ double redx[16], redy[16];
-    __shared__ double2 bcast;
-    const uint32_t full = (uint32_t)__cvta_generic_to_shared(bar_full);
-    const uint32_t empty = (uint32_t)__cvta_generic_to_shared(bar_empty);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-#pragma unroll
-        for (int q = 0; q < PT_SLOTS; ++q) {
-            mbar_init(full + 8 * q, 1);
-            mbar_init(empty + 8 * q, 2);      // a box (256 positions x 4 diagonals) is unpacked by exactly two warps
-            issued[q] = 0u;
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    if (warp == PT_CONS / 32) {
-        // ===== producer =====
-        if (lane == 0) {
-            uint32_t gb = 0;
-            for (int grp = blockIdx.x; grp < NG; grp += gridDim.x) {
-                const int nb = (N - GS * grp + PT_ROWS - 1) / PT_ROWS;
-                for (int j = 0; j < nb; ++j, ++gb) {
-                    const uint32_t slot = gb % PT_SLOTS, round = gb / PT_SLOTS;
-                    if (round > 0) mbar_wait(empty + 8 * slot, (round - 1) & 1);
-                    const uint32_t dst = ring + slot * PT_SLOT_BYTES;
-                    mbar_arrive_expect_tx(full + 8 * slot, PT_SLOT_BYTES);
-                    tma_load_3d(dst, &tmR, 2 * GS * grp, j * PT_ROWS, b, full + 8 * slot);
-                    tma_load_3d(dst + PT_ROWS * 64, &tmT, 2 * GS * grp, j * PT_ROWS, 0, full + 8 * slot);
-                    __threadfence_block();
-                    issued[slot] = round + 1u;
-                }
-            }
-        }
-        return;
-    }
-
-    // ===== consumers =====
-    const int s = tid & (GS - 1), c = tid >> 2;
-    const int nwarps = PT_CONS / 32;
-    const int k0 = c * L;
-    const int box = c >> 4;                       // 16 chunks per box
-    const uint32_t my_priv = priv + (uint32_t)tid * 16u;
-    const size_t off = (size_t)b * N * N;
-    double2 *X = P + off;
-    const unsigned stride = (unsigned)N + 1u;
-    uint32_t gb_base = 0;
-
-    for (int grp = blockIdx.x; grp < NG; grp += gridDim.x) {
-        const int m0 = GS * grp;
-        const int m = m0 + s;
-        const int n = N - m;                      // <= 0: this lane's diagonal does not exist
-        const int nb = (N - m0 + PT_ROWS - 1) / PT_ROWS;
-        const int nvalid = min(L, max(0, n - k0));
-        const unsigned e0 = (unsigned)k0 * stride + (unsigned)m;
-
-        // ---- unpack this thread's chunk from the ring
-        double2 r[L];
-        if (box < nb) {
-            const uint32_t gb = gb_base + (uint32_t)box;
-            const uint32_t slot = gb % PT_SLOTS, round = gb / PT_SLOTS;
-            while (issued[slot] < round + 1u) __nanosleep(32);   // the barrier is now in phase `round`
-            mbar_wait(full + 8 * slot, round & 1);
-            const uint32_t src = ring + slot * PT_SLOT_BYTES + (uint32_t)((c & 15) * L) * 64u + (uint32_t)s * 16u;
-#pragma unroll
-            for (int i = 0; i < L; ++i) {
-                double2 rv, tv;
-                asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(rv.x), "=d"(rv.y) : "r"(src + i * 64));
-                asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(tv.x), "=d"(tv.y) : "r"(src + PT_ROWS * 64 + i * 64));
-                const bool ok = i < nvalid;
-                r[i] = ok ? rv : make_double2(0.0, 0.0);
-                if (!ok) tv = make_double2(0.0, 0.0);
-                asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(my_priv + i * (PT_CONS * 16)), "d"(tv.x), "d"(tv.y) : "memory");
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + 8 * slot);
-        } else {
-#pragma unroll
-            for (int i = 0; i < L; ++i) {
-                r[i] = make_double2(0.0, 0.0);
-                asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(my_priv + i * (PT_CONS * 16)), "d"(0.0), "d"(0.0) : "memory");
-            }
-        }
-        gb_base += (uint32_t)nb;
-        // w of the first position of the next chunk (one scalar load per thread)
-        const double w_next = (k0 + L < n) ? __ldg(&tab_wu[e0 + (unsigned)L * stride].x) : 0.0;
-        auto tab = [&](int i) {
-            double2 v;
-            asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(my_priv + i * (PT_CONS * 16)));
-            return v;
-        };
-
-        // ---- m = 0: remove the mean of the diagonal from the right-hand side (cpu.py:311-317,327-328)
-        const bool diag = (m == 0);
-        if (grp == 0) {
-            double sx = 0.0, sy = 0.0;
-            if (diag) {
-#pragma unroll
-                for (int i = 0; i < L; ++i) { sx += r[i].x; sy += r[i].y; }
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-                sx += __shfl_xor_sync(0xffffffffu, sx, o);
-                sy += __shfl_xor_sync(0xffffffffu, sy, o);
-            }
-            if (lane == 0) { redx[warp] = sx; redy[warp] = sy; }
-            pt_bar();
-            if (tid == 0) {
-                double ax = 0.0, ay = 0.0;
-                for (int q = 0; q < nwarps; ++q) { ax += redx[q]; ay += redy[q]; }
-                bcast = make_double2(ax / N, ay / N);
-            }
-            pt_bar();
-            if (diag) {
-                const double2 tr = bcast;
-#pragma unroll
-                for (int i = 0; i < L; ++i)
-                    if (i < nvalid) { r[i].x -= tr.x; r[i].y -= tr.y; }
-            }
-            pt_bar();
-        }
-
-        // ---- forward, pass 1: chunk map  c_out = A c_in + B
-        double A = 1.0;
-        double2 B = make_double2(0.0, 0.0);
-#pragma unroll
-        for (int i = 0; i < L; ++i) {
-            const double w = tab(i).x;
-            B.x = r[i].x - w * B.x;
-            B.y = r[i].y - w * B.y;
-            A = -w * A;
-        }
-#pragma unroll
-        for (int d = GS; d < 32; d <<= 1) {
-            const double eA = __shfl_up_sync(0xffffffffu, A, d);
-            const double eBx = __shfl_up_sync(0xffffffffu, B.x, d);
-            const double eBy = __shfl_up_sync(0xffffffffu, B.y, d);
-            if (lane >= d) {
-                B.x = A * eBx + B.x;
-                B.y = A * eBy + B.y;
-                A = A * eA;
-            }
-        }
-        double xA = __shfl_up_sync(0xffffffffu, A, GS);
-        double xBx = __shfl_up_sync(0xffffffffu, B.x, GS);
-        double xBy = __shfl_up_sync(0xffffffffu, B.y, GS);
-        if (lane < GS) { xA = 1.0; xBx = 0.0; xBy = 0.0; }
-        if (lane >= 32 - GS) { totA[warp][s] = A; totBx[warp][s] = B.x; totBy[warp][s] = B.y; }
-        pt_bar();
-        double2 carry;
-        {
-            double pBx = 0.0, pBy = 0.0;
-            for (int q = 0; q < warp; ++q) {
-                const double tA = totA[q][s];
-                pBx = tA * pBx + totBx[q][s];
-                pBy = tA * pBy + totBy[q][s];
-            }
-            carry.x = xA * pBx + xBx;
-            carry.y = xA * pBy + xBy;
-        }
-        // ---- forward, pass 2 from the true carry-in; r becomes z = c / u
-#pragma unroll
-        for (int i = 0; i < L; ++i) {
-            const double2 t = tab(i);
-            carry.x = r[i].x - t.x * carry.x;
-            carry.y = r[i].y - t.x * carry.y;
-            r[i].x = carry.x * t.y;
-            r[i].y = carry.y * t.y;
-        }
-        pt_bar();   // tot* reused below
-
-        // ---- backward, pass 1: x_out = A x_in + B  (x_in = value just after the chunk); uses w_{k+1}
-        A = 1.0;
-        B = make_double2(0.0, 0.0);
-        {
-            double wn = w_next;
-#pragma unroll
-            for (int i = L - 1; i >= 0; --i) {
-                B.x = r[i].x - wn * B.x;
-                B.y = r[i].y - wn * B.y;
-                A = -wn * A;
-                wn = tab(i).x;
-            }
-        }
-#pragma unroll
-        for (int d = GS; d < 32; d <<= 1) {
-            const double eA = __shfl_down_sync(0xffffffffu, A, d);
-            const double eBx = __shfl_down_sync(0xffffffffu, B.x, d);
-            const double eBy = __shfl_down_sync(0xffffffffu, B.y, d);
-            if (lane + d < 32) {
-                B.x = A * eBx + B.x;
-                B.y = A * eBy + B.y;
-                A = A * eA;
-            }
-        }
-        xA = __shfl_down_sync(0xffffffffu, A, GS);
-        xBx = __shfl_down_sync(0xffffffffu, B.x, GS);
-        xBy = __shfl_down_sync(0xffffffffu, B.y, GS);
-        if (lane >= 32 - GS) { xA = 1.0; xBx = 0.0; xBy = 0.0; }
-        if (lane < GS) { totA[warp][s] = A; totBx[warp][s] = B.x; totBy[warp][s] = B.y; }
-        pt_bar();
-        {
-            double pBx = 0.0, pBy = 0.0;
-            for (int q = nwarps - 1; q > warp; --q) {
-                const double tA = totA[q][s];
-                pBx = tA * pBx + totBx[q][s];
-                pBy = tA * pBy + totBy[q][s];
-            }
-            carry.x = xA * pBx + xBx;
-            carry.y = xA * pBy + xBy;
-        }
-        // ---- backward, pass 2; r becomes x
-        {
-            double wn = w_next;
-#pragma unroll
-            for (int i = L - 1; i >= 0; --i) {
-                carry.x = r[i].x - wn * carry.x;
-                carry.y = r[i].y - wn * carry.y;
-                r[i] = carry;
-                wn = tab(i).x;
-            }
-        }
-
-        // ---- m = 0: remove the mean of diag(P) (cpu.py:342-352)
-        if (grp == 0) {
-            double sx = 0.0, sy = 0.0;
-            if (diag) {
-#pragma unroll
-                for (int i = 0; i < L; ++i)
-                    if (i < nvalid) { sx += r[i].x; sy += r[i].y; }
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-                sx += __shfl_xor_sync(0xffffffffu, sx, o);
-                sy += __shfl_xor_sync(0xffffffffu, sy, o);
-            }
-            pt_bar();
-            if (lane == 0) { redx[warp] = sx; redy[warp] = sy; }
-            pt_bar();
-            if (tid == 0) {
-                double ax = 0.0, ay = 0.0;
-                for (int q = 0; q < nwarps; ++q) { ax += redx[q]; ay += redy[q]; }
-                bcast = make_double2(ax / N, ay / N);
-            }
-            pt_bar();
-            if (diag) {
-                const double2 tr = bcast;
-#pragma unroll
-                for (int i = 0; i < L; ++i) { r[i].x -= tr.x; r[i].y -= tr.y; }
-            }
-        }
-
-        // ---- store P = eps x and its skew-Hermitian mirror (cpu.py:334,340; isospectral.py:492)
-        {
-            double2 *xp = X + e0;
-            double2 *xm = X + (unsigned)k0 * stride + (unsigned)m * (unsigned)N;
-            if (nvalid == L && m != 0) {
-#pragma unroll
-                for (int i = 0; i < L; ++i) {
-                    const double2 v = make_double2(eps * r[i].x, eps * r[i].y);
-                    xp[(size_t)i * stride] = v;
-                    xm[(size_t)i * stride] = make_double2(-v.x, v.y);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < L; ++i) {
-                    if (i < nvalid) {
-                        const double2 v = make_double2(eps * r[i].x, eps * r[i].y);
-                        xp[(size_t)i * stride] = v;
-                        if (m != 0) xm[(size_t)i * stride] = make_double2(-v.x, v.y);
-                    }
-                }
-            }
-        }
-        pt_bar();   // the private table slots and tot* are rewritten by the next group
-    }
-}
-
 // W = Delta P for a general matrix (cpu.py:98-108); coefficients recomputed on the fly.
 __global__ void k_laplace(const double2 *__restrict__ P, double2 *__restrict__ W, int N)
 {
@@ -796,49 +467,8 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
         k_whalf<<<gw, 256, 0, st>>>(W, dW, Wh, n2, h->ctrl, g);
         h->launches++;
     }
-    static int use_tma = -1;
-    if (use_tma < 0) {
-        // measured on B200 (N=2048): 74 us against 57 us for k_poisson_scan, so the TMA-fed variant is opt-in for now
-        const char *env = getenv("QF_POISSON_TMA");
-        use_tma = (qf_tmap_encoder() != nullptr) && (env && env[0] == '1');
-    }
-    if (N <= 2048 && N >= 8 && use_tma && Wh == h->Wh) {
-        // TMA-fed persistent kernel over the skewed view of h->Wh (padded allocation)
-        static bool attr_done = false;
-        if (!attr_done) {
-            QF_CUDA(cudaFuncSetAttribute(k_poisson_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
-            attr_done = true;
-        }
-        if (!h->poisson_maps_ready) {
-            const cuuint64_t Nn = (cuuint64_t)N;
-            cuuint64_t dimsR[3] = {2 * Nn, Nn, (cuuint64_t)h->batch};
-            cuuint64_t strR[2] = {16 * (Nn + 1), 16 * Nn * Nn};
-            cuuint64_t dimsT[3] = {2 * Nn, Nn, 1};
-            cuuint64_t strT[2] = {16 * (Nn + 1), 16 * Nn * Nn};
-            cuuint32_t box[3] = {2 * PT_GS, PT_ROWS, 1};
-            cuuint32_t estr[3] = {1, 1, 1};
-            PFN_tmapEncodeTiled enc = qf_tmap_encoder();
-            CUresult r1 = enc(reinterpret_cast<CUtensorMap *>(h->poisson_tmR), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->Wh, dimsR, strR, box,
-                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            CUresult r2 = enc(reinterpret_cast<CUtensorMap *>(h->poisson_tmT), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->tab_wu, dimsT, strT,
-                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
-                qf_set_error("cuTensorMapEncodeTiled (skewed Poisson view) failed: %d %d", (int)r1, (int)r2);
-                return QF_ERR_CUDA;
-            }
-            h->poisson_maps_ready = 1;
-        }
-        const int NG = (N + PT_GS - 1) / PT_GS;
-        const int gx = std::max(1, std::min(NG, h->sm_count / h->batch));
-        dim3 grid(gx, h->batch);
-        k_poisson_tma<<<grid, PT_THREADS, PT_SMEM, st>>>(P, h->tab_wu, N, NG, eps, h->ctrl, g,
-                                                        *reinterpret_cast<CUtensorMap *>(h->poisson_tmR),
-                                                        *reinterpret_cast<CUtensorMap *>(h->poisson_tmT));
-        h->launches++;
-    } else if (N <= 2048) {
-        // chunked scan with per-thread loads (no tensor-map encoder, tiny N, or a caller-owned input buffer)
+    if (N <= 2048) {
+        // chunked scan: 4 diagonals per CTA, 16 positions per thread (QF_POISSON_GS=2 selects 2 diagonals per CTA)
         const int chunks = (N + 15) / 16;
         static bool attr_done = false;
         if (!attr_done) {

@@ -57,8 +57,6 @@ __device__ __forceinline__ double zabs(double2 a) { return hypot(a.x, a.y); }
 // the handle
 // ---------------------------------------------------------------------------------------
 struct QfGemmPlan;   // zgemm.cu
-// elements of padding behind a matrix so that the skewed (pitch N+1) view of its last rows stays inside the allocation
-#define QF_SKEW_PAD(N) ((size_t)(N) + 64)
 #define QF_MAX_RANKS 16
 
 struct qf_handle_s {
@@ -71,10 +69,6 @@ struct qf_handle_s {
     double *tab_w = nullptr;   // w_k   = o_k / u_{k-1}          (0 at k = 0)
     double *tab_iu = nullptr;  // 1/u_k,  u_k = d_k - w_k o_k
     double *tab_o = nullptr;   // o_k   (coupling to position k-1; quflow lap[...,1])
-    double2 *tab_wu = nullptr; // interleaved (w_k, 1/u_k), padded, for the TMA Poisson kernel
-    alignas(64) unsigned char poisson_tmR[128];   // CUtensorMap: skewed view of Wh
-    alignas(64) unsigned char poisson_tmT[128];   // CUtensorMap: skewed view of tab_wu
-    int poisson_maps_ready = 0;
     double *tab_d = nullptr;   // d_k   (quflow lap[...,0], bc=False) — for laplace()
     // work matrices, batch * N * N complex128 each
     double2 *dW = nullptr, *Wh = nullptr, *P = nullptr, *A = nullptr, *S = nullptr, *scratch = nullptr;
