@@ -77,7 +77,8 @@ SYMBOLS = {
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, _LIBNAME)
+    # QF_LIBRARY: developer override (instrumented builds made by tools/microbench); still a CUDA build, never a fallback
+    return os.environ.get("QF_LIBRARY") or os.path.join(_HERE, _LIBNAME)
 
 
 def library():

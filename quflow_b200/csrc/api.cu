@@ -97,7 +97,7 @@ extern "C" int qf_destroy(qf_handle_t h)
     qf_gemm_destroy(h);
     qf_comm_destroy(h);
     qf_p2p_destroy(h);
-    void *ptrs[] = {h->tab_w, h->tab_iu, h->tab_o, h->dW, h->Wh, h->P, h->A, h->S, h->scratch, h->kahan_c,
+    void *ptrs[] = {h->tab_w, h->tab_iu, h->tab_o, h->ptab_w, h->ptab_iu, h->ptab_units, h->dW, h->Wh, h->P, h->A, h->S, h->scratch, h->kahan_c,
                     h->io, h->io2, h->rowpart, h->trbuf, h->ctrl, h->iters_dev};
     for (void *p : ptrs)
         if (p) cudaFree(p);

@@ -7,11 +7,11 @@
 // diagonal m (length N-m):  o_k x_{k-1} + d_k x_k + o_{k+1} x_{k+1} = r_k  with
 //   d_k = -((N-1)(2k+1+m) - 2k(k+m)),   o_k = sqrt((k+m)(N-k-m) k (N-k)),   d_0 -= 1/2 for m = 0.
 // The matrices do not depend on W, so their LU factors  w_k = o_k/u_{k-1}, u_k = d_k - w_k o_k
-// are built once per N on the host (the reference recomputes them every call) and kept in HBM in
-// the same [k][k+m] layout as the matrix, so a warp that walks "one system per lane" reads whole
-// rows: fully coalesced.
+// are built once per N on the host (the reference recomputes them every call) and kept in HBM packed
+// in the order the solve kernel reads them (k_poisson_band below).
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include <algorithm>
 #include <vector>
 
@@ -45,17 +45,125 @@ int qf_build_tables(qf_handle_s *h)
             u_prev = u;
         }
     }
-    QF_CUDA(cudaMalloc(&h->tab_w, n2 * sizeof(double)));
-    QF_CUDA(cudaMalloc(&h->tab_iu, n2 * sizeof(double)));
-    QF_CUDA(cudaMalloc(&h->tab_o, n2 * sizeof(double)));
-    QF_CUDA(cudaMemcpy(h->tab_w, tw.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
-    QF_CUDA(cudaMemcpy(h->tab_iu, tiu.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
-    QF_CUDA(cudaMemcpy(h->tab_o, to.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
+    // dense [k][k+m] tables: only the one-thread-per-diagonal fallback (very large N) reads them
+    auto upload_dense = [&]() -> int {
+        QF_CUDA(cudaMalloc(&h->tab_w, n2 * sizeof(double)));
+        QF_CUDA(cudaMalloc(&h->tab_iu, n2 * sizeof(double)));
+        QF_CUDA(cudaMalloc(&h->tab_o, n2 * sizeof(double)));
+        QF_CUDA(cudaMemcpy(h->tab_w, tw.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
+        QF_CUDA(cudaMemcpy(h->tab_iu, tiu.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
+        QF_CUDA(cudaMemcpy(h->tab_o, to.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
+        return QF_OK;
+    };
+
+    // ---- unit-packed tables for k_poisson_band.  A band is M adjacent diagonals m = M b + s (M = 8: a row piece of
+    // a band is one 128-byte line).  The work is cut into UNITS of PC positions x M diagonals, one per CTA: a "long
+    // piece" (positions [posbase, posbase + PC) of band bL) followed, from local position PS on, by a whole short
+    // band bS that fills the space the long piece leaves (diagonal lengths fall linearly, so band b and band
+    // nbands - b together have about N positions: every CTA is full).  A band longer than PC spans the first
+    // `nlink` CTAs of one thread-block cluster; the other CTAs of that cluster take independent units.  The factor
+    // entries of a unit are contiguous and ordered [warp block][i][chunk in block][s]: the 32 lanes of a warp read
+    // 32 consecutive doubles for every i.  Entries outside the diagonals are 0 (which also decouples the pieces).
+    {
+        int L = 16, M = 4;
+        if (const char *env = getenv("QF_POISSON_L")) L = atoi(env) == 8 ? 8 : 16;
+        if (const char *env = getenv("QF_POISSON_M")) M = atoi(env) == 8 ? 8 : 4;
+        const int chunks = (N + L - 1) / L;
+        int NTMAX = 512;
+        if (const char *env = getenv("QF_POISSON_NT")) NTMAX = atoi(env) == 256 ? 256 : 512;
+        int NT = NTMAX, CL = 1;
+        if (M * chunks <= NTMAX) {
+            NT = ((M * chunks + 31) / 32) * 32;
+        } else {
+            const int need = (M * chunks + NTMAX - 1) / NTMAX;
+            while (CL < need) CL *= 2;
+        }
+        if (CL > 8) return upload_dense();   // N too large for one cluster: k_thomas path
+        const int PC = (NT / M) * L, WB = (32 / M) * L;
+        const int nbands = (N + M - 1) / M;
+        std::vector<char> taken(nbands, 0);
+        std::vector<int> units;     // 8 ints per unit: bL, posbase, bS, PS, nlink, 0, 0, 0
+        auto filler = [&](int used) -> int {      // longest free band that fits into PC - used positions
+            const int room = PC - used;
+            if (room <= 0) return -1;
+            int b0 = (N - room + M - 1) / M;
+            if (b0 < 0) b0 = 0;
+            for (int bb = b0; bb < nbands; ++bb)
+                if (!taken[bb] && N - M * bb <= room) return bb;
+            return -1;
+        };
+        auto push_single = [&](int bb) {
+            taken[bb] = 1;
+            const int used = N - M * bb;
+            int bS = filler(used), PS = PC;
+            if (bS >= 0) { taken[bS] = 1; PS = used; }
+            units.insert(units.end(), {bb, 0, bS, PS, 1, 0, 0, 0});
+        };
+        for (int bb = 0; bb < nbands && N - M * bb > PC; ++bb) {          // clusters that hold a linked band
+            const int len = N - M * bb;
+            const int k = (len + PC - 1) / PC;
+            taken[bb] = 1;
+            for (int r = 0; r < k; ++r) {
+                int bS = -1, PS = PC;
+                if (r == k - 1) {
+                    const int used = len - r * PC;
+                    bS = filler(used);
+                    if (bS >= 0) { taken[bS] = 1; PS = used; }
+                }
+                units.insert(units.end(), {bb, r * PC, bS, PS, k, 0, 0, 0});
+            }
+            for (int r = k; r < CL; ++r) {                                 // spare ranks: independent short bands
+                int nb = -1;
+                for (int q = nbands - 1; q >= 0; --q) if (!taken[q] && N - M * q <= PC) nb = q;   // longest free short band
+                if (nb >= 0) push_single(nb); else units.insert(units.end(), {-1, 0, -1, PC, 1, 0, 0, 0});
+            }
+        }
+        for (int bb = 0; bb < nbands; ++bb)                                // the rest: one band (+ filler) per CTA
+            if (!taken[bb]) push_single(bb);
+        while ((units.size() / 8) % CL) units.insert(units.end(), {-1, 0, -1, PC, 1, 0, 0, 0});
+        const size_t nunits = units.size() / 8;
+        const size_t total = nunits * (size_t)PC * M;
+        if (total >= (1ull << 31)) return upload_dense();
+        const int CPW = 32 / M;
+        std::vector<double> pw(total, 0.0), piu(total, 0.0);
+        for (size_t u = 0; u < nunits; ++u) {
+            const int bL = units[8 * u], posbase = units[8 * u + 1], bS = units[8 * u + 2], PS = units[8 * u + 3];
+            for (int sl = 0; sl < M; ++sl) {
+                for (int pl = 0; pl < PC; ++pl) {
+                    int m = -1, k = 0;
+                    if (pl < PS) {
+                        if (bL >= 0) { m = M * bL + sl; k = posbase + pl; }
+                    } else if (bS >= 0) {
+                        m = M * bS + sl;
+                        k = pl - PS;
+                    }
+                    if (m < 0 || m >= N || k >= N - m) continue;
+                    const size_t src = (size_t)k * N + (k + m);
+                    const size_t dst = u * (size_t)PC * M + (size_t)(pl / WB) * WB * M + (size_t)(pl % L) * 32 +
+                                       (size_t)((pl / L) % CPW) * M + sl;
+                    pw[dst] = tw[src];
+                    piu[dst] = tiu[src];
+                }
+            }
+        }
+        QF_CUDA(cudaMalloc(&h->ptab_w, total * sizeof(double)));
+        QF_CUDA(cudaMalloc(&h->ptab_iu, total * sizeof(double)));
+        QF_CUDA(cudaMalloc(&h->ptab_units, units.size() * sizeof(int)));
+        QF_CUDA(cudaMemcpy(h->ptab_w, pw.data(), total * sizeof(double), cudaMemcpyHostToDevice));
+        QF_CUDA(cudaMemcpy(h->ptab_iu, piu.data(), total * sizeof(double), cudaMemcpyHostToDevice));
+        QF_CUDA(cudaMemcpy(h->ptab_units, units.data(), units.size() * sizeof(int), cudaMemcpyHostToDevice));
+        h->p_L = L;
+        h->p_M = M;
+        h->p_CL = CL;
+        h->p_NT = NT;
+        h->p_NTMAX = NTMAX;
+        h->p_nunits = (int)nunits;
+    }
     return QF_OK;
 }
 
 // ---------------------------------------------------------------------------------------
-// kernels (v1: one thread per diagonal, row-coalesced; see DESIGN.md for the roadmap)
+// fallback kernels for N beyond one cluster's reach (one thread per diagonal, row-coalesced) and helpers
 // ---------------------------------------------------------------------------------------
 // Wh = W + dW over the full matrix (GEMM 1 needs all of W~), fused with the trace of W~.
 __global__ void k_whalf(const double2 *__restrict__ W, const double2 *__restrict__ dW, double2 *__restrict__ Wh,
@@ -178,248 +286,496 @@ __global__ void k_fix_trace(double2 *P, int N, double eps, const QfCtrl *__restr
 }
 
 // ---------------------------------------------------------------------------------------
-// v2: chunked parallel solve.  One CTA owns GS = 4 adjacent diagonals m0..m0+3; thread (s, c) owns
-// positions [cL, (c+1)L) of system m0+s in registers.  With the LDL^T factors (w_k, 1/u_k) both sweeps
-// are first-order linear recurrences,
+// The solve: band kernel (chunked affine scan).
+//
+// With the LDL^T factors (w_k, 1/u_k) both sweeps are first-order linear recurrences,
 //     forward   c_k = r_k - w_k c_{k-1}                 backward  x_k = c_k/u_k - w_{k+1} x_{k+1},
-// so each chunk is an affine map of its carry-in.  Pass 1 evaluates the chunk with carry-in 0 and the
-// map's slope (a running product), a warp-shuffle + shared-memory scan composes the maps across the
-// chunks of a system, pass 2 re-runs the chunk from its true carry-in.  Lanes s = 0..3 of a quad touch
-// 64 contiguous bytes of a matrix row, every thread has L independent 16-byte loads in flight, and the
-// per-CTA sequential depth is 4L FMAs + two log-depth scans instead of 2N.
-// HBM traffic: upper triangle of W~ (8 N^2 B) + w and 1/u tables (8 N^2 B) + full P (16 N^2 B) = 32 N^2 B.
+// so a chunk of L positions is an affine map of its carry-in.  Thread (s, c) keeps chunk c of diagonal s of its
+// band in registers: pass 1 evaluates the chunk with carry-in 0 plus the map's slope (a running product), a
+// warp-shuffle + shared-memory scan composes the maps along the diagonal, pass 2 re-runs the chunk from its true
+// carry-in.  Sequential depth: 4 L FMAs + two log-depth scans instead of 2 N.
+//   * a CTA is up to 512 threads = M diagonals x chunks of L = 16 positions (M = 4: 2048 positions);
+//   * the work is cut into FULL units (qf_build_tables): a long piece of one band plus a whole short band, so
+//     the triangle costs N^2/2 thread slots, not N^2; warps past the end of their pieces do nothing;
+//   * a band longer than one CTA's positions is solved by a thread-block CLUSTER: every CTA reduces its part
+//     of the diagonal to an affine map; the maps travel through distributed shared memory with st.async, which
+//     signals an mbarrier in the receiving CTA.  No cluster-wide barrier and no memory fence sits in the solve
+//     (a fence would wait for every load and prefetch the CTA has in flight);
+//   * factor tables are unit-packed: every warp load is 256 contiguous bytes; 1/u goes straight to shared
+//     memory with cp.async and is consumed between the sweeps;
+//   * the skew-Hermitian mirror P[j,i] = -conj(P[i,j]) is transposed through shared memory, so the mirrored
+//     stores are 16 M-byte row pieces like the direct ones (no scattered 16-byte stores);
+//   * once its own loads have landed a CTA prefetches into L2 the inputs of the unit that will follow it on its
+//     SM slot (pf_stride units ahead), so HBM keeps streaming while the resident CTAs run their sweeps.
+// HBM traffic: upper triangle of W~ (8 N^2 B) + w and 1/u (8 N^2 B) + full P (16 N^2 B) = 32 N^2 B.
 // ---------------------------------------------------------------------------------------
-template <int L, int GS, int MAXT>
-__global__ void __launch_bounds__(MAXT, 512 / MAXT)
-k_poisson_scan(const double2 *__restrict__ Wh, double2 *__restrict__ P, const double *__restrict__ tw,
-               const double *__restrict__ tiu, int N, double eps, const QfCtrl *__restrict__ ctrl, int gated)
-{
-    const int b = blockIdx.y;
-    if (gated && !ctrl[b].active) return;
-    __shared__ double totA[16][GS], totBx[16][GS], totBy[16][GS];
-    __shared__ double redx[16], redy[16];
-    __shared__ double2 bcast;
+#ifdef QF_PTRACE
+__device__ unsigned long long g_ptrace[4096 * 16];
+#define PT(k) do { if (tid == 0 && mem == 0 && blockIdx.x < 4096) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_ptrace[blockIdx.x * 16 + (k)] = _t; } } while (0)
+#else
+#define PT(k)
+#endif
 
+__device__ __forceinline__ void pb_mbar_wait(uint32_t mb)
+{
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(mb), "r"(0u) : "memory");
+}
+// remote store of one double into CTA `dst` of the cluster; completes 8 bytes on that CTA's mbarrier
+__device__ __forceinline__ void pb_send(double *local_slot, uint64_t *local_mbar, unsigned dst, double v)
+{
+    uint32_t ra, rm;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"((uint32_t)__cvta_generic_to_shared(local_slot)), "r"(dst));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rm) : "r"((uint32_t)__cvta_generic_to_shared(local_mbar)), "r"(dst));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(ra), "d"(v), "r"(rm) : "memory");
+}
+
+template <int L, int M, int CL, int NTMAX>
+__global__ void __launch_bounds__(NTMAX, 512 / NTMAX)
+k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const double *__restrict__ tw,
+               const double *__restrict__ tiu, const int4 *__restrict__ units, int N, int nunits, int pf_stride,
+               double eps, const QfCtrl *__restrict__ ctrl, int gated)
+{
+    const int mem = blockIdx.y;
+    if (gated && !ctrl[mem].active) return;      // uniform over the grid row: whole clusters leave together
+    constexpr int LOGM = (M == 8) ? 3 : 2;
+    constexpr int CPW = 32 / M;                  // chunks of one diagonal per warp
+    constexpr int WB = CPW * L;                  // positions per warp
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
-    constexpr int GSH = (GS == 4) ? 2 : 1;
-    const int s = tid & (GS - 1), c = tid >> GSH;
-    const int m0 = blockIdx.x * GS;
-    const int m = m0 + s;
-    const int n = N - m;                 // length of this thread's system (<= 0: none)
-    const int k0 = c * L;
-    const size_t off = (size_t)b * N * N;
+    const int PC = (blockDim.x >> LOGM) * L;     // positions per CTA
+    const int unit = blockIdx.x;
+    const int rank = (CL > 1) ? unit % CL : 0;   // cluster dims are (CL, 1, 1): this is %cluster_ctarank
+    const int4 ud = __ldg(units + 2 * unit);
+    const int bL = ud.x, posbase = ud.y, bS = ud.z, PS = ud.w;
+    const int nlink = (CL > 1) ? __ldg(reinterpret_cast<const int *>(units + 2 * unit + 1)) : 1;
+    const bool linked = (CL > 1) && nlink > 1;   // this CTA holds part of a band that spans ranks 0 .. nlink-1
+    const bool diag0 = (bL == 0);                // the band of the main diagonal (all its ranks see bL == 0)
+
+    __shared__ double totA[NTMAX / 32][M], totBx[NTMAX / 32][M], totBy[NTMAX / 32][M];
+    __shared__ double xchF[CL][M][3], xchB[CL][M][3];     // per-rank chunk maps, written by the peers (DSMEM)
+    __shared__ double redx[NTMAX / 32], redy[NTMAX / 32];
+    __shared__ double sumR[CL][2], sumX[CL][2];
+    __shared__ uint64_t mbar[4];                          // arrival of xchF, xchB, sumR, sumX (each used once)
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    double *iu_s = reinterpret_cast<double *>(dyn_smem);     // [L][blockDim.x], consumed by the forward sweep
+    double2 *tr_s = reinterpret_cast<double2 *>(dyn_smem);   // mirror transpose buffer (reuses the same bytes later)
+
+    if (CL > 1) {
+        if (tid == 0) {
+            const uint32_t nF = linked ? rank * M * 24 : 0, nB = linked ? (nlink - 1 - rank) * M * 24 : 0;
+            const uint32_t nS = (linked && diag0) ? (nlink - 1) * 16 : 0;
+            const uint32_t tx[4] = {nF, nB, nS, nS};
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&mbar[q]);
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(tx[q]) : "memory");
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        // every CTA of the cluster arrives here (nothing is in flight yet); the wait sits before the first send
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    }
+    if (bL < 0 && bS < 0) return;                // padding unit
+#ifdef QF_PTRACE
+    if (tid == 0 && mem == 0 && blockIdx.x < 4096) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_ptrace[blockIdx.x * 16 + 15] = sm; }
+#endif
+    PT(0);
+
+    const int s = tid & (M - 1), c = tid >> LOGM;
+    const int plo = c * L;                         // first local position of this thread's chunk
+    const unsigned stride = (unsigned)N + 1u;
+    // long piece: system m = M bL + s, positions posbase + pl, pl < nL;  short piece: m' = M bS + s, positions pl - PS < nS
+    const int mL = bL * M + s, mS = bS * M + s;
+    const int nL = (bL >= 0) ? min(PS, max(0, N - mL - posbase)) : 0;
+    const int nS = (bS >= 0) ? max(0, N - mS) : 0;
+    // element (k, k+m) sits at k (N+1) + m, its mirror (k+m, k) at k (N+1) + m N; k = posbase + pl or pl - PS
+    const unsigned offL = (unsigned)posbase * stride + (unsigned)mL;
+    const unsigned offS = (unsigned)mS - (unsigned)PS * stride;
+    const unsigned offML = (unsigned)posbase * stride + (unsigned)mL * (unsigned)N;
+    const unsigned offMS = (unsigned)mS * (unsigned)N - (unsigned)PS * stride;
+    const int extent = max((bL >= 0) ? min(PS, max(0, N - bL * M - posbase)) : 0, (bS >= 0) ? PS + N - bS * M : 0);
+    const bool warp_work = warp * WB < extent;     // slot 0 is the longest thing a warp owns
+    const bool in_short = plo >= PS;               // a chunk that starts in the short piece lies entirely in it
+    const bool straddle = !in_short && plo + L > PS;
+    // number of leading valid positions of a chunk that does not straddle the two pieces
+    const int nvalid = straddle ? 0 : min(L, max(0, in_short ? nS - (plo - PS) : nL - plo));
+    const unsigned offD = in_short ? offS : offL;
+    const size_t off = (size_t)mem * N * N;
     const double2 *R = Wh + off;
     double2 *X = P + off;
 
     double2 r[L];
-    double w[L + 1];                     // w[L] = w of the first position of the next chunk
-    // Element (k, k+m) sits at flat index k (N+1) + m; its mirror (k+m, k) at k (N+1) + m N: both walk with stride N+1.
-    // N <= 2048 so flat indices fit 32 bits.
-    const unsigned stride = (unsigned)N + 1u;
-    const unsigned e0 = (unsigned)k0 * stride + (unsigned)m;
-    const int nvalid = min(L, max(0, n - k0));
-    extern __shared__ double iu_s[];     // [L][blockDim.x]: 1/u of this thread's chunk, prefetched while the forward sweep runs
+    double w[L + 1];                               // w[L]: w of the first position after the chunk
     const uint32_t iu_base = (uint32_t)__cvta_generic_to_shared(iu_s) + (uint32_t)tid * 8u;
     const uint32_t iu_pitch = blockDim.x * 8u;
-    if (nvalid == L) {
-        const double2 *rp = R + e0;
-        const double *wp = tw + e0;
-        const double *up = tiu + e0;
+    if (warp_work) {
+        const size_t tb = (size_t)unit * PC * M + (size_t)warp * (WB * M) + lane;
+        const double *wp = tw + tb;
+        const double *up = tiu + tb;
 #pragma unroll
         for (int i = 0; i < L; ++i) {
-            r[i] = rp[(size_t)i * stride];
-            w[i] = __ldg(wp + (size_t)i * stride);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(iu_base + i * iu_pitch), "l"(up + (size_t)i * stride));
+            w[i] = __ldg(wp + i * 32);             // zero outside the diagonals
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(iu_base + i * iu_pitch), "l"(up + i * 32));
         }
-        w[L] = (k0 + L < n) ? __ldg(wp + (size_t)L * stride) : 0.0;
+        if (nvalid == L) {
+            const double2 *rp = R + ((unsigned)plo * stride + offD);
+#pragma unroll
+            for (int i = 0; i < L; ++i) r[i] = rp[(size_t)i * stride];
+        } else {
+#pragma unroll
+            for (int i = 0; i < L; ++i) {
+                const int pl = plo + i;
+                const bool sh = pl >= PS;
+                const bool ok = sh ? (pl - PS < nS) : (pl < nL);
+                r[i] = ok ? R[(unsigned)pl * stride + (sh ? offS : offL)] : make_double2(0.0, 0.0);
+            }
+        }
+        // w of the position after the chunk: next chunk of this unit, or the first chunk of the next linked rank
+        w[L] = 0.0;
+        if (plo + L < PC) {
+            const int cn = c + 1;
+            w[L] = __ldg(tw + (size_t)unit * PC * M + (size_t)(cn / CPW) * (WB * M) + (cn % CPW) * M + s);
+        } else if (linked && rank + 1 < nlink) {
+            w[L] = __ldg(tw + (size_t)(unit + 1) * PC * M + s);
+        }
     } else {
 #pragma unroll
-        for (int i = 0; i < L; ++i) {
-            const bool ok = i < nvalid;
-            const unsigned idx = ok ? e0 + (unsigned)i * stride : 0u;
-            r[i] = ok ? R[idx] : make_double2(0.0, 0.0);
-            w[i] = ok ? __ldg(tw + idx) : 0.0;
-            const int sz = ok ? 8 : 0;       // src-size 0: zero fill
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(iu_base + i * iu_pitch), "l"(tiu + idx), "r"(sz));
-        }
+        for (int i = 0; i < L; ++i) { r[i] = make_double2(0.0, 0.0); w[i] = 0.0; }
         w[L] = 0.0;
     }
     asm volatile("cp.async.commit_group;");
+    PT(1);
 
     // ---- m = 0: remove the mean of the diagonal from the right-hand side (cpu.py:311-317,327-328)
-    if (m0 == 0) {
+    if (diag0) {
         double sx = 0.0, sy = 0.0;
         if (s == 0) {
 #pragma unroll
-            for (int i = 0; i < L; ++i) { sx += r[i].x; sy += r[i].y; }
+            for (int i = 0; i < L; ++i)
+                if (plo + i < nL) { sx += r[i].x; sy += r[i].y; }
         }
         for (int o = 16; o > 0; o >>= 1) {
             sx += __shfl_xor_sync(0xffffffffu, sx, o);
             sy += __shfl_xor_sync(0xffffffffu, sy, o);
         }
         if (lane == 0) { redx[warp] = sx; redy[warp] = sy; }
+        if (linked) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers' mbarriers are ready
         __syncthreads();
         if (tid == 0) {
             double ax = 0.0, ay = 0.0;
             for (int q = 0; q < nwarps; ++q) { ax += redx[q]; ay += redy[q]; }
-            bcast = make_double2(ax / N, ay / N);
+            sumR[rank][0] = ax;
+            sumR[rank][1] = ay;
+            if (linked) {
+                for (int d = 0; d < nlink; ++d) {
+                    if (d == rank) continue;
+                    pb_send(&sumR[rank][0], &mbar[2], d, ax);
+                    pb_send(&sumR[rank][1], &mbar[2], d, ay);
+                }
+            }
         }
         __syncthreads();
+        if (linked) pb_mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar[2]));
+        double tx = 0.0, ty = 0.0;
+        for (int d = 0; d < nlink; ++d) { tx += sumR[d][0]; ty += sumR[d][1]; }
+        tx /= N;
+        ty /= N;
         if (s == 0) {
-            const double2 tr = bcast;
 #pragma unroll
             for (int i = 0; i < L; ++i)
-                if (k0 + i < n) { r[i].x -= tr.x; r[i].y -= tr.y; }
+                if (plo + i < nL) { r[i].x -= tx; r[i].y -= ty; }
         }
-        __syncthreads();
+    } else if (linked) {
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");               // peers' mbarriers are ready
     }
 
     // ---- forward, pass 1: chunk map  c_out = A c_in + B
     double A = 1.0;
     double2 B = make_double2(0.0, 0.0);
+    double xA = 1.0, xBx = 0.0, xBy = 0.0;
+    if (warp_work) {
 #pragma unroll
-    for (int i = 0; i < L; ++i) {
-        B.x = r[i].x - w[i] * B.x;
-        B.y = r[i].y - w[i] * B.y;
-        A = -w[i] * A;
+        for (int i = 0; i < L; ++i) {
+            B.x = r[i].x - w[i] * B.x;
+            B.y = r[i].y - w[i] * B.y;
+            A = -w[i] * A;
+        }
+        // inclusive scan over the chunks of this warp (lanes with equal s are M apart)
+#pragma unroll
+        for (int d = M; d < 32; d <<= 1) {
+            const double eA = __shfl_up_sync(0xffffffffu, A, d);
+            const double eBx = __shfl_up_sync(0xffffffffu, B.x, d);
+            const double eBy = __shfl_up_sync(0xffffffffu, B.y, d);
+            if (lane >= d) {
+                B.x = A * eBx + B.x;
+                B.y = A * eBy + B.y;
+                A = A * eA;
+            }
+        }
+        xA = __shfl_up_sync(0xffffffffu, A, M);
+        xBx = __shfl_up_sync(0xffffffffu, B.x, M);
+        xBy = __shfl_up_sync(0xffffffffu, B.y, M);
+        if (lane < M) { xA = 1.0; xBx = 0.0; xBy = 0.0; }
     }
-    // inclusive scan over the 8 chunks of this warp (lanes with equal s are 4 apart)
+    PT(2);
+    // ---- L2 prefetch of the unit pf_stride ahead (same thread mapping; one request per end of a row piece)
+    if (pf_stride > 0 && unit + pf_stride < nunits) {
+        const int un = unit + pf_stride;
+        const int4 nd = __ldg(units + 2 * un);
+        if (tid < 2) {
+            const double *t = (tid == 0 ? tw : tiu) + (size_t)un * PC * M;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t), "r"(PC * M * 8) : "memory");
+        }
+        if (s == 0 || s == M - 1) {
+            const int nmL = nd.x * M + s, nmS = nd.z * M + s;
+            const int nnL = (nd.x >= 0) ? min(nd.w, max(0, N - nmL - nd.y)) : 0;
+            const int nnS = (nd.z >= 0) ? max(0, N - nmS) : 0;
+            const unsigned noL = (unsigned)nd.y * stride + (unsigned)nmL;
+            const unsigned noS = (unsigned)nmS - (unsigned)nd.w * stride;
 #pragma unroll
-    for (int d = GS; d < 32; d <<= 1) {
-        const double eA = __shfl_up_sync(0xffffffffu, A, d);
-        const double eBx = __shfl_up_sync(0xffffffffu, B.x, d);
-        const double eBy = __shfl_up_sync(0xffffffffu, B.y, d);
-        if (lane >= d) {
-            B.x = A * eBx + B.x;
-            B.y = A * eBy + B.y;
-            A = A * eA;
+            for (int i = 0; i < L; ++i) {
+                const int pl = plo + i;
+                const bool sh = pl >= nd.w;
+                const bool ok = sh ? (pl - nd.w < nnS) : (pl < nnL);
+                if (ok) asm volatile("prefetch.global.L2 [%0];" ::"l"(R + ((unsigned)pl * stride + (sh ? noS : noL))));
+            }
         }
     }
-    double xA = __shfl_up_sync(0xffffffffu, A, GS);
-    double xBx = __shfl_up_sync(0xffffffffu, B.x, GS);
-    double xBy = __shfl_up_sync(0xffffffffu, B.y, GS);
-    if (lane < GS) { xA = 1.0; xBx = 0.0; xBy = 0.0; }
-    if (lane >= 32 - GS) { totA[warp][s] = A; totBx[warp][s] = B.x; totBy[warp][s] = B.y; }
+    if (lane >= 32 - M) { totA[warp][s] = A; totBx[warp][s] = B.x; totBy[warp][s] = B.y; }
     __syncthreads();
+    PT(3);
+    if (linked) {
+        if (tid < M && rank + 1 < nlink) {         // the map of this CTA's whole part of diagonal s -> higher ranks
+            double tA = 1.0, tBx = 0.0, tBy = 0.0;
+            for (int q = 0; q < nwarps; ++q) {
+                const double a = totA[q][s];
+                tBx = a * tBx + totBx[q][s];
+                tBy = a * tBy + totBy[q][s];
+                tA = a * tA;
+            }
+            for (int d = rank + 1; d < nlink; ++d) {
+                pb_send(&xchF[rank][s][0], &mbar[0], d, tA);
+                pb_send(&xchF[rank][s][1], &mbar[0], d, tBx);
+                pb_send(&xchF[rank][s][2], &mbar[0], d, tBy);
+            }
+        }
+        if (rank > 0) pb_mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar[0]));
+    }
+    PT(4);
     double2 carry;
     {
         double pBx = 0.0, pBy = 0.0;
+        if (linked) {
+            for (int d = 0; d < rank; ++d) {
+                const double a = xchF[d][s][0];
+                pBx = a * pBx + xchF[d][s][1];
+                pBy = a * pBy + xchF[d][s][2];
+            }
+        }
         for (int q = 0; q < warp; ++q) {
-            const double tA = totA[q][s];
-            pBx = tA * pBx + totBx[q][s];
-            pBy = tA * pBy + totBy[q][s];
+            const double a = totA[q][s];
+            pBx = a * pBx + totBx[q][s];
+            pBy = a * pBy + totBy[q][s];
         }
         carry.x = xA * pBx + xBx;
         carry.y = xA * pBy + xBy;
     }
     // ---- forward, pass 2 from the true carry-in; r becomes z = c / u
     asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's own 1/u values (no cross-thread sharing)
+    if (warp_work) {
 #pragma unroll
-    for (int i = 0; i < L; ++i) {
-        carry.x = r[i].x - w[i] * carry.x;
-        carry.y = r[i].y - w[i] * carry.y;
-        const double iu = iu_s[i * blockDim.x + tid];
-        r[i].x = carry.x * iu;
-        r[i].y = carry.y * iu;
+        for (int i = 0; i < L; ++i) {
+            carry.x = r[i].x - w[i] * carry.x;
+            carry.y = r[i].y - w[i] * carry.y;
+            const double iu = iu_s[i * blockDim.x + tid];
+            r[i].x = carry.x * iu;
+            r[i].y = carry.y * iu;
+        }
     }
-    __syncthreads();   // tot* reused below
+    PT(5);
+    __syncthreads();   // tot* and the iu_s bytes are reused below
+    PT(6);
 
     // ---- backward, pass 1: x_out = A x_in + B  (x_in = value just after the chunk)
     A = 1.0;
     B = make_double2(0.0, 0.0);
+    xA = 1.0; xBx = 0.0; xBy = 0.0;
+    if (warp_work) {
 #pragma unroll
-    for (int i = L - 1; i >= 0; --i) {
-        B.x = r[i].x - w[i + 1] * B.x;
-        B.y = r[i].y - w[i + 1] * B.y;
-        A = -w[i + 1] * A;
-    }
-#pragma unroll
-    for (int d = GS; d < 32; d <<= 1) {
-        const double eA = __shfl_down_sync(0xffffffffu, A, d);
-        const double eBx = __shfl_down_sync(0xffffffffu, B.x, d);
-        const double eBy = __shfl_down_sync(0xffffffffu, B.y, d);
-        if (lane + d < 32) {
-            B.x = A * eBx + B.x;
-            B.y = A * eBy + B.y;
-            A = A * eA;
+        for (int i = L - 1; i >= 0; --i) {
+            B.x = r[i].x - w[i + 1] * B.x;
+            B.y = r[i].y - w[i + 1] * B.y;
+            A = -w[i + 1] * A;
         }
+#pragma unroll
+        for (int d = M; d < 32; d <<= 1) {
+            const double eA = __shfl_down_sync(0xffffffffu, A, d);
+            const double eBx = __shfl_down_sync(0xffffffffu, B.x, d);
+            const double eBy = __shfl_down_sync(0xffffffffu, B.y, d);
+            if (lane + d < 32) {
+                B.x = A * eBx + B.x;
+                B.y = A * eBy + B.y;
+                A = A * eA;
+            }
+        }
+        xA = __shfl_down_sync(0xffffffffu, A, M);
+        xBx = __shfl_down_sync(0xffffffffu, B.x, M);
+        xBy = __shfl_down_sync(0xffffffffu, B.y, M);
+        if (lane >= 32 - M) { xA = 1.0; xBx = 0.0; xBy = 0.0; }
     }
-    xA = __shfl_down_sync(0xffffffffu, A, GS);
-    xBx = __shfl_down_sync(0xffffffffu, B.x, GS);
-    xBy = __shfl_down_sync(0xffffffffu, B.y, GS);
-    if (lane >= 32 - GS) { xA = 1.0; xBx = 0.0; xBy = 0.0; }
-    if (lane < GS) { totA[warp][s] = A; totBx[warp][s] = B.x; totBy[warp][s] = B.y; }
+    PT(7);
+    if (lane < M) { totA[warp][s] = A; totBx[warp][s] = B.x; totBy[warp][s] = B.y; }
     __syncthreads();
+    PT(8);
+    if (linked) {
+        if (tid < M && rank > 0) {                 // -> lower ranks
+            double tA = 1.0, tBx = 0.0, tBy = 0.0;
+            for (int q = nwarps - 1; q >= 0; --q) {
+                const double a = totA[q][s];
+                tBx = a * tBx + totBx[q][s];
+                tBy = a * tBy + totBy[q][s];
+                tA = a * tA;
+            }
+            for (int d = 0; d < rank; ++d) {
+                pb_send(&xchB[rank][s][0], &mbar[1], d, tA);
+                pb_send(&xchB[rank][s][1], &mbar[1], d, tBx);
+                pb_send(&xchB[rank][s][2], &mbar[1], d, tBy);
+            }
+        }
+        if (rank + 1 < nlink) pb_mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar[1]));
+    }
+    PT(9);
     {
         double pBx = 0.0, pBy = 0.0;
+        if (linked) {
+            for (int d = nlink - 1; d > rank; --d) {
+                const double a = xchB[d][s][0];
+                pBx = a * pBx + xchB[d][s][1];
+                pBy = a * pBy + xchB[d][s][2];
+            }
+        }
         for (int q = nwarps - 1; q > warp; --q) {
-            const double tA = totA[q][s];
-            pBx = tA * pBx + totBx[q][s];
-            pBy = tA * pBy + totBy[q][s];
+            const double a = totA[q][s];
+            pBx = a * pBx + totBx[q][s];
+            pBy = a * pBy + totBy[q][s];
         }
         carry.x = xA * pBx + xBx;
         carry.y = xA * pBy + xBy;
     }
     // ---- backward, pass 2; r becomes x
+    if (warp_work) {
 #pragma unroll
-    for (int i = L - 1; i >= 0; --i) {
-        carry.x = r[i].x - w[i + 1] * carry.x;
-        carry.y = r[i].y - w[i + 1] * carry.y;
-        r[i] = carry;
+        for (int i = L - 1; i >= 0; --i) {
+            carry.x = r[i].x - w[i + 1] * carry.x;
+            carry.y = r[i].y - w[i + 1] * carry.y;
+            r[i] = carry;
+        }
     }
 
     // ---- m = 0: remove the mean of diag(P) (cpu.py:342-352)
-    if (m0 == 0) {
+    if (diag0) {
         double sx = 0.0, sy = 0.0;
         if (s == 0) {
 #pragma unroll
             for (int i = 0; i < L; ++i)
-                if (k0 + i < n) { sx += r[i].x; sy += r[i].y; }
+                if (plo + i < nL) { sx += r[i].x; sy += r[i].y; }
         }
         for (int o = 16; o > 0; o >>= 1) {
             sx += __shfl_xor_sync(0xffffffffu, sx, o);
             sy += __shfl_xor_sync(0xffffffffu, sy, o);
         }
-        __syncthreads();
         if (lane == 0) { redx[warp] = sx; redy[warp] = sy; }
         __syncthreads();
         if (tid == 0) {
             double ax = 0.0, ay = 0.0;
             for (int q = 0; q < nwarps; ++q) { ax += redx[q]; ay += redy[q]; }
-            bcast = make_double2(ax / N, ay / N);
+            sumX[rank][0] = ax;
+            sumX[rank][1] = ay;
+            if (linked) {
+                for (int d = 0; d < nlink; ++d) {
+                    if (d == rank) continue;
+                    pb_send(&sumX[rank][0], &mbar[3], d, ax);
+                    pb_send(&sumX[rank][1], &mbar[3], d, ay);
+                }
+            }
         }
         __syncthreads();
+        if (linked) pb_mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar[3]));
+        double tx = 0.0, ty = 0.0;
+        for (int d = 0; d < nlink; ++d) { tx += sumX[d][0]; ty += sumX[d][1]; }
+        tx /= N;
+        ty /= N;
         if (s == 0) {
-            const double2 tr = bcast;
 #pragma unroll
-            for (int i = 0; i < L; ++i) { r[i].x -= tr.x; r[i].y -= tr.y; }
+            for (int i = 0; i < L; ++i)
+                if (plo + i < nL) { r[i].x -= tx; r[i].y -= ty; }
         }
     }
 
-    // ---- store P = eps x and its skew-Hermitian mirror (cpu.py:334,340; isospectral.py:492)
-    {
-        double2 *xp = X + e0;
-        double2 *xm = X + (unsigned)k0 * stride + (unsigned)m * (unsigned)N;
-        if (nvalid == L && m != 0) {
+    PT(10);
+    // ---- store P = eps x (cpu.py:334; isospectral.py:492) and stage it for the mirror
+    // tr_s[(pl, s)] with pl the local position; 64 bytes of padding per chunk keep both the chunk-major writes
+    // and the row-major reads below free of bank conflicts.
+    if (warp_work) {
+        double2 *ts = tr_s + (plo * M + s + c * 4);
+        if (nvalid == L) {
+            double2 *xp = X + ((unsigned)plo * stride + offD);
 #pragma unroll
             for (int i = 0; i < L; ++i) {
                 const double2 v = make_double2(eps * r[i].x, eps * r[i].y);
                 xp[(size_t)i * stride] = v;
-                xm[(size_t)i * stride] = make_double2(-v.x, v.y);
+                ts[i * M] = v;
             }
         } else {
 #pragma unroll
             for (int i = 0; i < L; ++i) {
-                if (i < nvalid) {
-                    const double2 v = make_double2(eps * r[i].x, eps * r[i].y);
-                    xp[(size_t)i * stride] = v;
-                    if (m != 0) xm[(size_t)i * stride] = make_double2(-v.x, v.y);
-                }
+                const int pl = plo + i;
+                const bool sh = pl >= PS;
+                const bool ok = sh ? (pl - PS < nS) : (pl < nL);
+                const double2 v = make_double2(eps * r[i].x, eps * r[i].y);
+                if (ok) X[(unsigned)pl * stride + (sh ? offS : offL)] = v;
+                ts[i * M] = v;
             }
         }
     }
+    PT(11);
+    __syncthreads();
+    PT(12);
+    // ---- mirror P[k+m, k] = -conj(P[k, k+m]) (cpu.py:340).  Row j of the mirror block holds the positions
+    // pl = j - s of the M diagonals in columns j - s: M lanes write M * 16 contiguous bytes.
+    if (warp_work) {
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+            const int pl = plo + i - s;
+            const bool sh = pl >= PS;
+            const bool ok = pl >= 0 && (sh ? (pl - PS < nS) : (pl < nL)) && (sh ? mS : mL) != 0;
+            if (ok) {
+                const double2 v = tr_s[pl * M + s + (pl / L) * 4];
+                X[(unsigned)pl * stride + (sh ? offMS : offML)] = make_double2(-v.x, v.y);
+            }
+        }
+    }
+    if (tid < M * (M - 1)) {   // rows PC .. PC+M-2 of the mirror block hold the last positions of diagonals s >= 1
+        const int pl = PC + (tid >> LOGM) - s;
+        const bool sh = pl >= PS;
+        const bool ok = pl < PC && (sh ? (pl - PS < nS) : (pl < nL)) && (sh ? mS : mL) != 0;
+        if (ok) {
+            const double2 v = tr_s[pl * M + s + (pl / L) * 4];
+            X[(unsigned)pl * stride + (sh ? offMS : offML)] = make_double2(-v.x, v.y);
+        }
+    }
+    PT(13);
 }
+
+#ifdef QF_PTRACE
+extern "C" int qf_ptrace_read(unsigned long long *out, int n)
+{
+    return (int)cudaMemcpyFromSymbol(out, g_ptrace, sizeof(unsigned long long) * (size_t)n);
+}
+#endif
 
 // W = Delta P for a general matrix (cpu.py:98-108); coefficients recomputed on the fly.
 __global__ void k_laplace(const double2 *__restrict__ P, double2 *__restrict__ W, int N)
@@ -467,29 +823,52 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
         k_whalf<<<gw, 256, 0, st>>>(W, dW, Wh, n2, h->ctrl, g);
         h->launches++;
     }
-    if (N <= 2048) {
-        // chunked scan: 4 diagonals per CTA, 16 positions per thread (QF_POISSON_GS=2 selects 2 diagonals per CTA)
-        const int chunks = (N + 15) / 16;
-        static bool attr_done = false;
-        if (!attr_done) {
-            QF_CUDA(cudaFuncSetAttribute(k_poisson_scan<16, 4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 16 * 8));
-            QF_CUDA(cudaFuncSetAttribute(k_poisson_scan<16, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 16 * 8));
-            attr_done = true;
+    if (h->p_L) {
+        const int L = h->p_L, M = h->p_M, CL = h->p_CL, NT = h->p_NT;
+        const int PC = (NT / M) * L;
+        const size_t smem = std::max((size_t)NT * L * 8, (size_t)(PC * M + (PC / L) * 4) * sizeof(double2));
+        void *fn = nullptr;
+#define QF_PB(LL, MM, CC)                                                                               \
+    if (L == LL && M == MM && CL == CC) fn = h->p_NTMAX == 512 ? (void *)k_poisson_band<LL, MM, CC, 512> : (void *)k_poisson_band<LL, MM, CC, 256>;
+        QF_PB(16, 8, 1) QF_PB(16, 8, 2) QF_PB(16, 8, 4) QF_PB(16, 8, 8) QF_PB(16, 4, 1) QF_PB(16, 4, 2) QF_PB(16, 4, 4) QF_PB(16, 4, 8)
+        QF_PB(8, 8, 1) QF_PB(8, 8, 2) QF_PB(8, 8, 4) QF_PB(8, 8, 8) QF_PB(8, 4, 1) QF_PB(8, 4, 2) QF_PB(8, 4, 4) QF_PB(8, 4, 8)
+#undef QF_PB
+        static void *attr_fn[32] = {nullptr};
+        bool seen = false;
+        for (void *f : attr_fn) seen |= (f == fn);
+        if (!seen) {
+            QF_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->p_NTMAX == 512 ? 144 * 1024 : 72 * 1024));
+            for (void *&f : attr_fn) if (!f) { f = fn; break; }
         }
-        static int gs = 0;
-        if (!gs) {
-            const char *env = getenv("QF_POISSON_GS");
-            gs = (env && env[0] == '2') ? 2 : 4;
+        static int pf = -1;
+        if (pf < 0) {
+            const char *env = getenv("QF_POISSON_PF");
+            pf = env ? atoi(env) : 1;
         }
-        if (gs == 4) {
-            const int threads = ((4 * chunks + 31) / 32) * 32;
-            dim3 grid((N + 3) / 4, h->batch);
-            k_poisson_scan<16, 4, 512><<<grid, threads, threads * 16 * sizeof(double), st>>>(Wh, P, h->tab_w, h->tab_iu, N, eps, h->ctrl, g);
-        } else {
-            const int threads = ((2 * chunks + 31) / 32) * 32;
-            dim3 grid((N + 1) / 2, h->batch);
-            k_poisson_scan<16, 2, 256><<<grid, threads, threads * 16 * sizeof(double), st>>>(Wh, P, h->tab_w, h->tab_iu, N, eps, h->ctrl, g);
-        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)h->p_nunits, (unsigned)h->batch);
+        cfg.blockDim = dim3((unsigned)NT);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)CL;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const double2 *a0 = Wh;
+        double2 *a1 = P;
+        const double *a2 = h->ptab_w, *a3 = h->ptab_iu;
+        const int4 *a4 = reinterpret_cast<const int4 *>(h->ptab_units);
+        int a5 = N, a6 = h->p_nunits;
+        // L2 prefetch distance = units resident at once: 2 CTAs per SM, a multiple of the cluster size
+        int a7 = pf ? (pf > 1 ? pf : (512 / h->p_NTMAX) * h->sm_count) / CL * CL : 0;
+        double a8 = eps;
+        const QfCtrl *a9 = h->ctrl;
+        int a10 = g;
+        void *args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10};
+        QF_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
         h->launches++;
     } else {
         // large-N fallback: one thread per diagonal

@@ -70,6 +70,15 @@ struct qf_handle_s {
     double *tab_iu = nullptr;  // 1/u_k,  u_k = d_k - w_k o_k
     double *tab_o = nullptr;   // o_k   (coupling to position k-1; quflow lap[...,1])
     double *tab_d = nullptr;   // d_k   (quflow lap[...,0], bc=False) — for laplace()
+    // band-packed factor tables of the clustered band kernel (poisson.cu: k_poisson_band)
+    double *ptab_w = nullptr, *ptab_iu = nullptr;
+    int *ptab_units = nullptr;      // [nunits][8] = bL, posbase, bS, PS, nlink, 0, 0, 0 (poisson.cu: qf_build_tables)
+    int p_L = 0;                    // positions per thread (0: band kernel not available for this N)
+    int p_M = 8;                    // diagonals per band
+    int p_CL = 1;                   // CTAs per cluster
+    int p_NT = 0;                   // threads per CTA
+    int p_NTMAX = 256;              // launch bound of the instantiation in use
+    int p_nunits = 0;               // CTAs in the launch
     // work matrices, batch * N * N complex128 each
     double2 *dW = nullptr, *Wh = nullptr, *P = nullptr, *A = nullptr, *S = nullptr, *scratch = nullptr;
     double2 *kahan_c = nullptr;   // compensation term (compsum), lazily allocated
