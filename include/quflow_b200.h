@@ -111,6 +111,40 @@ int qf_isomp_host(qf_handle_t h, void *W_host, double dt, int steps, double tol,
 int qf_solve_poisson_host(qf_handle_t h, const void *W_host, void *P_host);
 int qf_laplace_host(qf_handle_t h, const void *P_host, void *W_host);
 
+/* ---- host-stepped driver -----------------------------------------------------------------
+ * The callers' hooks of isomp_fixedpoint run HOST code inside the step: `callback(W, dW)`
+ * (isospectral.py:550-551), `forcing(P, W[, time])` (:403-414, :511-520, :594-596),
+ * `strang_splitting(dt/2, W)` (:466-467, :602-603) and custom or time-dependent Hamiltonians
+ * (:416-424, :488-491).  For them the same device kernels are driven one fixed-point iteration at a
+ * time; the host may read or replace the intermediate matrices between the calls.  One member
+ * (batch = 1), one GPU.  Call order per qf_isomp-equivalent run:
+ *   qf_step_open                                   dW = 0, tolerance from ||W||_inf      (:430, :440-452)
+ *   per step:   [W = strang(dt/2, W)]  qf_step_begin        W~ = W + dW, resnorm = inf   (:470-472, :481-482)
+ *     per iteration:  qf_step_hamiltonian  P~ = eps Delta^-1 W~                          (:489, :492)
+ *                     (or: write P into QF_BUF_P, then qf_step_scale_p(h, 0))
+ *                     qf_step_products     A = P~ W~,  S = A P~                          (:496, :499)
+ *                     [qf_step_scale_p(h, 1); FW = forcing(QF_BUF_P, QF_BUF_WHALF)]      (:513-517)
+ *                     qf_step_close_iteration   dW = S + (A - A^H) [+ fscale FW], residual and stopping
+ *                                               rule; *active = 0 ends the loop          (:503-536)
+ *     [qf_step_increment -> callback(W, dW)]  qf_step_update   W += 2 (A - A^H) [+ 2 fscale FW]  (:547-596)
+ *   qf_step_stats
+ * Every matrix on this path is assumed skew-Hermitian (as the reference's solve_poisson and
+ * conj_subtract_ assume); FW is read in full. */
+#define QF_BUF_WHALF 0    /* W~ = W + dW, the midpoint state the Hamiltonian and the forcing receive */
+#define QF_BUF_P 1        /* P~ (scaled by eps) / P (after qf_step_scale_p(h, 1)) */
+#define QF_BUF_SCRATCH 2  /* free N x N buffer (used by the Python side for the callback increment) */
+int qf_step_open(qf_handle_t h, const void *W_dev, double dt, double tol, unsigned flags, double *tol_used, void *stream);
+int qf_step_begin(qf_handle_t h, const void *W_dev, void *stream);
+void *qf_step_buffer(qf_handle_t h, int which);   /* device pointer owned by the handle, NULL for a bad index */
+int qf_step_hamiltonian(qf_handle_t h, void *stream);
+int qf_step_scale_p(qf_handle_t h, int divide, void *stream);   /* QF_BUF_P *= eps (0) or /= eps (1) */
+int qf_step_products(qf_handle_t h, void *stream);
+int qf_step_close_iteration(qf_handle_t h, const void *W_dev, const void *F_dev /* may be NULL */, double fscale,
+                            int maxit, int minit, int *active, double *resnorm, void *stream);
+int qf_step_increment(qf_handle_t h, void *out_dev, void *stream);   /* out = 2 (A - A^H) */
+int qf_step_update(qf_handle_t h, void *W_dev, const void *F_dev /* may be NULL */, double fscale, void *stream);
+int qf_step_stats(qf_handle_t h, qf_stats *stats, void *stream);
+
 /* Introspection used by bench.py: number of kernels this library launched since creation
  * of the handle, and per-phase device time of the last qf_profile_iteration call. */
 int64_t qf_launch_count(qf_handle_t h);

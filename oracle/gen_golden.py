@@ -201,8 +201,52 @@ def gen_isomp_smooth():
         save(f"isomp_S_N{N}.npz", **arrays)
 
 
+# ---------------------------------------------------------------------------
+# H. the callers' hooks of the loop: callback, forcing, strang_splitting, custom / time-dependent Hamiltonians
+# ---------------------------------------------------------------------------
+def gen_hooks():
+    from oracle import hooks
+    print("H. isomp with caller hooks on R(32,42), 30 steps")
+    N, steps = 32, 30
+    W0 = random_skewherm(N, 42)
+    dt = 0.25 * hbar(N)
+    arrays = dict(W0=W0, dt=dt, steps=steps)
+    for case in hooks.CASES:
+        kw = hooks.case_kwargs(case, lambda W: qucpu.solve_poisson(W).copy())
+        per_step, cb_norms = [], []
+        calls, last = [0], [0]
+        ham = kw.pop("hamiltonian", None)
+        if ham is None:
+            def counted(W):
+                calls[0] += 1
+                return qucpu.solve_poisson(W)
+        elif "time" in ham.__code__.co_varnames:
+            def counted(W, time=0.0, _h=ham):
+                calls[0] += 1
+                return _h(W, time=time)
+        else:
+            def counted(W, _h=ham):
+                calls[0] += 1
+                return _h(W)
+
+        def callback(W, dW):
+            per_step.append(calls[0] - last[0])
+            last[0] = calls[0]
+            cb_norms.append((np.linalg.norm(W), np.linalg.norm(dW)))
+
+        stats = {'iterations': 0.0}
+        W = isomp_fixedpoint(W0.copy(), dt, steps=steps, hamiltonian=counted, stats=stats, callback=callback, **kw)
+        its = np.array(per_step, dtype=np.int32)
+        if "time" in kw and ham is not None:
+            its[0] -= 1          # the autonomy probe hamiltonian(W, time=time) of isospectral.py:419-421
+        print(f"   {case:13s} it/step={stats['iterations']:.3f}  |W|={np.linalg.norm(W):.6f}")
+        arrays.update({f"{case}_Wfinal": W, f"{case}_iterations": its, f"{case}_tol_auto": stats['tol_auto'],
+                       f"{case}_mean_iterations": stats['iterations'], f"{case}_cb_norms": np.array(cb_norms)})
+    save("isomp_hooks_N32.npz", **arrays)
+
+
 if __name__ == "__main__":
-    parts = dict(A=gen_reference_golden, B=gen_poisson, C=gen_isomp_random, S=gen_isomp_smooth)
+    parts = dict(A=gen_reference_golden, B=gen_poisson, C=gen_isomp_random, S=gen_isomp_smooth, H=gen_hooks)
     for key in (sys.argv[1:] or list(parts)):
         parts[key]()
     print("done")

@@ -193,18 +193,36 @@ def isomp_fixedpoint(W, dt, steps=100, hamiltonian=None, time=None, forcing=None
                      record=None):
     """Isospectral midpoint by fixed-point iteration, isospectral.py:338-613.
 
-    Restated for the in-scope configuration (autonomous Hamiltonian, 2-D state);
-    ``forcing`` / ``strang_splitting`` are outside the hot path and rejected.
+    Restated for a 2-D state, including the callers' hooks of the loop: ``callback`` (:550-551),
+    ``forcing`` (:403-414, :511-520, :594-596), ``strang_splitting`` (:466-467, :602-603) and custom or
+    time-dependent Hamiltonians (:416-424, :488-491).
     ``record`` (oracle-only extra): dict that receives per-step ``iterations``
     and ``resnorm`` lists so tests can compare iteration counts step by step.
     """
     assert minit >= 1, "minit must be at least 1."          # :400
     assert maxit >= minit, "maxit must be at minit."         # :401
-    if forcing is not None or strang_splitting is not None:
-        raise NotImplementedError("oracle covers the autonomous isomp hot path only")
     if hamiltonian is None:
         hamiltonian = solve_poisson
     assert W.ndim == 2
+
+    if forcing is not None:                                  # :403-414
+        autonomous_force = True
+        if time is not None:
+            try:
+                FW = forcing(W, W, time=time)
+            except TypeError:
+                pass
+            else:
+                autonomous_force = False
+        FW = np.zeros_like(W)
+    autonomous = True                                        # :416-424
+    if time is not None:
+        try:
+            Phalf = hamiltonian(W, time=time)
+        except TypeError:
+            pass
+        else:
+            autonomous = False
 
     total_iterations = 0                                     # :426-427
     number_of_maxit = 0
@@ -237,6 +255,8 @@ def isomp_fixedpoint(W, dt, steps=100, hamiltonian=None, time=None, forcing=None
         record['tol'] = float(tol)
 
     for k in range(steps):                                   # :463
+        if strang_splitting:                                 # :466-467
+            W = strang_splitting(dt / 2, W)
         resnorm = np.inf                                     # :470-472
         if reinitialize:
             dW.fill(0.0)
@@ -247,12 +267,23 @@ def isomp_fixedpoint(W, dt, steps=100, hamiltonian=None, time=None, forcing=None
             np.copyto(Whalf, W)                              # :481-482
             Whalf += dW
             np.copyto(dW_old, dW)                            # :485
-            Phalf = hamiltonian(Whalf)                       # :489
+            if autonomous:                                   # :488-491
+                Phalf = hamiltonian(Whalf)
+            else:
+                Phalf = hamiltonian(Whalf, time=time + dt / 2)
             Phalf *= vareps                                  # :492
             np.matmul(Phalf, Whalf, out=PWcomm)              # :496
             np.matmul(PWcomm, Phalf, out=dW)                 # :499
             conj_subtract_(PWcomm, PWcomm)                   # :503
             dW += PWcomm                                     # :509
+            if forcing:                                      # :511-520
+                Phalf /= vareps
+                if autonomous_force:
+                    FW = forcing(Phalf, Whalf)
+                else:
+                    FW = forcing(Phalf, Whalf, time=time + dt / 2)
+                FW *= dt / 2
+                dW += FW
             if i + 1 >= minit:                               # :523-536
                 resnorm_old = resnorm
                 dW_old -= dW
@@ -282,10 +313,17 @@ def isomp_fixedpoint(W, dt, steps=100, hamiltonian=None, time=None, forcing=None
             np.copyto(c_compsum, delta_compsum)
             c_compsum -= y_compsum
             np.copyto(W, t_compsum)
+            if forcing:                                      # :588-589
+                raise NotImplementedError("Compensated sum with forcing is not yet implemented.")
         else:
             W += PWcomm                                      # :592
+            if forcing:                                      # :594-596
+                FW *= 2
+                W += FW
         if time is not None:                                 # :598-599
             time += dt
+        if strang_splitting:                                 # :602-603
+            W = strang_splitting(dt / 2, W)
 
     if verbatim:
         print("Average number of iterations per step: {:.2f}".format(total_iterations / steps))

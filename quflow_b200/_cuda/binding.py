@@ -25,6 +25,7 @@ QF_FLAG_COMPSUM = 1
 QF_FLAG_REINITIALIZE = 2
 QF_UNIQUE_ID_BYTES = 128
 QF_P2P_BLOB_BYTES = 256
+QF_BUF_WHALF, QF_BUF_P, QF_BUF_SCRATCH = 0, 1, 2
 
 
 class QfError(RuntimeError):
@@ -64,6 +65,16 @@ SYMBOLS = {
     "qf_isomp_host": (_i, [_vp, _vp, _d, _i, _d, _i, _i, _u, ctypes.POINTER(qf_stats), ctypes.POINTER(ctypes.c_int32)]),
     "qf_solve_poisson_host": (_i, [_vp, _vp, _vp]),
     "qf_laplace_host": (_i, [_vp, _vp, _vp]),
+    "qf_step_open": (_i, [_vp, _vp, _d, _d, _u, ctypes.POINTER(_d), _vp]),
+    "qf_step_begin": (_i, [_vp, _vp, _vp]),
+    "qf_step_buffer": (_vp, [_vp, _i]),
+    "qf_step_hamiltonian": (_i, [_vp, _vp]),
+    "qf_step_scale_p": (_i, [_vp, _i, _vp]),
+    "qf_step_products": (_i, [_vp, _vp]),
+    "qf_step_close_iteration": (_i, [_vp, _vp, _vp, _d, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_d), _vp]),
+    "qf_step_increment": (_i, [_vp, _vp, _vp]),
+    "qf_step_update": (_i, [_vp, _vp, _vp, _d, _vp]),
+    "qf_step_stats": (_i, [_vp, ctypes.POINTER(qf_stats), _vp]),
     "qf_launch_count": (ctypes.c_int64, [_vp]),
     "qf_gemm_executed_flops": (_d, [_vp, _i]),
     "qf_gemm_is_3m": (_i, [_vp]),
@@ -231,6 +242,63 @@ class Handle:
         if want_iters:
             iters = iters[:, :steps]
         return out, iters
+
+    # -- host-stepped driver (include/quflow_b200.h, "host-stepped driver") -----------------
+    def buffer_tensor(self, which: int):
+        """A torch view (N, N) complex128 of one of the handle's device buffers (QF_BUF_*)."""
+        import torch
+        ptr = self._lib.qf_step_buffer(self._h, int(which))
+        if not ptr:
+            raise QfError(QF_ERR_INVALID, f"qf_step_buffer({which}) returned NULL")
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (self.N, self.N), "typestr": "<c16", "data": (int(ptr), False),
+                                        "version": 2, "strides": None}
+        return torch.as_tensor(_View(), device=f"cuda:{self.device}")
+
+    def step_open(self, W, dt, tol=-1.0, compsum=False, reinitialize=False) -> float:
+        flags = (QF_FLAG_COMPSUM if compsum else 0) | (QF_FLAG_REINITIALIZE if reinitialize else 0)
+        used = _d(0.0)
+        _check(self._lib.qf_step_open(self._h, _dev_ptr(W), float(dt), float(tol), flags, ctypes.byref(used), _stream_ptr()))
+        return used.value
+
+    def step_begin(self, W):
+        _check(self._lib.qf_step_begin(self._h, _dev_ptr(W), _stream_ptr()))
+
+    def step_hamiltonian(self):
+        _check(self._lib.qf_step_hamiltonian(self._h, _stream_ptr()))
+
+    def step_scale_p(self, divide: bool):
+        _check(self._lib.qf_step_scale_p(self._h, 1 if divide else 0, _stream_ptr()))
+
+    def step_products(self):
+        _check(self._lib.qf_step_products(self._h, _stream_ptr()))
+
+    def step_close_iteration(self, W, F, fscale, maxit, minit):
+        """Returns (loop continues?, residual).  Raises ValueError on a non-finite residual like scipy.linalg.norm."""
+        active, res = _i(0), _d(0.0)
+        rc = self._lib.qf_step_close_iteration(self._h, _dev_ptr(W), _dev_ptr(F) if F is not None else None, float(fscale),
+                                               int(maxit), int(minit), ctypes.byref(active), ctypes.byref(res), _stream_ptr())
+        if rc == QF_ERR_NONFINITE:
+            raise ValueError("array must not contain infs or NaNs")
+        _check(rc)
+        return bool(active.value), res.value
+
+    def step_increment(self, out):
+        _check(self._lib.qf_step_increment(self._h, _dev_ptr(out), _stream_ptr()))
+        return out
+
+    def step_update(self, W, F, fscale):
+        rc = self._lib.qf_step_update(self._h, _dev_ptr(W), _dev_ptr(F) if F is not None else None, float(fscale), _stream_ptr())
+        if rc == QF_ERR_UNSUPPORTED:
+            raise NotImplementedError(self._lib.qf_last_error().decode())
+        _check(rc)
+
+    def step_stats(self):
+        st = qf_stats()
+        _check(self._lib.qf_step_stats(self._h, ctypes.byref(st), _stream_ptr()))
+        return dict(tol_used=st.tol_used, last_resnorm=st.last_resnorm, total_iterations=int(st.total_iterations),
+                    number_of_maxit=int(st.number_of_maxit), steps_done=int(st.steps_done))
 
     def profile_iteration(self, W, dt, reps=5):
         pt = qf_phase_times()

@@ -88,9 +88,11 @@ __global__ void k_zero(double2 *X, size_t n2, const QfCtrl *__restrict__ ctrl)
 // dW_ij = d, dW_ji = -conj(d);  deterministic partial row sums of r for the infinity norm:
 //   direct[i][bj] = sum_{j in tile, j >= i} r_ij      mirr[j][bi] = sum_{i in tile, i < j} r_ij
 // It also writes the next iterate W~ = W + dW (both triangles), so no separate pass is needed before the Poisson solve.
+template <bool FORCING>
 __global__ void __launch_bounds__(256)
 k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *__restrict__ dWg, double *__restrict__ rowpart,
-       int N, int nslots, const QfCtrl *__restrict__ ctrl, int hb, int G, const double2 *__restrict__ Wg, double2 *__restrict__ Whg)
+       int N, int nslots, const QfCtrl *__restrict__ ctrl, int hb, int G, const double2 *__restrict__ Wg, double2 *__restrict__ Whg,
+       const double2 *__restrict__ Fg, double fscale)
 {
     const int b = blockIdx.z;
     if (!ctrl[b].active) return;
@@ -105,6 +107,7 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
     double2 *dW = dWg + off;
     const double2 *W = Wg + off;
     double2 *Wh = Whg + off;
+    const double2 *F = FORCING ? Fg + off : nullptr;
     double *direct = rowpart + ((size_t)b * 2 + 0) * nslots * N;
     double *mirr = rowpart + ((size_t)b * 2 + 1) * nslots * N;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -130,12 +133,14 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
             double2 s = S[pij];
             if (i == j) s.x = 0.0;                                    // P W P is skew-Hermitian
             d = zadd(s, c);                                           // :499,:509
+            double2 dn = d;
+            if (FORCING) dn = zadd(d, zscale(fscale, F[ij]));         // dW += FW * dt/2  (:518-520)
             const double2 old = dW[ij];
-            r = zabs(zsub(old, d));                                   // :526,:534
-            dW[ij] = d;
-            Wh[ij] = zadd(W[ij], d);                                  // next iterate W~ = W + dW (:481-482)
+            r = zabs(zsub(old, dn));                                  // :526,:534
+            dW[ij] = dn;
+            Wh[ij] = zadd(W[ij], dn);                                 // next iterate W~ = W + dW (:481-482)
         }
-        D[ii][tx] = d;
+        D[ii][tx] = d;                                                // without the forcing term: mirrored below
         R[ii][tx] = r;
         // direct row sum over the 32 columns of this tile (fixed shuffle tree => deterministic)
         double s = r;
@@ -147,13 +152,21 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
     for (int q = 0; q < 4; ++q) {
         const int jj = ty + 8 * q;
         const int j = bj * TS + jj, i = bi * TS + tx;
+        double rl = 0.0;
         if (j < N && i < N && i < j) {
+            const size_t ji = (size_t)j * N + i;
             const double2 d = D[tx][jj];
-            const double2 dm = make_double2(-d.x, d.y);
-            dW[(size_t)j * N + i] = dm;
-            Wh[(size_t)j * N + i] = zadd(W[(size_t)j * N + i], dm);
+            double2 dm = make_double2(-d.x, d.y);
+            if (FORCING) {                                            // the forcing term of the lower triangle is its own
+                dm = zadd(dm, zscale(fscale, F[ji]));
+                rl = zabs(zsub(dW[ji], dm));
+            } else {
+                rl = R[tx][jj];
+            }
+            dW[ji] = dm;
+            Wh[ji] = zadd(W[ji], dm);
         }
-        double s = (i < j) ? R[tx][jj] : 0.0;
+        double s = rl;
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (tx == 0 && j < N) mirr[(size_t)j * nslots + bi] = s;
     }
@@ -226,10 +239,11 @@ __device__ __forceinline__ double2 kahan_add(double2 w, double2 inc, double2 &kc
     return tt;                                // :586
 }
 
-template <bool COMPSUM>
+template <bool COMPSUM, bool FORCING>
 __global__ void __launch_bounds__(256)
 k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__restrict__ Kg, int N, QfCtrl *ctrl,
-         int32_t *iters, int steps_cap, int hb, int G, const double2 *__restrict__ dWg, double2 *__restrict__ Whg, int reinit)
+         int32_t *iters, int steps_cap, int hb, int G, const double2 *__restrict__ dWg, double2 *__restrict__ Whg, int reinit,
+         const double2 *__restrict__ Fg, double fscale)
 {
     const int b = blockIdx.z;
     QfCtrl &c = ctrl[b];
@@ -247,6 +261,7 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
     double2 *K = COMPSUM ? Kg + off : nullptr;
     const double2 *dW = dWg + off;
     double2 *Wh = Whg + off;
+    const double2 *F = FORCING ? Fg + off : nullptr;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -272,6 +287,7 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
                 K[ij] = kc;
             } else {
                 w = zadd(w, cm);                                       // :592
+                if (FORCING) w = zadd(w, zscale(2.0, zscale(fscale, F[ij])));   // FW *= 2; W += FW (:594-596)
             }
             W[ij] = w;
             Wh[ij] = reinit ? w : zadd(w, dW[ij]);
@@ -297,10 +313,66 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
                 K[ji] = kc;
             } else {
                 w = zadd(w, cm);
+                if (FORCING) w = zadd(w, zscale(2.0, zscale(fscale, F[ji])));
             }
             W[ji] = w;
             Wh[ji] = reinit ? w : zadd(w, dW[ji]);
         }
+    }
+}
+
+// out = 2 (A - A^H): the increment handed to `callback(W, dW)` just before the update (isospectral.py:547-551)
+__global__ void __launch_bounds__(256)
+k_increment(const double2 *__restrict__ Ag, double2 *__restrict__ Og, int N, int hb, int G)
+{
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bi > bj) return;
+    __shared__ double2 T[TS][TS + 1];
+    const size_t off = (size_t)blockIdx.z * N * N;
+    const double2 *A = Ag + off;
+    double2 *O = Og + off;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int jj = ty + 8 * q;
+        const int j = bj * TS + jj, i = bi * TS + tx;
+        T[jj][tx] = (j < N && i < N) ? A[(size_t)qf_prow(j, hb, G) * N + i] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    double2 cv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int ii = ty + 8 * q;
+        const int i = bi * TS + ii, j = bj * TS + tx;
+        double2 cm = make_double2(0.0, 0.0);
+        if (i < N && j < N && i <= j) {
+            cm = zsub(A[(size_t)qf_prow(i, hb, G) * N + j], zconj(T[tx][ii]));
+            cm = make_double2(2.0 * cm.x, 2.0 * cm.y);
+            O[(size_t)i * N + j] = cm;
+        }
+        cv[q] = cm;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) T[ty + 8 * q][tx] = cv[q];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int jj = ty + 8 * q;
+        const int j = bj * TS + jj, i = bi * TS + tx;
+        if (j < N && i < N && i < j) {
+            const double2 cu = T[tx][jj];
+            O[(size_t)j * N + i] = make_double2(-cu.x, cu.y);
+        }
+    }
+}
+
+// X *= s  or  X /= s  (Phalf *= vareps, isospectral.py:492;  Phalf /= vareps, :513)
+__global__ void k_scale(double2 *X, size_t n, double s, int divide)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double2 v = X[i];
+        X[i] = divide ? make_double2(v.x / s, v.y / s) : make_double2(v.x * s, v.y * s);
     }
 }
 
@@ -342,7 +414,7 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
     if (ev) QF_CUDA(cudaEventRecord(ev[3], st));
     const int nb = (N + TS - 1) / TS;
     dim3 g(nb, nb, h->batch);
-    k_post<<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, G, W, h->Wh);
+    k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, G, W, h->Wh, nullptr, 0.0);
     k_control<<<dim3((N + 7) / 8, h->batch), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit);
     h->launches += 2;
     if (ev) QF_CUDA(cudaEventRecord(ev[4], st));
@@ -357,9 +429,9 @@ int qf_enqueue_update(qf_handle_s *h, double2 *W, bool compsum, bool reinit, cud
     const int hb = qf_block_rows(N, h->nranks);
     dim3 g(nb, nb, h->batch);
     if (compsum)
-        k_update<true><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks, h->dW, h->Wh, reinit ? 1 : 0);
+        k_update<true, false><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks, h->dW, h->Wh, reinit ? 1 : 0, nullptr, 0.0);
     else
-        k_update<false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks, h->dW, h->Wh, reinit ? 1 : 0);
+        k_update<false, false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks, h->dW, h->Wh, reinit ? 1 : 0, nullptr, 0.0);
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;
@@ -490,11 +562,13 @@ static int build_step_graph(qf_handle_s *h, double2 *W, double eps, int maxit, i
     double2 *Kp = h->kahan_c;
     int32_t *iters = h->iters_dev;
     int steps_cap = h->steps_cap, hb = qf_block_rows(N, h->nranks), G = h->nranks, Nv = N;
-    void *upd = compsum ? (void *)k_update<true> : (void *)k_update<false>;
+    void *upd = compsum ? (void *)k_update<true, false> : (void *)k_update<false, false>;
     const double2 *dWp = h->dW;
     double2 *Whp = h->Wh;
     int reinit_i = reinit ? 1 : 0;
-    QF_G(add_kernel_node(&n_update, g->graph, &n_while, 1, upd, gu, dim3(256), Ap, W, Kp, Nv, ctrl, iters, steps_cap, hb, G, dWp, Whp, reinit_i));
+    const double2 *Fnull = nullptr;
+    double fzero = 0.0;
+    QF_G(add_kernel_node(&n_update, g->graph, &n_while, 1, upd, gu, dim3(256), Ap, W, Kp, Nv, ctrl, iters, steps_cap, hb, G, dWp, Whp, reinit_i, Fnull, fzero));
     QF_G(cudaGraphInstantiate(&g->exec, g->graph, 0));
 #undef QF_G
     h->step_graph = g;
@@ -595,6 +669,182 @@ extern "C" int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double
         }
     }
     return rc;
+}
+
+// ------------------------------------------------------------------------------- host-stepped driver
+// The same kernels as qf_isomp, driven one fixed-point iteration at a time by the host, for callers whose step
+// contains host code: callback (isospectral.py:550-551), forcing (:403-414, :511-520, :594-596), strang_splitting
+// (:466-467, :602-603), custom or time-dependent Hamiltonians (:416-424, :488-491).
+static int step_check(qf_handle_s *h, const char *who)
+{
+    if (!h) { qf_set_error("%s: null handle", who); return QF_ERR_INVALID; }
+    if (h->batch != 1 || h->nranks != 1) { qf_set_error("%s: the host-stepped driver runs one member on one GPU", who); return QF_ERR_UNSUPPORTED; }
+    if (!h->step_open) { qf_set_error("%s: qf_step_open was not called", who); return QF_ERR_INVALID; }
+    return QF_OK;
+}
+
+extern "C" int qf_step_open(qf_handle_t h, const void *W_dev, double dt, double tol, unsigned flags, double *tol_used, void *stream)
+{
+    if (!h || !W_dev) { qf_set_error("qf_step_open: null argument"); return QF_ERR_INVALID; }
+    if (h->batch != 1 || h->nranks != 1) { qf_set_error("qf_step_open: the host-stepped driver runs one member on one GPU"); return QF_ERR_UNSUPPORTED; }
+    QF_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n2 = h->mat_elems;
+    const bool compsum = (flags & QF_FLAG_COMPSUM) != 0;
+    if (compsum && !h->kahan_c) QF_CUDA(cudaMalloc(&h->kahan_c, sizeof(double2) * n2));
+    const double hb = qf_hbar(h->N);
+    h->step_eps = dt / (2.0 * hb);                                          // isospectral.py:436-437
+    h->step_flags = flags;
+    double mach_eps = 2.220446049250313e-16;
+    if (!compsum) mach_eps = sqrt(mach_eps);                                // :441-443
+    QF_CUDA(cudaMemsetAsync(h->dW, 0, sizeof(double2) * n2, st));           // :430
+    if (compsum) QF_CUDA(cudaMemsetAsync(h->kahan_c, 0, sizeof(double2) * n2, st));
+    QF_CHECK(qf_launch_norm_inf(h, (const double2 *)W_dev, st));
+    k_call_begin<<<1, 1, 0, st>>>(h->ctrl, tol, mach_eps * dt / hb);        // :440-448
+    h->launches++;
+    QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl), cudaMemcpyDeviceToHost, st));
+    QF_CUDA(cudaStreamSynchronize(st));
+    if (tol_used) *tol_used = h->ctrl_host[0].tol;
+    h->step_open = 1;
+    return QF_OK;
+}
+
+extern "C" int qf_step_begin(qf_handle_t h, const void *W_dev, void *stream)
+{
+    QF_CHECK(step_check(h, "qf_step_begin"));
+    if (!W_dev) { qf_set_error("qf_step_begin: null W"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n2 = h->mat_elems;
+    k_step_begin<<<1, 1, 0, st>>>(h->ctrl, 1, 0, 0);                        // resnorm = inf (:470)
+    h->launches++;
+    if (h->step_flags & QF_FLAG_REINITIALIZE) QF_CUDA(cudaMemsetAsync(h->dW, 0, sizeof(double2) * n2, st));   // :471-472
+    QF_CHECK(qf_launch_whalf(h, (const double2 *)W_dev, h->dW, h->Wh, st));   // W~ = W + dW (:481-482); W may have been changed by the host
+    return QF_OK;
+}
+
+extern "C" void *qf_step_buffer(qf_handle_t h, int which)
+{
+    if (!h) return nullptr;
+    switch (which) {
+        case QF_BUF_WHALF: return h->Wh;
+        case QF_BUF_P: return h->P;
+        case QF_BUF_SCRATCH: return h->scratch;
+        default: return nullptr;
+    }
+}
+
+extern "C" int qf_step_hamiltonian(qf_handle_t h, void *stream)
+{
+    QF_CHECK(step_check(h, "qf_step_hamiltonian"));
+    QF_CUDA(cudaSetDevice(h->device));
+    return qf_launch_poisson(h, h->Wh, nullptr, h->Wh, h->P, h->step_eps, true, (cudaStream_t)stream);   // :489,:492
+}
+
+extern "C" int qf_step_scale_p(qf_handle_t h, int divide, void *stream)
+{
+    QF_CHECK(step_check(h, "qf_step_scale_p"));
+    QF_CUDA(cudaSetDevice(h->device));
+    const size_t n2 = h->mat_elems;
+    k_scale<<<(unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)h->sm_count * 8), 256, 0, (cudaStream_t)stream>>>(h->P, n2, h->step_eps, divide);
+    h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
+extern "C" int qf_step_products(qf_handle_t h, void *stream)
+{
+    QF_CHECK(step_check(h, "qf_step_products"));
+    QF_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    QF_CHECK(qf_launch_zgemm(h, h->P, h->Wh, h->A, false, true, -1, 1, false, st));   // :496
+    QF_CHECK(qf_launch_zgemm(h, h->A, h->P, h->S, true, true, -1, 1, true, st));      // :499
+    return QF_OK;
+}
+
+extern "C" int qf_step_close_iteration(qf_handle_t h, const void *W_dev, const void *F_dev, double fscale, int maxit, int minit,
+                                       int *active, double *resnorm, void *stream)
+{
+    QF_CHECK(step_check(h, "qf_step_close_iteration"));
+    if (!W_dev) { qf_set_error("qf_step_close_iteration: null W"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->N;
+    const int nb = (N + TS - 1) / TS;
+    dim3 g(nb, nb, 1);
+    if (F_dev)
+        k_post<true><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, N, 1, (const double2 *)W_dev, h->Wh,
+                                        (const double2 *)F_dev, fscale);
+    else
+        k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, N, 1, (const double2 *)W_dev, h->Wh, nullptr, 0.0);
+    k_control<<<dim3((N + 7) / 8, 1), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit);
+    h->launches += 2;
+    QF_CUDA(cudaGetLastError());
+    QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl), cudaMemcpyDeviceToHost, st));
+    QF_CUDA(cudaStreamSynchronize(st));
+    const QfCtrl &c = h->ctrl_host[0];
+    if (active) *active = c.active;
+    if (resnorm) *resnorm = c.resnorm;
+    if (c.nonfinite) {
+        qf_set_error("array must not contain infs or NaNs");
+        return QF_ERR_NONFINITE;
+    }
+    return QF_OK;
+}
+
+extern "C" int qf_step_increment(qf_handle_t h, void *out_dev, void *stream)
+{
+    QF_CHECK(step_check(h, "qf_step_increment"));
+    if (!out_dev) { qf_set_error("qf_step_increment: null output"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    const int N = h->N;
+    const int nb = (N + TS - 1) / TS;
+    k_increment<<<dim3(nb, nb, 1), 256, 0, (cudaStream_t)stream>>>(h->A, (double2 *)out_dev, N, N, 1);
+    h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
+extern "C" int qf_step_update(qf_handle_t h, void *W_dev, const void *F_dev, double fscale, void *stream)
+{
+    QF_CHECK(step_check(h, "qf_step_update"));
+    if (!W_dev) { qf_set_error("qf_step_update: null W"); return QF_ERR_INVALID; }
+    const bool compsum = (h->step_flags & QF_FLAG_COMPSUM) != 0;
+    if (compsum && F_dev) { qf_set_error("Compensated sum with forcing is not yet implemented."); return QF_ERR_UNSUPPORTED; }   // :588-589
+    QF_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->N;
+    const int nb = (N + TS - 1) / TS;
+    dim3 g(nb, nb, 1);
+    const int reinit = (h->step_flags & QF_FLAG_REINITIALIZE) ? 1 : 0;
+    double2 *W = (double2 *)W_dev;
+    if (compsum)
+        k_update<true, false><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, nullptr, 0.0);
+    else if (F_dev)
+        k_update<false, true><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, (const double2 *)F_dev, fscale);
+    else
+        k_update<false, false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, nullptr, 0.0);
+    h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
+extern "C" int qf_step_stats(qf_handle_t h, qf_stats *stats, void *stream)
+{
+    QF_CHECK(step_check(h, "qf_step_stats"));
+    if (!stats) { qf_set_error("qf_step_stats: null output"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl), cudaMemcpyDeviceToHost, st));
+    QF_CUDA(cudaStreamSynchronize(st));
+    const QfCtrl &c = h->ctrl_host[0];
+    stats->tol_used = c.tol;
+    stats->last_resnorm = c.resnorm;
+    stats->total_iterations = c.total_it;
+    stats->number_of_maxit = c.n_maxit;
+    stats->nonfinite = c.nonfinite;
+    stats->steps_done = c.steps_done;
+    return QF_OK;
 }
 
 extern "C" int qf_profile_iteration(qf_handle_t h, const void *W_dev, double dt, int reps, qf_phase_times *out, void *stream)

@@ -882,6 +882,17 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
     return QF_OK;
 }
 
+// Wh = W + dW (all members, ungated)
+int qf_launch_whalf(qf_handle_s *h, const double2 *W, const double2 *dW, double2 *Wh, cudaStream_t st)
+{
+    const size_t n2 = h->mat_elems;
+    dim3 gw((unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)h->sm_count * 8), h->batch);
+    k_whalf<<<gw, 256, 0, st>>>(W, dW, Wh, n2, h->ctrl, 0);
+    h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
 int qf_launch_laplace(qf_handle_s *h, const double2 *P, double2 *W, cudaStream_t st)
 {
     const int N = h->N;

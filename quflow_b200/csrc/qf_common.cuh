@@ -103,6 +103,10 @@ struct qf_handle_s {
     void *step_graph = nullptr;
     cudaStream_t cap_stream = nullptr;
     int use_graph = 1;
+    // host-stepped driver (qf_step_*): parameters fixed by qf_step_open
+    double step_eps = 0.0;
+    unsigned step_flags = 0;
+    int step_open = 0;
     int graph_warned = 0;
 };
 
@@ -115,6 +119,7 @@ int qf_build_tables(qf_handle_s *h);
 int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, double2 *Wh, double2 *P, double eps,
                       bool gated, cudaStream_t st);
 int qf_launch_laplace(qf_handle_s *h, const double2 *P, double2 *W, cudaStream_t st);
+int qf_launch_whalf(qf_handle_s *h, const double2 *W, const double2 *dW, double2 *Wh, cudaStream_t st);
 
 // zgemm.cu
 int qf_gemm_create(qf_handle_s *h);

@@ -289,7 +289,11 @@ def solve(W,
     # device-resident fast path: keep the state on the GPU across output intervals
     host_out = None
     Wdev = W
-    on_device = integrator is isomp and not _is_torch(W)
+    # (hooks that run host code must see arrays of the caller's kind, so they keep the numpy calling convention)
+    from .integrators import _is_default_hamiltonian
+    host_hooks = (ikw.get('forcing') is not None or ikw.get('strang_splitting') is not None or ikw.get('callback') is not None
+                  or not _is_default_hamiltonian(ikw.get('hamiltonian')))
+    on_device = integrator is isomp and not _is_torch(W) and not host_hooks
     if on_device:
         import torch
         if not (isinstance(W, np.ndarray) and W.dtype == np.complex128 and W.flags.c_contiguous and W.ndim == 2):

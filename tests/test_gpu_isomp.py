@@ -151,13 +151,77 @@ def test_python_api_semantics(qf):
         qf.isomp(W0.copy(), dt, 1, minit=0)
     with pytest.raises(AssertionError):
         qf.isomp(W0.copy(), dt, 1, minit=4, maxit=3)
-    with pytest.raises(NotImplementedError):
-        qf.isomp(W0.copy(), dt, 1, hamiltonian=lambda X: X)
-    with pytest.raises(NotImplementedError):
-        qf.isomp(W0.copy(), dt, 1, forcing=lambda P, X: X)
     bad = W0.copy(); bad[3, 4] = np.nan; bad[4, 3] = np.nan
     with pytest.raises(ValueError):
         qf.isomp(bad, dt, 2)
+
+
+@pytest.mark.parametrize("kind", ["numpy", "torch"])
+@pytest.mark.parametrize("case", ["callback", "forcing", "forcing_time", "strang", "ham_scaled", "ham_time", "all"])
+def test_isomp_hooks(qf, case, kind):
+    """The callers' hooks of the loop (callback, forcing, strang_splitting, custom / time-dependent Hamiltonians) run in
+    the host-stepped mode through the qf_step_* entry points.  Golden: the reference's own output
+    (tests/golden/isomp_hooks_N32.npz, oracle/gen_golden.py part H): <= 1e-12 relative Frobenius after 30 steps,
+    identical per-step iteration counts, callback arguments equal to 1e-11."""
+    import torch
+    from oracle import hooks
+    g = golden("isomp_hooks_N32.npz")
+    kw = hooks.case_kwargs(case, qf.solve_poisson)
+    dt, steps = float(g["dt"]), int(g["steps"])
+    W0 = g["W0"].copy()
+    W = W0 if kind == "numpy" else torch.from_numpy(W0).to("cuda:0")
+    cb, per_step, calls = [], [], [0]
+    ham = kw.pop("hamiltonian", None)
+    if ham is not None:           # count Hamiltonian evaluations per step, like the golden generator
+        if "time" in ham.__code__.co_varnames:
+            def counted(X, time=0.0, _h=ham):
+                calls[0] += 1
+                return _h(X, time=time)
+        else:
+            def counted(X, _h=ham):
+                calls[0] += 1
+                return _h(X)
+        kw["hamiltonian"] = counted
+
+    def callback(Wc, dWc):
+        per_step.append(calls[0])
+        calls[0] = 0
+        nW = float(np.linalg.norm(Wc)) if kind == "numpy" else float(torch.linalg.norm(Wc))
+        nd = float(np.linalg.norm(dWc)) if kind == "numpy" else float(torch.linalg.norm(dWc))
+        cb.append((nW, nd))
+        assert type(Wc) is type(W) and type(dWc) is type(W)
+
+    stats = {'iterations': 0.0}
+    out = qf.isomp(W, dt, steps=steps, stats=stats, callback=callback, **kw)
+    assert out is W
+    Wf = W if kind == "numpy" else W.cpu().numpy()
+    assert relfro(Wf, g[f"{case}_Wfinal"]) < 1e-12
+    assert stats['iterations'] == float(g[f"{case}_mean_iterations"])
+    assert stats['tol_auto'] == pytest.approx(float(g[f"{case}_tol_auto"]), rel=1e-14)
+    np.testing.assert_allclose(np.array(cb), g[f"{case}_cb_norms"], rtol=1e-11)
+    if ham is not None:
+        its = np.array(per_step)
+        if "time" in kw:
+            its[0] -= 1               # the autonomy probe (isospectral.py:419-421)
+        assert list(its) == list(g[f"{case}_iterations"])
+    assert np.abs(Wf + Wf.conj().T).max() < 1e-15 * np.abs(Wf).max() * 32
+
+
+def test_isomp_hooks_errors_and_equivalence(qf):
+    """compsum + forcing raises like the reference (isospectral.py:588-589); a callback-only run equals the fused run."""
+    from oracle import hooks
+    N = 48
+    W0 = oracle.random_skewherm(N, 7)
+    dt = 0.25 * qf.hbar(N)
+    with pytest.raises(NotImplementedError):
+        qf.isomp(W0.copy(), dt, 2, forcing=hooks.forcing_linear, compsum=True)
+    seen = []
+    Wa = qf.isomp(W0.copy(), dt, 12, callback=lambda W, dW: seen.append(np.abs(dW + dW.conj().T).max()), compsum=True)
+    Wb = qf.isomp(W0.copy(), dt, 12, compsum=True)
+    assert len(seen) == 12 and max(seen) == 0.0          # the increment is exactly skew-Hermitian (isospectral.py:66-81)
+    assert np.array_equal(Wa, Wb)                        # same kernels, same order: bit-identical
+    with pytest.raises(ValueError):                      # hook returns the wrong shape
+        qf.isomp(W0.copy(), dt, 1, forcing=lambda P, W: W[:4, :4])
 
 
 def test_isomp_ensemble_matches_independent_runs(qf):

@@ -39,3 +39,28 @@ def test_solve_restart_equivalence(cuda_device):
     Wb = W0.copy()
     qf.solve(Wb, stepsize=0.1, steps=100, steps_out=10, progress_bar=False)
     assert np.array_equal(Wa, Wb)
+
+
+def test_solve_passes_hooks_with_the_numpy_convention(cuda_device):
+    """solve() forwards forcing / integrator_callback / time to the integrator (simulation.py:726-733, 788): the hooks
+    receive numpy arrays when W is numpy, and `time` advances across output chunks for a time-dependent forcing."""
+    import quflow_b200 as qf
+    from oracle import hooks
+    N = 40
+    W0 = oracle.random_skewherm(N, 11)
+    dt = 0.2 * oracle.hbar(N)
+    seen = []
+
+    def icb(W, dW):
+        assert isinstance(W, np.ndarray) and isinstance(dW, np.ndarray)
+        seen.append(float(np.linalg.norm(dW)))
+
+    W = W0.copy()
+    qf.solve(W, dt=dt, steps=12, steps_out=5, progress_bar=False, forcing=hooks.forcing_time, integrator_callback=icb, time=0.3)
+    Wref, t, ref_seen = W0.copy(), 0.3, []
+    for n in (5, 5, 2):
+        Wref = oracle.isomp(Wref, dt, n, forcing=hooks.forcing_time, time=t,
+                            callback=lambda W, dW: ref_seen.append(float(np.linalg.norm(dW))))
+        t += n * dt
+    assert relfro(W, Wref) < 1e-12
+    np.testing.assert_allclose(seen, ref_seen, rtol=1e-11)

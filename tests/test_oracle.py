@@ -157,6 +157,25 @@ def test_isomp_smooth_N512_known_answers():
     assert np.linalg.norm(W) == pytest.approx(float(g["normF"]), rel=1e-13)
 
 
+@pytest.mark.parametrize("case", ["callback", "forcing", "forcing_time", "strang", "ham_scaled", "ham_time", "all"])
+def test_isomp_hooks(case):
+    """callback / forcing / strang_splitting / custom and time-dependent Hamiltonians against the reference's own
+    output (oracle/gen_golden.py part H)."""
+    from oracle import hooks
+    g = golden("isomp_hooks_N32.npz")
+    kw = hooks.case_kwargs(case, oracle.solve_poisson)
+    rec, stats, cb = {}, {'iterations': 0.0}, []
+    W = oracle.isomp(g["W0"].copy(), float(g["dt"]), int(g["steps"]), stats=stats, record=rec,
+                     callback=lambda W, dW: cb.append((np.linalg.norm(W), np.linalg.norm(dW))), **kw)
+    assert rec['iterations'] == list(g[f"{case}_iterations"])
+    assert stats['tol_auto'] == pytest.approx(float(g[f"{case}_tol_auto"]), rel=1e-14)
+    assert relfro(W, g[f"{case}_Wfinal"]) < 1e-12
+    np.testing.assert_allclose(np.array(cb), g[f"{case}_cb_norms"], rtol=1e-11)
+    if case in ("forcing", "forcing_time"):
+        with pytest.raises(NotImplementedError):      # isospectral.py:588-589
+            oracle.isomp(g["W0"].copy(), float(g["dt"]), 1, compsum=True, **kw)
+
+
 def test_asserts_and_stats_semantics():
     W = oracle.random_skewherm(8, 3)
     with pytest.raises(AssertionError):
