@@ -299,9 +299,9 @@ def gpu_arm(args):
         "share_of_iteration": (ph["gemm1_ms"] + ph["gemm2_ms"]) / iter_ms,
     }
     roofline_poisson = {
-        "bound": "hbm", "kernel": "W~=W+dW, P~=eps*Laplace^-1 W~ (32 N^2 algorithmic bytes)", "achieved": pois_gbs,
+        "bound": "hbm", "kernel": "k_poisson_band: P~ = eps*Laplace^-1 W~ (32 N^2 algorithmic bytes: read W~, write P~)", "achieved": pois_gbs,
         "peak": hbm, "unit": "GB/s", "frac": pois_gbs / hbm,
-        "traffic": ncu_traffic("k_poisson_scan") if N == 2048 else None, "launch_ms": ph["poisson_ms"],
+        "traffic": ncu_traffic("k_poisson_band") if N == 2048 else None, "launch_ms": ph["poisson_ms"],
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "B200_PROFILING.md fallback 6.65 TB/s (of fallback)",
     }
 
