@@ -179,6 +179,11 @@ int qf_comm_init(qf_handle_t h, const void *unique_id, int rank, int nranks);
 #define QF_P2P_BLOB_BYTES 256
 int qf_comm_p2p_export(qf_handle_t h, void *blob_out /* QF_P2P_BLOB_BYTES */);
 int qf_comm_p2p_import(qf_handle_t h, const void *blobs /* nranks * QF_P2P_BLOB_BYTES */, int rank, int nranks);
+/* After the import the default data path is the FUSED one: the GEMM kernel stores every finished tile of its row
+ * blocks into all peers' copies of the output as well (plain stores through the NVLink peer mappings), A and S are
+ * double-buffered by iteration parity, and one flag barrier per fixed-point iteration replaces the gathers.
+ * qf_comm_set_push(h, 0) selects the separate pull kernels instead (also: QF_COMM=pull in the environment). */
+int qf_comm_set_push(qf_handle_t h, int enable);
 /* Test hook: run the row-sharded data path for `nranks` ranks on ONE GPU (all ranks' tiles, no communication). */
 int qf_set_emulated_ranks(qf_handle_t h, int nranks);
 

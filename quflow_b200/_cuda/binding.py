@@ -84,6 +84,7 @@ SYMBOLS = {
     "qf_set_emulated_ranks": (_i, [_vp, _i]),
     "qf_comm_p2p_export": (_i, [_vp, _vp]),
     "qf_comm_p2p_import": (_i, [_vp, _vp, _i, _i]),
+    "qf_comm_set_push": (_i, [_vp, _i]),
 }
 
 
@@ -318,6 +319,9 @@ class Handle:
         raw = b"".join(blobs)
         assert len(raw) == nranks * QF_P2P_BLOB_BYTES
         _check(self._lib.qf_comm_p2p_import(self._h, ctypes.create_string_buffer(raw, len(raw)), int(rank), int(nranks)))
+
+    def comm_set_push(self, enable: bool):
+        _check(self._lib.qf_comm_set_push(self._h, 1 if enable else 0))
 
     def comm_init(self, unique_id: bytes, rank: int, nranks: int):
         buf = ctypes.create_string_buffer(unique_id, QF_UNIQUE_ID_BYTES)

@@ -92,7 +92,7 @@ template <bool FORCING>
 __global__ void __launch_bounds__(256)
 k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *__restrict__ dWg, double *__restrict__ rowpart,
        int N, int nslots, const QfCtrl *__restrict__ ctrl, int hb, int G, const double2 *__restrict__ Wg, double2 *__restrict__ Whg,
-       const double2 *__restrict__ Fg, double fscale)
+       const double2 *__restrict__ Fg, double fscale, const double2 *__restrict__ Ag1, const double2 *__restrict__ Sg1)
 {
     const int b = blockIdx.z;
     if (!ctrl[b].active) return;
@@ -102,8 +102,9 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
     __shared__ double2 D[TS][TS + 1];
     __shared__ double R[TS][TS + 1];
     const size_t off = (size_t)b * N * N;
-    const double2 *A = Ag + off;
-    const double2 *S = Sg + off;
+    const bool odd = Ag1 && (ctrl[b].gseq & 1ull);     // multi-GPU push mode: A and S alternate between two buffers
+    const double2 *A = (odd ? Ag1 : Ag) + off;
+    const double2 *S = (odd ? Sg1 : Sg) + off;
     double2 *dW = dWg + off;
     const double2 *W = Wg + off;
     double2 *Wh = Whg + off;
@@ -243,7 +244,7 @@ template <bool COMPSUM, bool FORCING>
 __global__ void __launch_bounds__(256)
 k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__restrict__ Kg, int N, QfCtrl *ctrl,
          int32_t *iters, int steps_cap, int hb, int G, const double2 *__restrict__ dWg, double2 *__restrict__ Whg, int reinit,
-         const double2 *__restrict__ Fg, double fscale)
+         const double2 *__restrict__ Fg, double fscale, const double2 *__restrict__ Ag1)
 {
     const int b = blockIdx.z;
     QfCtrl &c = ctrl[b];
@@ -256,7 +257,8 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
     if (bi > bj) return;
     __shared__ double2 T[TS][TS + 1];
     const size_t off = (size_t)b * N * N;
-    const double2 *A = Ag + off;
+    const bool odd = Ag1 && ((c.gseq - 1ull) & 1ull);   // the buffer of the last executed iteration (push mode)
+    const double2 *A = (odd ? Ag1 : Ag) + off;
     double2 *W = Wg + off;
     double2 *K = COMPSUM ? Kg + off : nullptr;
     const double2 *dW = dWg + off;
@@ -405,16 +407,25 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
     // W~ = W + dW was written by the previous k_post / k_update (or copied at call start): solve straight from it
     QF_CHECK(qf_launch_poisson(h, h->Wh, nullptr, h->Wh, h->P, eps, true, st));
     if (ev) QF_CUDA(cudaEventRecord(ev[1], st));
-    QF_CHECK(qf_launch_zgemm(h, h->P, h->Wh, h->A, false, true, my, G, false, st));        // rows of A = P~ W~
-    // (An overlapped A gather on a forked stream was tried: no gain, and two spin-waiting kernels sharing SMs can deadlock.)
-    if (real_comm) QF_CHECK(h->comm_mode == 2 ? qf_comm_p2p_allgather(h, 0, true, st) : qf_comm_allgather_rows(h, h->A, st));
+    const bool push = real_comm && h->comm_mode == 3;
+    QfGemmPush pa, ps;
+    if (push) {
+        QF_CHECK(qf_comm_push_args(h, 0, &pa));
+        QF_CHECK(qf_comm_push_args(h, 1, &ps));
+    }
+    QF_CHECK(qf_launch_zgemm(h, h->P, h->Wh, h->A, false, true, my, G, false, st, push ? &pa : nullptr));   // rows of A = P~ W~
+    // (Running the A gather on a forked branch next to the second GEMM was measured twice: no gain — the cooperative
+    // GEMM launch waits for the gather's CTAs — so the gathers stay in stream order.)
+    if (real_comm && !push) QF_CHECK(h->comm_mode == 2 ? qf_comm_p2p_allgather(h, 0, true, st) : qf_comm_allgather_rows(h, h->A, st));
     if (ev) QF_CUDA(cudaEventRecord(ev[2], st));
-    QF_CHECK(qf_launch_zgemm(h, h->A, h->P, h->S, true, true, my, G, true, st));          // rows of S = A P~ (A rows are local)
-    if (real_comm) QF_CHECK(h->comm_mode == 2 ? qf_comm_p2p_allgather(h, 1, true, st) : qf_comm_allgather_rows(h, h->S, st));
+    QF_CHECK(qf_launch_zgemm(h, h->A, h->P, h->S, true, true, my, G, true, st, push ? &ps : nullptr));      // rows of S = A P~ (A rows are local)
+    if (real_comm && !push) QF_CHECK(h->comm_mode == 2 ? qf_comm_p2p_allgather(h, 1, true, st) : qf_comm_allgather_rows(h, h->S, st));
+    if (push) QF_CHECK(qf_comm_push_barrier(h, true, st));   // the GEMM epilogues pushed the tiles; wait until everybody's have landed
     if (ev) QF_CUDA(cudaEventRecord(ev[3], st));
     const int nb = (N + TS - 1) / TS;
     dim3 g(nb, nb, h->batch);
-    k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, G, W, h->Wh, nullptr, 0.0);
+    k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, G, W, h->Wh, nullptr, 0.0,
+                                     push ? h->A2 : nullptr, push ? h->S2 : nullptr);
     k_control<<<dim3((N + 7) / 8, h->batch), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit);
     h->launches += 2;
     if (ev) QF_CUDA(cudaEventRecord(ev[4], st));
@@ -428,10 +439,11 @@ int qf_enqueue_update(qf_handle_s *h, double2 *W, bool compsum, bool reinit, cud
     const int nb = (N + TS - 1) / TS;
     const int hb = qf_block_rows(N, h->nranks);
     dim3 g(nb, nb, h->batch);
+    const double2 *A1 = (h->nranks > 1 && h->comm_mode == 3) ? h->A2 : nullptr;
     if (compsum)
-        k_update<true, false><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks, h->dW, h->Wh, reinit ? 1 : 0, nullptr, 0.0);
+        k_update<true, false><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks, h->dW, h->Wh, reinit ? 1 : 0, nullptr, 0.0, A1);
     else
-        k_update<false, false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks, h->dW, h->Wh, reinit ? 1 : 0, nullptr, 0.0);
+        k_update<false, false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks, h->dW, h->Wh, reinit ? 1 : 0, nullptr, 0.0, A1);
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;
@@ -568,7 +580,8 @@ static int build_step_graph(qf_handle_s *h, double2 *W, double eps, int maxit, i
     int reinit_i = reinit ? 1 : 0;
     const double2 *Fnull = nullptr;
     double fzero = 0.0;
-    QF_G(add_kernel_node(&n_update, g->graph, &n_while, 1, upd, gu, dim3(256), Ap, W, Kp, Nv, ctrl, iters, steps_cap, hb, G, dWp, Whp, reinit_i, Fnull, fzero));
+    const double2 *A1p = (h->nranks > 1 && h->comm_mode == 3) ? h->A2 : nullptr;
+    QF_G(add_kernel_node(&n_update, g->graph, &n_while, 1, upd, gu, dim3(256), Ap, W, Kp, Nv, ctrl, iters, steps_cap, hb, G, dWp, Whp, reinit_i, Fnull, fzero, A1p));
     QF_G(cudaGraphInstantiate(&g->exec, g->graph, 0));
 #undef QF_G
     h->step_graph = g;
@@ -774,9 +787,10 @@ extern "C" int qf_step_close_iteration(qf_handle_t h, const void *W_dev, const v
     dim3 g(nb, nb, 1);
     if (F_dev)
         k_post<true><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, N, 1, (const double2 *)W_dev, h->Wh,
-                                        (const double2 *)F_dev, fscale);
+                                        (const double2 *)F_dev, fscale, nullptr, nullptr);
     else
-        k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, N, 1, (const double2 *)W_dev, h->Wh, nullptr, 0.0);
+        k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, N, 1, (const double2 *)W_dev, h->Wh, nullptr, 0.0,
+                                         nullptr, nullptr);
     k_control<<<dim3((N + 7) / 8, 1), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit);
     h->launches += 2;
     QF_CUDA(cudaGetLastError());
@@ -819,11 +833,11 @@ extern "C" int qf_step_update(qf_handle_t h, void *W_dev, const void *F_dev, dou
     const int reinit = (h->step_flags & QF_FLAG_REINITIALIZE) ? 1 : 0;
     double2 *W = (double2 *)W_dev;
     if (compsum)
-        k_update<true, false><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, nullptr, 0.0);
+        k_update<true, false><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, nullptr, 0.0, nullptr);
     else if (F_dev)
-        k_update<false, true><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, (const double2 *)F_dev, fscale);
+        k_update<false, true><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, (const double2 *)F_dev, fscale, nullptr);
     else
-        k_update<false, false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, nullptr, 0.0);
+        k_update<false, false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, nullptr, 0.0, nullptr);
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;

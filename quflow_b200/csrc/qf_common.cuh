@@ -81,6 +81,7 @@ struct qf_handle_s {
     int p_nunits = 0;               // CTAs in the launch
     // work matrices, batch * N * N complex128 each
     double2 *dW = nullptr, *Wh = nullptr, *P = nullptr, *A = nullptr, *S = nullptr, *scratch = nullptr;
+    double2 *A2 = nullptr, *S2 = nullptr;   // odd-iteration copies of A and S (multi-GPU push mode only)
     double2 *kahan_c = nullptr;   // compensation term (compsum), lazily allocated
     double2 *io = nullptr;        // staging for the *_host entry points, lazily allocated
     double2 *io2 = nullptr;
@@ -96,7 +97,8 @@ struct qf_handle_s {
     // multi-GPU
     void *nccl_comm = nullptr;
     void *p2p = nullptr;          // QfP2P (comm.cu)
-    int comm_mode = 0;            // 0: none / emulated, 1: NCCL all-gather (eager only), 2: peer-memory pull kernel
+    int comm_mode = 0;            // 0: none / emulated, 1: NCCL all-gather (eager only), 2: peer-memory pull kernel,
+                                  // 3: GEMM epilogue pushes its tiles to the peers (fused all-gather), double-buffered A/S
     int rank = 0, nranks = 1;     // nranks > 1 with nccl_comm == nullptr: all ranks emulated on this GPU (tests)
     QfGemmPlan *gemm = nullptr;
     // CUDA-graph execution of a step (isomp.cu)
@@ -127,8 +129,16 @@ void qf_gemm_destroy(qf_handle_s *h);
 // C = A * B.  upper_only: compute only the 64-wide column blocks that intersect the upper triangle
 // (used for S = A P~ which is skew-Hermitian).  rank/nranks: row-block sharding (rank < 0: all blocks).
 // a_permuted: the A operand is itself stored in the rank-permuted row layout (an earlier GEMM's output).
+// push (multi-GPU "push" mode, comm.cu): the output is double-buffered by the parity of the iteration counter
+// (C / push->C1; the A operand likewise: A / push->A1) and every finished tile is also stored into the peers' copies.
+struct QfGemmPush {
+    double2 *C1;                 // output buffer of odd iterations
+    const double2 *A1;           // A operand of odd iterations (nullptr: not double-buffered)
+    double2 *const *peers;       // device table [2][QF_MAX_RANKS] of the peers' output buffers, parity-major
+    int nranks, rank;
+};
 int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 *C, bool upper_only, bool gated,
-                    int rank, int nranks, bool a_permuted, cudaStream_t st);
+                    int rank, int nranks, bool a_permuted, cudaStream_t st, const QfGemmPush *push = nullptr);
 
 // ---------------------------------------------------------------------------------------
 // Row-block sharding across G ranks (multi-GPU).
@@ -148,6 +158,8 @@ __host__ __device__ __forceinline__ int qf_prow(int i, int hb, int G)
 }
 int qf_comm_allgather_rows(qf_handle_s *h, double2 *M, cudaStream_t st);   // comm.cu
 int qf_comm_p2p_allgather(qf_handle_s *h, int kind, bool gated, cudaStream_t st);   // comm.cu
+int qf_comm_push_barrier(qf_handle_s *h, bool gated, cudaStream_t st);              // comm.cu: all peers' pushed tiles have landed
+int qf_comm_push_args(qf_handle_s *h, int kind, QfGemmPush *out);                    // comm.cu: kind 0 = A, 1 = S
 void qf_p2p_destroy(qf_handle_s *h);
 int qf_gemm_prepare(qf_handle_s *h, int rank, int nranks);                  // zgemm.cu: build tile lists (allocates)
 void qf_graph_destroy(qf_handle_s *h);                                      // isomp.cu

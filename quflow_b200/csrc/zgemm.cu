@@ -496,10 +496,17 @@ __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 
 constexpr int WS_THREADS = GEMM_THREADS + 32;
 
 __global__ void __launch_bounds__(WS_THREADS, 1)
-k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, int ntiles, double2 *__restrict__ ws,
-             int *__restrict__ flags, const QfCtrl *__restrict__ ctrl, int gated, const __grid_constant__ CUtensorMap tmA,
-             const __grid_constant__ CUtensorMap tmB)
+k_zgemm3m_ws(double2 *__restrict__ C0, double2 *__restrict__ C1, int N, const SkTile *__restrict__ tiles, int ntiles,
+             double2 *__restrict__ ws, int *__restrict__ flags, const QfCtrl *__restrict__ ctrl, int gated, int dbuf,
+             double2 *const *__restrict__ peers, int nranks, int my_rank, const __grid_constant__ CUtensorMap tmA0,
+             const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB)
 {
+    // Double-buffered output (multi-GPU push mode): the fixed-point iteration number selects the buffer pair, so a
+    // peer may still read the previous iteration's matrices while this one is being produced.
+    const int par = dbuf ? (int)(ctrl[0].gseq & 1ull) : 0;
+    double2 *__restrict__ Cg = par ? C1 : C0;
+    const CUtensorMap *tmAp = par ? &tmA1 : &tmA0;
+    double2 *const *peers_par = peers ? peers + par * QF_MAX_RANKS : nullptr;
     constexpr bool M3 = true;
     constexpr int STAGES = Cfg<M3>::STAGES, NJ = Cfg<M3>::NJ, NACC = Cfg<M3>::NACC, WN = Cfg<M3>::WN;
     constexpr int BM = Cfg<M3>::BM, BN = Cfg<M3>::BN, BK = Cfg<M3>::BK;
@@ -544,7 +551,7 @@ k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, 
                     mbar_arrive_expect_tx(bar, STAGE_BYTES);
 #pragma unroll
                     for (int hh = 0; hh < BK / 8; ++hh)
-                        tma_load_3d(sb + hh * (BM * 128), &tmA, 2 * (k0 + 8 * hh), ti.op_row0, ti.member, bar);
+                        tma_load_3d(sb + hh * (BM * 128), tmAp, 2 * (k0 + 8 * hh), ti.op_row0, ti.member, bar);
 #pragma unroll
                     for (int c = 0; c < BN / 8; ++c)
                         tma_load_3d(sb + A_STAGE_BYTES + c * (BK * 128), &tmB, 2 * (ti.col0 + 8 * c), k0, ti.member, bar);
@@ -620,8 +627,17 @@ k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, 
                 }
             }
             gemm_store_tile<M3>(acc, Cg + moff, N, ti.c_row0, ti.c_row0 + (ti.row_end - ti.a_row0), ti.col0, wm, wn, g, t);
+            // fused all-gather: the finished tile also goes to the same place in every peer's copy of C, as plain
+            // stores through NVLink peer mappings; they drain while the next tile is being multiplied
+            if (peers_par) {
+                for (int pr = 0; pr < nranks; ++pr) {
+                    if (pr == my_rank) continue;
+                    gemm_store_tile<M3>(acc, peers_par[pr] + moff, N, ti.c_row0, ti.c_row0 + (ti.row_end - ti.a_row0), ti.col0, wm, wn, g, t);
+                }
+            }
         }
     }
+    if (peers_par) __threadfence_system();   // remote tiles are performed before the kernel (and the flag that follows it) completes
 }
 
 }   // namespace
@@ -822,7 +838,7 @@ static cudaError_t launch_sk(qf_handle_s *h, bool tma, int G, const double2 *A, 
 
 // rank/nranks select the row blocks (see qf_prow); rank < 0 computes every rank's blocks (emulation on one GPU).
 int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 *C, bool upper_only, bool gated,
-                    int rank, int nranks, bool a_permuted, cudaStream_t st)
+                    int rank, int nranks, bool a_permuted, cudaStream_t st, const QfGemmPush *push)
 {
     const int N = h->N;
     QfGemmPlan *p = h->gemm;
@@ -840,9 +856,16 @@ int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 
     CUtensorMap tmA, tmB;
     memset(&tmA, 0, sizeof(tmA));
     memset(&tmB, 0, sizeof(tmB));
+    CUtensorMap tmA1;
+    memset(&tmA1, 0, sizeof(tmA1));
     if (tma) {
         QF_CHECK(make_tmap(h, A, p->BM(), &tmA));
         QF_CHECK(make_tmap(h, B, BK, &tmB));   // B boxes: BK rows x 8 complex
+        QF_CHECK(make_tmap(h, (push && push->A1) ? push->A1 : A, p->BM(), &tmA1));
+    }
+    if (push && !(p->m3 && tma && p->warp_spec)) {
+        qf_set_error("the fused GEMM + peer push needs the warp-specialised 3M TMA kernel (QF_GEMM_3M/QF_GEMM_WS/QF_GEMM_LOAD defaults)");
+        return QF_ERR_UNSUPPORTED;
     }
     if (p->m3 && tma && p->warp_spec) {
         cudaLaunchConfig_t cfg = {};
@@ -855,8 +878,10 @@ int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 
         attr[0].val.cooperative = 1;
         cfg.attrs = attr;
         cfg.numAttrs = p->cooperative ? 1 : 0;
-        QF_CUDA(cudaLaunchKernelEx(&cfg, k_zgemm3m_ws, C, N, tiles, ntiles, p->ws, p->flags, (const QfCtrl *)h->ctrl,
-                                   gated ? 1 : 0, tmA, tmB));
+        double2 *C1 = push ? push->C1 : C;
+        double2 *const *peers = push ? push->peers : nullptr;
+        QF_CUDA(cudaLaunchKernelEx(&cfg, k_zgemm3m_ws, C, C1, N, tiles, ntiles, p->ws, p->flags, (const QfCtrl *)h->ctrl,
+                                   gated ? 1 : 0, push ? 1 : 0, peers, push ? push->nranks : 1, push ? push->rank : 0, tmA, tmA1, tmB));
     } else {
         QF_CUDA(p->m3 ? launch_sk<true>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st)
                       : launch_sk<false>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st));

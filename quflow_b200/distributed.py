@@ -52,10 +52,15 @@ def broadcast_unique_id(dist, make_id=None) -> bytes:
 def attach_row_sharding(handle, dist, mode=None):
     """Make ``handle`` (batch == 1) run its GEMMs row-sharded over the default process group.
 
-    mode "p2p" (default): peer-memory pull kernels over NVLink inside the step graph — torch.distributed (NCCL
-    backend) only all-gathers one 256-byte blob of CUDA IPC handles per rank.
+    mode "p2p" (default): "push" when every rank's first GEMM has at least two data-parallel waves of tiles,
+    else "pull" (decided in csrc/comm.cu).
+    mode "push": the GEMM kernel itself stores every finished tile into all peers'
+    copies of its output over NVLink peer mappings (fused GEMM + all-gather), A and S are double-buffered by iteration
+    parity and one flag barrier per fixed-point iteration is all that is left of the collective.  torch.distributed
+    only all-gathers one 256-byte blob of CUDA IPC handles per rank at set-up.
+    mode "pull": one pull kernel after each GEMM, inside the step graph.
     mode "nccl": one in-place ncclAllGather per GEMM, issued by the library on the compute stream (eager launches;
-    NCCL cannot run inside the conditional graph body).  Select with QF_COMM=nccl.
+    NCCL cannot run inside the conditional graph body).  Select with QF_COMM=push|pull|nccl.
     """
     import os
     world, rank = dist.get_world_size(), dist.get_rank()
@@ -69,7 +74,9 @@ def attach_row_sharding(handle, dist, mode=None):
     else:
         blobs = [None] * world
         dist.all_gather_object(blobs, handle.p2p_export())
-        handle.p2p_import(blobs, rank, world)
+        handle.p2p_import(blobs, rank, world)       # picks push or pull by the tile count per rank (csrc/comm.cu)
+        if mode in ("push", "pull"):
+            handle.comm_set_push(mode == "push")
         dist.barrier()              # every rank has mapped every peer before anybody starts signalling
     return handle
 
