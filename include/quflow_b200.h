@@ -57,6 +57,9 @@ typedef struct {
 /* Flags for qf_isomp */
 #define QF_FLAG_COMPSUM 1u       /* compensated (Kahan) update, isospectral.py:553-589 */
 #define QF_FLAG_REINITIALIZE 2u  /* zero the iterate dW at every step, isospectral.py:471-472 */
+#define QF_FLAG_MULTISTATE 4u    /* the `batch` members are ONE multi-state (k, N, N) run of the reference: members
+                                    1.. are advected by member 0's stream function (select_first, cpu.py:672-674),
+                                    tolerance and residual come from member 0 (isospectral.py:444-446, 528-531) */
 
 /* Library / device info. Returns the number of CUDA devices (>=0) or a negative qf_status. */
 int qf_device_count(void);

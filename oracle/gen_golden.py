@@ -245,8 +245,36 @@ def gen_hooks():
     save("isomp_hooks_N32.npz", **arrays)
 
 
+# ---------------------------------------------------------------------------
+# M. multi-state (k, N, N): members 1.. advected by member 0's stream function (cpu.py:672-674)
+# ---------------------------------------------------------------------------
+def gen_multistate():
+    print("M. multi-state isomp, k=3 members of R(32, seed), 30 steps")
+    N, steps = 32, 30
+    W0 = np.stack([random_skewherm(N, s) for s in (42, 43, 44)])
+    dt = 0.25 * hbar(N)
+    ham = CountingHamiltonian()
+    per_step, last = [], [0]
+
+    def callback(W, dW):
+        per_step.append(ham.calls - last[0])
+        last[0] = ham.calls
+
+    arrays = dict(W0=W0, dt=dt, steps=steps)
+    for tag, kw in (("plain", dict()), ("compsum", dict(compsum=True))):
+        del per_step[:]
+        ham.calls = last[0] = 0
+        stats = {'iterations': 0.0}
+        W = isomp_fixedpoint(W0.copy(), dt, steps=steps, hamiltonian=ham, stats=stats, callback=callback, **kw)
+        print(f"   {tag}: it/step={stats['iterations']:.3f}")
+        arrays.update({f"{tag}_Wfinal": W, f"{tag}_iterations": np.array(per_step, dtype=np.int32),
+                       f"{tag}_tol_auto": stats['tol_auto'], f"{tag}_mean_iterations": stats['iterations']})
+    save("isomp_multistate_N32.npz", **arrays)
+
+
 if __name__ == "__main__":
-    parts = dict(A=gen_reference_golden, B=gen_poisson, C=gen_isomp_random, S=gen_isomp_smooth, H=gen_hooks)
+    parts = dict(A=gen_reference_golden, B=gen_poisson, C=gen_isomp_random, S=gen_isomp_smooth, H=gen_hooks,
+                 M=gen_multistate)
     for key in (sys.argv[1:] or list(parts)):
         parts[key]()
     print("done")

@@ -173,8 +173,13 @@ def laplace(P: np.ndarray) -> np.ndarray:
 
 
 def conj_subtract_(a: np.ndarray, out: np.ndarray) -> None:
-    """out = a - a^H with exact skew-symmetry, isospectral.py:66-81 (2-D branch)."""
-    assert a.ndim == 2 and a.flags.c_contiguous and out.flags.c_contiguous
+    """out = a - a^H with exact skew-symmetry, isospectral.py:66-81 (2-D branch, and member by member for 3-D)."""
+    assert a.flags.c_contiguous and out.flags.c_contiguous
+    if a.ndim == 3:                                          # :75-81
+        for k in range(a.shape[0]):
+            _lib().qfo_conj_subtract(a.shape[-1], _ptr(a[k]), _ptr(out[k]))
+        return
+    assert a.ndim == 2
     _lib().qfo_conj_subtract(a.shape[-1], _ptr(a), _ptr(out))
 
 
@@ -193,7 +198,9 @@ def isomp_fixedpoint(W, dt, steps=100, hamiltonian=None, time=None, forcing=None
                      record=None):
     """Isospectral midpoint by fixed-point iteration, isospectral.py:338-613.
 
-    Restated for a 2-D state, including the callers' hooks of the loop: ``callback`` (:550-551),
+    Restated for a 2-D state and for the multi-state (k, N, N) mode (members 1.. are advected passively by member 0's
+    stream function: select_first, cpu.py:672-674; tolerance and residual from member 0, isospectral.py:444-446, 529-531),
+    including the callers' hooks of the loop: ``callback`` (:550-551),
     ``forcing`` (:403-414, :511-520, :594-596), ``strang_splitting`` (:466-467, :602-603) and custom or
     time-dependent Hamiltonians (:416-424, :488-491).
     ``record`` (oracle-only extra): dict that receives per-step ``iterations``
@@ -203,7 +210,7 @@ def isomp_fixedpoint(W, dt, steps=100, hamiltonian=None, time=None, forcing=None
     assert maxit >= minit, "maxit must be at minit."         # :401
     if hamiltonian is None:
         hamiltonian = solve_poisson
-    assert W.ndim == 2
+    assert W.ndim in (2, 3)
 
     if forcing is not None:                                  # :403-414
         autonomous_force = True
@@ -237,7 +244,7 @@ def isomp_fixedpoint(W, dt, steps=100, hamiltonian=None, time=None, forcing=None
         mach_eps = np.finfo(W.dtype).eps
         if not compsum:
             mach_eps = np.sqrt(mach_eps)
-        tol = (mach_eps * dt / hb) * np.linalg.norm(W, np.inf)
+        tol = (mach_eps * dt / hb) * np.linalg.norm(W[0] if W.ndim > 2 else W, np.inf)   # :444-448
         if verbatim:
             print("Tolerance set to {}.".format(tol))
         if stats:
@@ -287,7 +294,14 @@ def isomp_fixedpoint(W, dt, steps=100, hamiltonian=None, time=None, forcing=None
             if i + 1 >= minit:                               # :523-536
                 resnorm_old = resnorm
                 dW_old -= dW
-                resnorm = norm_inf(dW_old)
+                if dW_old.ndim > 2:
+                    # scipy.linalg.norm(., ord=inf, axis=(-1, -2)) (:528): row axis -1, column axis -2, i.e. the max
+                    # COLUMN sum of each member; member 0 decides when the Hamiltonian returns one matrix (:529-530)
+                    resnorm = float(np.abs(dW_old[0]).sum(axis=-2).max())
+                    if not np.isfinite(np.abs(dW_old).sum()):
+                        resnorm = np.nan
+                else:
+                    resnorm = norm_inf(dW_old)
                 if not np.isfinite(resnorm):                 # scipy's asarray_chkfinite
                     raise ValueError("array must not contain infs or NaNs")
                 if resnorm <= tol or resnorm >= resnorm_old:

@@ -23,6 +23,7 @@ QF_ERR_NCCL = -4
 QF_ERR_UNSUPPORTED = -5
 QF_FLAG_COMPSUM = 1
 QF_FLAG_REINITIALIZE = 2
+QF_FLAG_MULTISTATE = 4
 QF_UNIQUE_ID_BYTES = 128
 QF_P2P_BLOB_BYTES = 256
 QF_BUF_WHALF, QF_BUF_P, QF_BUF_SCRATCH = 0, 1, 2
@@ -217,13 +218,15 @@ class Handle:
         _check(self._lib.qf_zgemm(self._h, _dev_ptr(A), _dev_ptr(B), _dev_ptr(out), _stream_ptr()))
         return out
 
-    def isomp(self, W, dt, steps, tol=-1.0, maxit=10, minit=1, compsum=False, reinitialize=False, want_iters=False):
+    def isomp(self, W, dt, steps, tol=-1.0, maxit=10, minit=1, compsum=False, reinitialize=False, want_iters=False,
+              multistate=False):
         """Advance W in place.  Returns (list of per-member stats dicts, iters array or None).
 
         Raises ValueError on a non-finite residual (the reference raises it from scipy.linalg.norm).
         """
         self._shape_ok(W)
-        flags = (QF_FLAG_COMPSUM if compsum else 0) | (QF_FLAG_REINITIALIZE if reinitialize else 0)
+        flags = ((QF_FLAG_COMPSUM if compsum else 0) | (QF_FLAG_REINITIALIZE if reinitialize else 0)
+                 | (QF_FLAG_MULTISTATE if multistate else 0))
         stats = (qf_stats * self.batch)()
         iters = np.zeros((self.batch, max(steps, 1)), dtype=np.int32) if want_iters else None
         iters_p = iters.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)) if want_iters else None

@@ -36,10 +36,11 @@ __global__ void k_rowsum_abs(const double2 *__restrict__ W, int N, QfCtrl *ctrl)
     }
 }
 
-__global__ void k_call_begin(QfCtrl *ctrl, double tol, double tol_factor)
+__global__ void k_call_begin(QfCtrl *ctrl, double tol, double tol_factor, int multistate)
 {
     QfCtrl &c = ctrl[blockIdx.x];
-    c.tol = (tol < 0.0) ? tol_factor * c.norm0 : tol;
+    const double n0 = multistate ? ctrl[0].norm0 : c.norm0;      // multi-state: ||W[0]||_inf (isospectral.py:444-446)
+    c.tol = (tol < 0.0) ? tol_factor * n0 : tol;
     c.resnorm = INFINITY;
     c.resnorm_old = INFINITY;
     c.total_it = 0;
@@ -177,7 +178,7 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
 // Row sums of the residual (one warp per row, slots contiguous), max over rows through an order-independent
 // atomicMax, and the stopping rule evaluated by the last block to finish (ticket counter).
 __global__ void __launch_bounds__(256)
-k_control(const double *__restrict__ rowpart, int N, int nslots, QfCtrl *ctrl, int maxit, int minit)
+k_control(const double *__restrict__ rowpart, int N, int nslots, QfCtrl *ctrl, int maxit, int minit, int nfollow)
 {
     const int b = blockIdx.y;
     QfCtrl &c = ctrl[b];
@@ -223,8 +224,30 @@ k_control(const double *__restrict__ rowpart, int N, int nslots, QfCtrl *ctrl, i
         active = 0;
         c.n_maxit += 1;
     }
+    // multi-state run: members 1..nfollow take every decision from member 0 (isospectral.py:529-531)
+    for (int f = 1; f <= nfollow; ++f) {
+        QfCtrl &d = ctrl[f];
+        d.it = c.it;
+        d.total_it = c.total_it;
+        d.gseq = c.gseq;
+        d.resnorm = c.resnorm;
+        d.resnorm_old = c.resnorm_old;
+        d.n_maxit = c.n_maxit;
+        d.nonfinite = c.nonfinite;
+    }
     __threadfence();
     c.active = active;
+    for (int f = 1; f <= nfollow; ++f) ctrl[f].active = active;
+}
+
+// multi-state run: P~ of member 0 is everybody's stream function (select_first, cpu.py:672-674)
+__global__ void k_bcast_p(double2 *P, size_t n2, int batch, const QfCtrl *__restrict__ ctrl)
+{
+    if (!ctrl[0].active) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        const double2 v = P[i];
+        for (int b = 1; b < batch; ++b) P[(size_t)b * n2 + i] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------- update
@@ -405,7 +428,13 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
     const int hb = qf_block_rows(N, G);
     if (ev) QF_CUDA(cudaEventRecord(ev[0], st));
     // W~ = W + dW was written by the previous k_post / k_update (or copied at call start): solve straight from it
-    QF_CHECK(qf_launch_poisson(h, h->Wh, nullptr, h->Wh, h->P, eps, true, st));
+    const bool multistate = h->multistate && h->batch > 1;
+    QF_CHECK(qf_launch_poisson(h, h->Wh, nullptr, h->Wh, h->P, eps, true, st, multistate ? 1 : h->batch));
+    if (multistate) {
+        const size_t n2 = h->mat_elems;
+        k_bcast_p<<<(unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)h->sm_count * 8), 256, 0, st>>>(h->P, n2, h->batch, h->ctrl);
+        h->launches++;
+    }
     if (ev) QF_CUDA(cudaEventRecord(ev[1], st));
     const bool push = real_comm && h->comm_mode == 3;
     QfGemmPush pa, ps;
@@ -426,7 +455,8 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
     dim3 g(nb, nb, h->batch);
     k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, G, W, h->Wh, nullptr, 0.0,
                                      push ? h->A2 : nullptr, push ? h->S2 : nullptr);
-    k_control<<<dim3((N + 7) / 8, h->batch), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit);
+    k_control<<<dim3((N + 7) / 8, multistate ? 1 : h->batch), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit,
+                                                                        multistate ? h->batch - 1 : 0);
     h->launches += 2;
     if (ev) QF_CUDA(cudaEventRecord(ev[4], st));
     QF_CUDA(cudaGetLastError());
@@ -603,6 +633,12 @@ extern "C" int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double
     double2 *W = (double2 *)W_dev;
     const bool compsum = (flags & QF_FLAG_COMPSUM) != 0;
     const bool reinit = (flags & QF_FLAG_REINITIALIZE) != 0;
+    const bool multistate = (flags & QF_FLAG_MULTISTATE) != 0 && B > 1;
+    if (multistate && h->nranks > 1) { qf_set_error("multi-state runs are single-GPU"); return QF_ERR_UNSUPPORTED; }
+    if ((int)multistate != h->multistate) {
+        h->multistate = multistate ? 1 : 0;
+        qf_graph_destroy(h);        // the step graph bakes the member coupling in
+    }
 
     if (steps > h->steps_cap) {
         if (h->iters_dev) QF_CUDA(cudaFree(h->iters_dev));
@@ -621,7 +657,7 @@ extern "C" int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double
     QF_CUDA(cudaMemcpyAsync(h->Wh, W, sizeof(double2) * n2 * B, cudaMemcpyDeviceToDevice, st));   // W~ = W + 0
     if (compsum) QF_CUDA(cudaMemsetAsync(h->kahan_c, 0, sizeof(double2) * n2 * B, st));   // :457
     QF_CHECK(qf_launch_norm_inf(h, W, st));
-    k_call_begin<<<B, 1, 0, st>>>(h->ctrl, tol, tol_factor);
+    k_call_begin<<<B, 1, 0, st>>>(h->ctrl, tol, tol_factor, multistate ? 1 : 0);
     h->launches++;
 
     const dim3 gz((unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)h->sm_count * 8), B);
@@ -713,7 +749,7 @@ extern "C" int qf_step_open(qf_handle_t h, const void *W_dev, double dt, double 
     QF_CUDA(cudaMemsetAsync(h->dW, 0, sizeof(double2) * n2, st));           // :430
     if (compsum) QF_CUDA(cudaMemsetAsync(h->kahan_c, 0, sizeof(double2) * n2, st));
     QF_CHECK(qf_launch_norm_inf(h, (const double2 *)W_dev, st));
-    k_call_begin<<<1, 1, 0, st>>>(h->ctrl, tol, mach_eps * dt / hb);        // :440-448
+    k_call_begin<<<1, 1, 0, st>>>(h->ctrl, tol, mach_eps * dt / hb, 0);     // :440-448
     h->launches++;
     QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl), cudaMemcpyDeviceToHost, st));
     QF_CUDA(cudaStreamSynchronize(st));
@@ -791,7 +827,7 @@ extern "C" int qf_step_close_iteration(qf_handle_t h, const void *W_dev, const v
     else
         k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, N, 1, (const double2 *)W_dev, h->Wh, nullptr, 0.0,
                                          nullptr, nullptr);
-    k_control<<<dim3((N + 7) / 8, 1), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit);
+    k_control<<<dim3((N + 7) / 8, 1), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit, 0);
     h->launches += 2;
     QF_CUDA(cudaGetLastError());
     QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl), cudaMemcpyDeviceToHost, st));
@@ -876,7 +912,7 @@ extern "C" int qf_profile_iteration(qf_handle_t h, const void *W_dev, double dt,
     QF_CUDA(cudaMemsetAsync(h->dW, 0, sizeof(double2) * n2 * B, st));
     QF_CUDA(cudaMemcpyAsync(h->Wh, h->io, sizeof(double2) * n2 * B, cudaMemcpyDeviceToDevice, st));
     QF_CHECK(qf_launch_norm_inf(h, h->io, st));
-    k_call_begin<<<B, 1, 0, st>>>(h->ctrl, 0.0, 0.0);   // tol = 0: never converges by tolerance
+    k_call_begin<<<B, 1, 0, st>>>(h->ctrl, 0.0, 0.0, 0);   // tol = 0: never converges by tolerance
     float acc[5] = {0, 0, 0, 0, 0};
     for (int r = -1; r < reps; ++r) {   // r = -1: warm-up
         k_step_begin<<<1, 1, 0, st>>>(h->ctrl, B, 0, 0);

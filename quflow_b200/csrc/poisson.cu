@@ -813,9 +813,10 @@ __global__ void k_laplace(const double2 *__restrict__ P, double2 *__restrict__ W
 // launchers
 // ---------------------------------------------------------------------------------------
 int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, double2 *Wh, double2 *P, double eps,
-                      bool gated, cudaStream_t st)
+                      bool gated, cudaStream_t st, int members)
 {
     const int N = h->N;
+    const int nmem = (members > 0 && members < h->batch) ? members : h->batch;
     const size_t n2 = h->mat_elems;
     const int g = gated ? 1 : 0;
     if (Wh != W) {
@@ -846,7 +847,7 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
             pf = env ? atoi(env) : 1;
         }
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)h->p_nunits, (unsigned)h->batch);
+        cfg.gridDim = dim3((unsigned)h->p_nunits, (unsigned)nmem);
         cfg.blockDim = dim3((unsigned)NT);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
@@ -872,10 +873,10 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
         h->launches++;
     } else {
         // large-N fallback: one thread per diagonal
-        k_trace<<<h->batch, 256, 0, st>>>(Wh, N, h->ctrl, h->trbuf, g);
-        dim3 gt((N + 63) / 64, h->batch);
+        k_trace<<<nmem, 256, 0, st>>>(Wh, N, h->ctrl, h->trbuf, g);
+        dim3 gt((N + 63) / 64, nmem);
         k_thomas<<<gt, 64, 0, st>>>(Wh, P, h->scratch, h->tab_w, h->tab_iu, h->tab_o, N, eps, h->ctrl, h->trbuf, g);
-        k_fix_trace<<<h->batch, 256, 0, st>>>(P, N, eps, h->ctrl, g);
+        k_fix_trace<<<nmem, 256, 0, st>>>(P, N, eps, h->ctrl, g);
         h->launches += 3;
     }
     QF_CUDA(cudaGetLastError());

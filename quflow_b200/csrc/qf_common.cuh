@@ -109,6 +109,7 @@ struct qf_handle_s {
     double step_eps = 0.0;
     unsigned step_flags = 0;
     int step_open = 0;
+    int multistate = 0;           // the members are one (k, N, N) run: member 0's stream function drives everybody
     int graph_warned = 0;
 };
 
@@ -119,7 +120,7 @@ struct qf_handle_s {
 int qf_build_tables(qf_handle_s *h);
 // Wh = W (+ dW);  P = eps * Delta^{-1} Wh.  If ctrl != null the launch is skipped on device when !ctrl->active.
 int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, double2 *Wh, double2 *P, double eps,
-                      bool gated, cudaStream_t st);
+                      bool gated, cudaStream_t st, int members = -1 /* solve only the first `members` (default: all) */);
 int qf_launch_laplace(qf_handle_s *h, const double2 *P, double2 *W, cudaStream_t st);
 int qf_launch_whalf(qf_handle_s *h, const double2 *W, const double2 *dW, double2 *Wh, cudaStream_t st);
 

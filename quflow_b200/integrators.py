@@ -175,7 +175,8 @@ def isomp_fixedpoint(W,
     """Time-stepping by the isospectral midpoint method with fixed-point iterations
     (reference: isospectral.py:338-613).
 
-    ``W``: skew-Hermitian (N, N) complex128; a numpy array is overwritten in place and returned, exactly like
+    ``W``: skew-Hermitian (N, N) complex128, or (k, N, N) for the reference's multi-state mode (members 1.. are
+    advected passively by member 0's stream function, cpu.py:672-674); a numpy array is overwritten in place and returned, exactly like
     the reference (host→device and back once per call); a torch CUDA tensor is advanced in place on the device.
     ``time`` is accepted (``qf.solve`` always passes it, simulation.py:727) — the default Hamiltonian is
     autonomous so it has no effect on it.  ``callback(W, dW)``, ``forcing(P, W[, time])``,
@@ -185,11 +186,12 @@ def isomp_fixedpoint(W,
     """
     assert minit >= 1, "minit must be at least 1."          # isospectral.py:400
     assert maxit >= minit, "maxit must be at minit."         # isospectral.py:401
-    if W.ndim != 2:
-        raise NotImplementedError("multi-state (k, N, N) input is not implemented; use quflow_b200.isomp_ensemble "
-                                  "for independent members")
-    if (forcing is not None or strang_splitting is not None or callback is not None
-            or not _is_default_hamiltonian(hamiltonian)):
+    hooks = (forcing is not None or strang_splitting is not None or callback is not None
+             or not _is_default_hamiltonian(hamiltonian))
+    if W.ndim != 2 and (W.ndim != 3 or hooks):
+        raise NotImplementedError("multi-state input must be (k, N, N) and runs with the default Hamiltonian and without "
+                                  "hooks; use quflow_b200.isomp_ensemble for independent members")
+    if hooks:
         return _isomp_host_stepped(W, dt, steps, hamiltonian, time, forcing, strang_splitting, stats, callback, tol,
                                    maxit, minit, verbatim, compsum, reinitialize)
     Wc = _prepare(W)
@@ -198,9 +200,12 @@ def isomp_fixedpoint(W,
     auto = (isinstance(tol, str) and tol == 'auto') or (not isinstance(tol, str) and tol < 0)   # :440
     if isinstance(tol, str) and not auto:
         raise ValueError("tol must be a float or 'auto'")
-    handle = get_handle(N, 1, Wc.device.index if _is_torch(Wc) else None)
+    # (k, N, N): ONE multi-state run — members 1.. are advected by member 0's stream function (select_first,
+    # cpu.py:672-674); tolerance, residual and statistics come from member 0 (isospectral.py:444-446, 528-531)
+    k = Wc.shape[0] if Wc.ndim == 3 else 1
+    handle = get_handle(N, k, Wc.device.index if _is_torch(Wc) else None)
     res, _ = handle.isomp(Wc, dt, steps, tol=-1.0 if auto else float(tol), maxit=maxit, minit=minit,
-                          compsum=bool(compsum), reinitialize=bool(reinitialize))
+                          compsum=bool(compsum), reinitialize=bool(reinitialize), multistate=Wc.ndim == 3)
     st = res[0]
     if not inplace:   # non-contiguous input: copy the result back into the caller's array
         if _is_torch(W):

@@ -84,8 +84,8 @@ def test_argument_validation_happens_before_any_device_work():
         qf.isomp(W, 0.1, 1, minit=0)
     with pytest.raises(AssertionError, match="maxit must be at minit"):
         qf.isomp(W, 0.1, 1, minit=5, maxit=2)
-    with pytest.raises(NotImplementedError):                       # multi-state input is not part of the path
-        qf.isomp(np.zeros((2, 8, 8), dtype=np.complex128), 0.1, 1)
+    with pytest.raises(NotImplementedError):                       # multi-state input with hooks is not part of the path
+        qf.isomp(np.zeros((2, 8, 8), dtype=np.complex128), 0.1, 1, callback=lambda W, dW: None)
     with pytest.raises(TypeError):
         qf.solve_poisson(W.astype(np.complex64))
     with pytest.raises(TypeError):

@@ -224,6 +224,31 @@ def test_isomp_hooks_errors_and_equivalence(qf):
         qf.isomp(W0.copy(), dt, 1, forcing=lambda P, W: W[:4, :4])
 
 
+@pytest.mark.parametrize("tag,kw", [("plain", dict()), ("compsum", dict(compsum=True))])
+def test_isomp_multistate(qf, tag, kw):
+    """(k, N, N) input = the reference's multi-state mode: members 1.. advected by member 0's stream function
+    (cpu.py:672-674), tolerance / residual / statistics from member 0 (isospectral.py:444-446, 528-531).
+    Golden: the reference's own output, <= 1e-12 relative Frobenius after 30 steps, same mean iteration count."""
+    import torch
+    g = golden("isomp_multistate_N32.npz")
+    dt, steps = float(g["dt"]), int(g["steps"])
+    W = g["W0"].copy()
+    stats = {'iterations': 0.0}
+    assert qf.isomp(W, dt, steps=steps, stats=stats, **kw) is W
+    assert relfro(W, g[f"{tag}_Wfinal"]) < 1e-12
+    assert stats['iterations'] == float(g[f"{tag}_mean_iterations"])
+    assert stats['tol_auto'] == pytest.approx(float(g[f"{tag}_tol_auto"]), rel=1e-14)
+    Wd = torch.from_numpy(g["W0"].copy()).to("cuda:0")
+    qf.isomp(Wd, dt, steps=steps, **kw)
+    assert np.array_equal(Wd.cpu().numpy(), W)
+    # member 0 is exactly the single-state run; an ensemble of the same members is something else
+    W0 = g["W0"][0].copy()
+    qf.isomp(W0, dt, steps=steps, **kw)
+    assert relfro(W0, W[0]) < 1e-14           # (the batched stream-K split differs: equal to rounding, not bitwise)
+    with pytest.raises(NotImplementedError):
+        qf.isomp(g["W0"].copy(), dt, 1, callback=lambda W, dW: None)
+
+
 def test_isomp_ensemble_matches_independent_runs(qf):
     """BASELINE config 5 in miniature: members converge independently."""
     N, k = 64, 5

@@ -176,6 +176,18 @@ def test_isomp_hooks(case):
             oracle.isomp(g["W0"].copy(), float(g["dt"]), 1, compsum=True, **kw)
 
 
+@pytest.mark.parametrize("tag,kw", [("plain", dict()), ("compsum", dict(compsum=True))])
+def test_isomp_multistate(tag, kw):
+    """(k, N, N) input: members 1.. are advected by member 0's stream function, tolerance and residual come from
+    member 0 (cpu.py:672-674, isospectral.py:444-446, 528-531)."""
+    g = golden("isomp_multistate_N32.npz")
+    rec, stats = {}, {'iterations': 0.0}
+    W = oracle.isomp(g["W0"].copy(), float(g["dt"]), int(g["steps"]), stats=stats, record=rec, **kw)
+    assert rec['iterations'] == list(g[f"{tag}_iterations"])
+    assert stats['tol_auto'] == pytest.approx(float(g[f"{tag}_tol_auto"]), rel=1e-14)
+    assert relfro(W, g[f"{tag}_Wfinal"]) < 1e-12
+
+
 def test_asserts_and_stats_semantics():
     W = oracle.random_skewherm(8, 3)
     with pytest.raises(AssertionError):
