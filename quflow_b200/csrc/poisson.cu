@@ -332,6 +332,36 @@ __device__ __forceinline__ void pb_send(double *local_slot, uint64_t *local_mbar
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(ra), "d"(v), "r"(rm) : "memory");
 }
 
+// L2 prefetch of the inputs of unit `un` with this CTA's thread mapping: the factor tables as two bulk requests, the
+// row pieces of W~ one request per end of a piece (fire and forget: no data comes back to the SM, so these requests do
+// not occupy the L1 miss queue that throttles ordinary loads to about 30 GB/s per SM at DRAM latency).
+template <int L, int M>
+__device__ __forceinline__ void pb_prefetch_unit(int un, const int4 *__restrict__ units, const double *__restrict__ tw,
+                                                 const double *__restrict__ tiu, const double2 *__restrict__ R, int N, int PC,
+                                                 int tid, int s, int plo)
+{
+    const unsigned stride = (unsigned)N + 1u;
+    const int4 nd = __ldg(units + 2 * un);
+    if (tid < 2) {
+        const double *t = (tid == 0 ? tw : tiu) + (size_t)un * PC * M;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t), "r"(PC * M * 8) : "memory");
+    }
+    if (s == 0 || s == M - 1) {
+        const int nmL = nd.x * M + s, nmS = nd.z * M + s;
+        const int nnL = (nd.x >= 0) ? min(nd.w, max(0, N - nmL - nd.y)) : 0;
+        const int nnS = (nd.z >= 0) ? max(0, N - nmS) : 0;
+        const unsigned noL = (unsigned)nd.y * stride + (unsigned)nmL;
+        const unsigned noS = (unsigned)nmS - (unsigned)nd.w * stride;
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+            const int pl = plo + i;
+            const bool sh = pl >= nd.w;
+            const bool ok = sh ? (pl - nd.w < nnS) : (pl < nnL);
+            if (ok) asm volatile("prefetch.global.L2 [%0];" ::"l"(R + ((unsigned)pl * stride + (sh ? noS : noL))));
+        }
+    }
+}
+
 template <int L, int M, int CL, int NTMAX>
 __global__ void __launch_bounds__(NTMAX, 512 / NTMAX)
 k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const double *__restrict__ tw,
@@ -521,29 +551,9 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
         if (lane < M) { xA = 1.0; xBx = 0.0; xBy = 0.0; }
     }
     PT(2);
-    // ---- L2 prefetch of the unit pf_stride ahead (same thread mapping; one request per end of a row piece)
-    if (pf_stride > 0 && unit + pf_stride < nunits) {
-        const int un = unit + pf_stride;
-        const int4 nd = __ldg(units + 2 * un);
-        if (tid < 2) {
-            const double *t = (tid == 0 ? tw : tiu) + (size_t)un * PC * M;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t), "r"(PC * M * 8) : "memory");
-        }
-        if (s == 0 || s == M - 1) {
-            const int nmL = nd.x * M + s, nmS = nd.z * M + s;
-            const int nnL = (nd.x >= 0) ? min(nd.w, max(0, N - nmL - nd.y)) : 0;
-            const int nnS = (nd.z >= 0) ? max(0, N - nmS) : 0;
-            const unsigned noL = (unsigned)nd.y * stride + (unsigned)nmL;
-            const unsigned noS = (unsigned)nmS - (unsigned)nd.w * stride;
-#pragma unroll
-            for (int i = 0; i < L; ++i) {
-                const int pl = plo + i;
-                const bool sh = pl >= nd.w;
-                const bool ok = sh ? (pl - nd.w < nnS) : (pl < nnL);
-                if (ok) asm volatile("prefetch.global.L2 [%0];" ::"l"(R + ((unsigned)pl * stride + (sh ? noS : noL))));
-            }
-        }
-    }
+    // ---- L2 prefetch of the unit pf_stride ahead: it will follow this one on the same SM slot
+    if (pf_stride > 0 && unit + pf_stride < nunits)
+        pb_prefetch_unit<L, M>(unit + pf_stride, units, tw, tiu, R, N, PC, tid, s, plo);
     if (lane >= 32 - M) { totA[warp][s] = A; totBx[warp][s] = B.x; totBy[warp][s] = B.y; }
     __syncthreads();
     PT(3);
