@@ -65,12 +65,10 @@ int qf_build_tables(qf_handle_s *h)
     // entries of a unit are contiguous and ordered [warp block][i][chunk in block][s]: the 32 lanes of a warp read
     // 32 consecutive doubles for every i.  Entries outside the diagonals are 0 (which also decouples the pieces).
     {
-        int L = 16, M = 4;
-        if (const char *env = getenv("QF_POISSON_L")) L = atoi(env) == 8 ? 8 : 16;
-        if (const char *env = getenv("QF_POISSON_M")) M = atoi(env) == 8 ? 8 : 4;
+        // Measured at N = 2048: 16 positions per thread, 4 diagonals per band and CTAs of up to 512
+        // threads are the fastest combination (8 positions: +13 us; 8 diagonals: +7 us; 256-thread cluster pairs: +3 us).
+        const int L = 16, M = 4, NTMAX = 512;
         const int chunks = (N + L - 1) / L;
-        int NTMAX = 512;
-        if (const char *env = getenv("QF_POISSON_NT")) NTMAX = atoi(env) == 256 ? 256 : 512;
         int NT = NTMAX, CL = 1;
         if (M * chunks <= NTMAX) {
             NT = ((M * chunks + 31) / 32) * 32;
@@ -839,12 +837,11 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
         const int PC = (NT / M) * L;
         const size_t smem = std::max((size_t)NT * L * 8, (size_t)(PC * M + (PC / L) * 4) * sizeof(double2));
         void *fn = nullptr;
-#define QF_PB(LL, MM, CC)                                                                               \
-    if (L == LL && M == MM && CL == CC) fn = h->p_NTMAX == 512 ? (void *)k_poisson_band<LL, MM, CC, 512> : (void *)k_poisson_band<LL, MM, CC, 256>;
-        QF_PB(16, 8, 1) QF_PB(16, 8, 2) QF_PB(16, 8, 4) QF_PB(16, 8, 8) QF_PB(16, 4, 1) QF_PB(16, 4, 2) QF_PB(16, 4, 4) QF_PB(16, 4, 8)
-        QF_PB(8, 8, 1) QF_PB(8, 8, 2) QF_PB(8, 8, 4) QF_PB(8, 8, 8) QF_PB(8, 4, 1) QF_PB(8, 4, 2) QF_PB(8, 4, 4) QF_PB(8, 4, 8)
+#define QF_PB(CC) if (L == 16 && M == 4 && CL == CC && h->p_NTMAX == 512) fn = (void *)k_poisson_band<16, 4, CC, 512>;
+        QF_PB(1) QF_PB(2) QF_PB(4) QF_PB(8)
 #undef QF_PB
-        static void *attr_fn[32] = {nullptr};
+        if (!fn) { qf_set_error("no k_poisson_band instantiation for L=%d M=%d CL=%d", L, M, CL); return QF_ERR_UNSUPPORTED; }
+        static void *attr_fn[8] = {nullptr};
         bool seen = false;
         for (void *f : attr_fn) seen |= (f == fn);
         if (!seen) {
