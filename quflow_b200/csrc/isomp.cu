@@ -178,7 +178,8 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
 // Row sums of the residual (one warp per row, slots contiguous), max over rows through an order-independent
 // atomicMax, and the stopping rule evaluated by the last block to finish (ticket counter).
 __global__ void __launch_bounds__(256)
-k_control(const double *__restrict__ rowpart, int N, int nslots, QfCtrl *ctrl, int maxit, int minit, int nfollow)
+k_control(const double *__restrict__ rowpart, int N, int nslots, QfCtrl *ctrl, int maxit, int minit, int nfollow,
+          cudaGraphConditionalHandle cond, int use_cond)
 {
     const int b = blockIdx.y;
     QfCtrl &c = ctrl[b];
@@ -238,6 +239,9 @@ k_control(const double *__restrict__ rowpart, int N, int nslots, QfCtrl *ctrl, i
     __threadfence();
     c.active = active;
     for (int f = 1; f <= nfollow; ++f) ctrl[f].active = active;
+    // one deciding member (single run or multi-state): arm the WHILE node of the step graph right here instead of in a
+    // separate k_loop_cond launch
+    if (use_cond) cudaGraphSetConditional(cond, (unsigned)active);
 }
 
 // multi-state run: P~ of member 0 is everybody's stream function (select_first, cpu.py:672-674)
@@ -456,7 +460,7 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
     k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, G, W, h->Wh, nullptr, 0.0,
                                      push ? h->A2 : nullptr, push ? h->S2 : nullptr);
     k_control<<<dim3((N + 7) / 8, multistate ? 1 : h->batch), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit,
-                                                                        multistate ? h->batch - 1 : 0);
+                                                                        multistate ? h->batch - 1 : 0, h->cap_cond, h->cap_use_cond);
     h->launches += 2;
     if (ev) QF_CUDA(cudaEventRecord(ev[4], st));
     QF_CUDA(cudaGetLastError());
@@ -586,8 +590,14 @@ static int build_step_graph(qf_handle_s *h, double2 *W, double eps, int maxit, i
     // loop body by stream capture (the launchers below are the same ones the eager path uses)
     const long long l0 = h->launches;
     QF_G(cudaStreamBeginCaptureToGraph(h->cap_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    // with ONE deciding member (single run, multi-state) k_control arms the WHILE node itself; ensembles need the OR
+    // over their members: k_loop_cond
+    const bool single_decider = (B == 1) || h->multistate;
+    h->cap_cond = g->cond;
+    h->cap_use_cond = single_decider ? 1 : 0;
     int rc = qf_enqueue_iteration(h, W, eps, maxit, minit, h->cap_stream, nullptr);
-    if (rc == QF_OK) {
+    h->cap_use_cond = 0;
+    if (rc == QF_OK && !single_decider) {
         k_loop_cond<<<1, 1, 0, h->cap_stream>>>(h->ctrl, B, g->cond);
         h->launches++;
     }
@@ -827,7 +837,7 @@ extern "C" int qf_step_close_iteration(qf_handle_t h, const void *W_dev, const v
     else
         k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, N, 1, (const double2 *)W_dev, h->Wh, nullptr, 0.0,
                                          nullptr, nullptr);
-    k_control<<<dim3((N + 7) / 8, 1), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit, 0);
+    k_control<<<dim3((N + 7) / 8, 1), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit, 0, 0, 0);
     h->launches += 2;
     QF_CUDA(cudaGetLastError());
     QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl), cudaMemcpyDeviceToHost, st));

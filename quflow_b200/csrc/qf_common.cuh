@@ -105,6 +105,8 @@ struct qf_handle_s {
     void *step_graph = nullptr;
     cudaStream_t cap_stream = nullptr;
     int use_graph = 1;
+    unsigned long long cap_cond = 0;   // conditional handle of the step graph being captured
+    int cap_use_cond = 0;              // k_control arms the WHILE node (set only while capturing)
     // host-stepped driver (qf_step_*): parameters fixed by qf_step_open
     double step_eps = 0.0;
     unsigned step_flags = 0;
