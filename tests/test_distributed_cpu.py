@@ -51,6 +51,25 @@ def _free_port():
     return p
 
 
+class _FakeHandle:
+    """Stands in for binding.Handle: records what attach_row_sharding asks the library to do (no CUDA)."""
+
+    def __init__(self, N, rank):
+        self.N, self.rank, self.calls = N, rank, []
+
+    def p2p_export(self):
+        return bytes([self.rank]) * 256
+
+    def p2p_import(self, blobs, rank, world):
+        self.calls.append(("import", [b[0] for b in blobs], rank, world))
+
+    def comm_set_push(self, enable):
+        self.calls.append(("push", bool(enable)))
+
+    def comm_init(self, uid, rank, world):
+        self.calls.append(("nccl", len(uid), rank, world))
+
+
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -65,6 +84,19 @@ def _worker(rank, world, port, out):
         gathered = [None] * world
         dist.all_gather_object(gathered, mine.tolist())
         ok = ok and sum(gathered, []) == list(range(k))
+        # row sharding set-up: every rank imports every rank's IPC blob in rank order; the data path follows `mode`
+        h = _FakeHandle(1024, rank)
+        qd.attach_row_sharding(h, dist, mode="p2p")
+        ok = ok and h.calls == [("import", list(range(world)), rank, world)]          # default: the library picks push/pull
+        for mode, want in (("push", True), ("pull", False)):
+            h = _FakeHandle(1024, rank)
+            qd.attach_row_sharding(h, dist, mode=mode)
+            ok = ok and h.calls == [("import", list(range(world)), rank, world), ("push", want)]
+        try:
+            qd.attach_row_sharding(_FakeHandle(1002, rank), dist)                    # N not divisible by 2 * world
+            ok = False
+        except ValueError:
+            pass
         out[rank] = ok
     finally:
         dist.destroy_process_group()
