@@ -187,6 +187,8 @@ int qf_comm_p2p_import(qf_handle_t h, const void *blobs /* nranks * QF_P2P_BLOB_
  * double-buffered by iteration parity, and one flag barrier per fixed-point iteration replaces the gathers.
  * qf_comm_set_push(h, 0) selects the separate pull kernels instead (also: QF_COMM=pull in the environment). */
 int qf_comm_set_push(qf_handle_t h, int enable);
+/* Data path in use: 0 none (single GPU / emulated ranks), 1 NCCL all-gather, 2 pull kernels, 3 fused GEMM + push. */
+int qf_comm_mode(qf_handle_t h);
 /* Test hook: run the row-sharded data path for `nranks` ranks on ONE GPU (all ranks' tiles, no communication). */
 int qf_set_emulated_ranks(qf_handle_t h, int nranks);
 

@@ -86,6 +86,7 @@ SYMBOLS = {
     "qf_comm_p2p_export": (_i, [_vp, _vp]),
     "qf_comm_p2p_import": (_i, [_vp, _vp, _i, _i]),
     "qf_comm_set_push": (_i, [_vp, _i]),
+    "qf_comm_mode": (_i, [_vp]),
 }
 
 
@@ -322,6 +323,9 @@ class Handle:
         raw = b"".join(blobs)
         assert len(raw) == nranks * QF_P2P_BLOB_BYTES
         _check(self._lib.qf_comm_p2p_import(self._h, ctypes.create_string_buffer(raw, len(raw)), int(rank), int(nranks)))
+
+    def comm_mode(self) -> str:
+        return {0: "none", 1: "nccl", 2: "pull", 3: "push"}[int(self._lib.qf_comm_mode(self._h))]
 
     def comm_set_push(self, enable: bool):
         _check(self._lib.qf_comm_set_push(self._h, 1 if enable else 0))

@@ -335,6 +335,9 @@ extern "C" int qf_comm_set_push(qf_handle_t h, int enable)
     return QF_OK;
 }
 
+// 0: single GPU / emulated ranks, 1: NCCL all-gather, 2: pull kernels, 3: fused GEMM + push
+extern "C" int qf_comm_mode(qf_handle_t h) { return h ? h->comm_mode : 0; }
+
 // Single-GPU emulation of G ranks (tests): same tile lists, same permuted layout, no communication.
 extern "C" int qf_set_emulated_ranks(qf_handle_t h, int nranks)
 {
