@@ -185,9 +185,11 @@ int qf_comm_p2p_import(qf_handle_t h, const void *blobs /* nranks * QF_P2P_BLOB_
 /* After the import the default data path is the FUSED one: the GEMM kernel stores every finished tile of its row
  * blocks into all peers' copies of the output as well (plain stores through the NVLink peer mappings), A and S are
  * double-buffered by iteration parity, and one flag barrier per fixed-point iteration replaces the gathers.
- * qf_comm_set_push(h, 0) selects the separate pull kernels instead (also: QF_COMM=pull in the environment). */
+ * qf_comm_set_push(h, 0) selects the separate pull kernels instead, qf_comm_set_push(h, 2) one push-copy kernel after
+ * both GEMMs (also: QF_COMM=pull|push|pushcopy in the environment). */
 int qf_comm_set_push(qf_handle_t h, int enable);
-/* Data path in use: 0 none (single GPU / emulated ranks), 1 NCCL all-gather, 2 pull kernels, 3 fused GEMM + push. */
+/* Data path in use: 0 none (single GPU / emulated ranks), 1 NCCL all-gather, 2 pull kernels, 3 fused GEMM + push,
+ * 4 push-copy kernel after the GEMMs. */
 int qf_comm_mode(qf_handle_t h);
 /* Test hook: run the row-sharded data path for `nranks` ranks on ONE GPU (all ranks' tiles, no communication). */
 int qf_set_emulated_ranks(qf_handle_t h, int nranks);

@@ -325,10 +325,11 @@ class Handle:
         _check(self._lib.qf_comm_p2p_import(self._h, ctypes.create_string_buffer(raw, len(raw)), int(rank), int(nranks)))
 
     def comm_mode(self) -> str:
-        return {0: "none", 1: "nccl", 2: "pull", 3: "push"}[int(self._lib.qf_comm_mode(self._h))]
+        return {0: "none", 1: "nccl", 2: "pull", 3: "push", 4: "pushcopy"}[int(self._lib.qf_comm_mode(self._h))]
 
-    def comm_set_push(self, enable: bool):
-        _check(self._lib.qf_comm_set_push(self._h, 1 if enable else 0))
+    def comm_set_push(self, enable):
+        """False/0: pull kernels, True/1: fused GEMM + push, 2: one push-copy kernel after the GEMMs."""
+        _check(self._lib.qf_comm_set_push(self._h, int(enable)))
 
     def comm_init(self, unique_id: bytes, rank: int, nranks: int):
         buf = ctypes.create_string_buffer(unique_id, QF_UNIQUE_ID_BYTES)

@@ -189,6 +189,7 @@ extern "C" int qf_comm_p2p_import(qf_handle_t h, const void *blobs, int rank, in
         pull = tiles < 2LL * h->sm_count;
     }
     h->comm_mode = (nranks > 1) ? (pull ? 2 : 3) : 0;
+    if (nranks > 1 && env && strcmp(env, "pushcopy") == 0) h->comm_mode = 4;
     return QF_OK;
 }
 
@@ -311,13 +312,67 @@ int qf_comm_push_barrier(qf_handle_s *h, bool gated, cudaStream_t st)
     return QF_OK;
 }
 
+// Push-copy mode: the GEMMs write their (double-buffered) outputs locally; afterwards one kernel copies this rank's
+// rows of A and of S into every peer's copy with plain remote stores (NVLink writes run faster than the reads of the
+// pull kernels), followed by the same flag barrier.  One warp per (matrix, row): the row is read once from local
+// memory, 8 x 16 bytes per lane in flight, and stored to all peers.
+__global__ void __launch_bounds__(256)
+k_push_rows(double2 *const *__restrict__ peersA, double2 *const *__restrict__ peersS, int rank, int nranks, int N, int hb,
+            const QfCtrl *__restrict__ ctrl, int gated)
+{
+    if (gated && !ctrl[0].active) return;
+    const int par = (int)(ctrl[0].gseq & 1ull);
+    double2 *const *pa = peersA + par * QF_MAX_RANKS;
+    double2 *const *ps = peersS + par * QF_MAX_RANKS;
+    const int lane = threadIdx.x & 31;
+    const int rows_per_rank = 2 * hb;
+    const int total = 2 * rows_per_rank;                   // A rows, then S rows
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
+        const int kind = w / rows_per_rank;
+        const int lr = w - kind * rows_per_rank;           // row inside this rank's permuted region
+        const int prow = rank * rows_per_rank + lr;
+        int c0 = 0;
+        if (kind == 1) {                                   // k_post reads S only at columns >= its row (64-aligned tiles)
+            const int blk = lr < hb ? rank : 2 * nranks - 1 - rank;
+            c0 = ((blk * hb) / 64) * 64;
+        }
+        double2 *const *tab = kind ? ps : pa;
+        const double2 *__restrict__ src = tab[rank] + (size_t)prow * N;
+        for (int c = c0 + lane; c < N; c += 32 * 8) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (c + 32 * u < N) v[u] = __ldcg(src + c + 32 * u);
+            for (int p = 0; p < nranks; ++p) {
+                if (p == rank) continue;
+                double2 *__restrict__ d = tab[p] + (size_t)prow * N;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (c + 32 * u < N) d[c + 32 * u] = v[u];
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+int qf_comm_push_rows(qf_handle_s *h, bool gated, cudaStream_t st)
+{
+    QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
+    const int hb = qf_block_rows(h->N, h->nranks);
+    k_push_rows<<<h->sm_count * 2, 256, 0, st>>>(p->pushA_dev, p->pushS_dev, h->rank, h->nranks, h->N, hb, h->ctrl, gated ? 1 : 0);
+    h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
 int qf_comm_push_args(qf_handle_s *h, int kind, QfGemmPush *out)
 {
     QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
     if (!p || !p->pushA_dev) { qf_set_error("push mode needs qf_comm_p2p_import"); return QF_ERR_INVALID; }
     out->C1 = kind == 0 ? h->A2 : h->S2;
     out->A1 = kind == 0 ? nullptr : h->A2;      // the second GEMM multiplies the A of the same iteration
-    out->peers = kind == 0 ? p->pushA_dev : p->pushS_dev;
+    out->peers = (h->comm_mode == 4) ? nullptr : (kind == 0 ? p->pushA_dev : p->pushS_dev);   // mode 4 copies after the GEMMs
     out->nranks = h->nranks;
     out->rank = h->rank;
     return QF_OK;
@@ -326,11 +381,11 @@ int qf_comm_push_args(qf_handle_s *h, int kind, QfGemmPush *out)
 // Switch between the fused push (1, default) and the separate pull kernels (0) after qf_comm_p2p_import.
 extern "C" int qf_comm_set_push(qf_handle_t h, int enable)
 {
-    if (!h || !h->p2p || h->nranks < 2 || (h->comm_mode != 2 && h->comm_mode != 3)) {
+    if (!h || !h->p2p || h->nranks < 2 || h->comm_mode < 2) {
         qf_set_error("qf_comm_set_push: the handle has no peer-memory communicator");
         return QF_ERR_INVALID;
     }
-    h->comm_mode = enable ? 3 : 2;
+    h->comm_mode = enable == 2 ? 4 : (enable ? 3 : 2);   // 2: push-copy after the GEMMs
     qf_graph_destroy(h);   // the step graph bakes the data path in
     return QF_OK;
 }

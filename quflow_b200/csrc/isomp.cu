@@ -440,7 +440,7 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
         h->launches++;
     }
     if (ev) QF_CUDA(cudaEventRecord(ev[1], st));
-    const bool push = real_comm && h->comm_mode == 3;
+    const bool push = real_comm && (h->comm_mode == 3 || h->comm_mode == 4);   // double-buffered A/S + flag barrier
     QfGemmPush pa, ps;
     if (push) {
         QF_CHECK(qf_comm_push_args(h, 0, &pa));
@@ -453,7 +453,8 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
     if (ev) QF_CUDA(cudaEventRecord(ev[2], st));
     QF_CHECK(qf_launch_zgemm(h, h->A, h->P, h->S, true, true, my, G, true, st, push ? &ps : nullptr));      // rows of S = A P~ (A rows are local)
     if (real_comm && !push) QF_CHECK(h->comm_mode == 2 ? qf_comm_p2p_allgather(h, 1, true, st) : qf_comm_allgather_rows(h, h->S, st));
-    if (push) QF_CHECK(qf_comm_push_barrier(h, true, st));   // the GEMM epilogues pushed the tiles; wait until everybody's have landed
+    if (push && h->comm_mode == 4) QF_CHECK(qf_comm_push_rows(h, true, st));   // copy my rows of A and S into the peers' buffers
+    if (push) QF_CHECK(qf_comm_push_barrier(h, true, st));   // pushed tiles / rows: wait until everybody's have landed
     if (ev) QF_CUDA(cudaEventRecord(ev[3], st));
     const int nb = (N + TS - 1) / TS;
     dim3 g(nb, nb, h->batch);
@@ -473,7 +474,7 @@ int qf_enqueue_update(qf_handle_s *h, double2 *W, bool compsum, bool reinit, cud
     const int nb = (N + TS - 1) / TS;
     const int hb = qf_block_rows(N, h->nranks);
     dim3 g(nb, nb, h->batch);
-    const double2 *A1 = (h->nranks > 1 && h->comm_mode == 3) ? h->A2 : nullptr;
+    const double2 *A1 = (h->nranks > 1 && h->comm_mode >= 3) ? h->A2 : nullptr;
     if (compsum)
         k_update<true, false><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks, h->dW, h->Wh, reinit ? 1 : 0, nullptr, 0.0, A1);
     else
@@ -620,7 +621,7 @@ static int build_step_graph(qf_handle_s *h, double2 *W, double eps, int maxit, i
     int reinit_i = reinit ? 1 : 0;
     const double2 *Fnull = nullptr;
     double fzero = 0.0;
-    const double2 *A1p = (h->nranks > 1 && h->comm_mode == 3) ? h->A2 : nullptr;
+    const double2 *A1p = (h->nranks > 1 && h->comm_mode >= 3) ? h->A2 : nullptr;
     QF_G(add_kernel_node(&n_update, g->graph, &n_while, 1, upd, gu, dim3(256), Ap, W, Kp, Nv, ctrl, iters, steps_cap, hb, G, dWp, Whp, reinit_i, Fnull, fzero, A1p));
     QF_G(cudaGraphInstantiate(&g->exec, g->graph, 0));
 #undef QF_G

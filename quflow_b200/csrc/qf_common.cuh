@@ -99,6 +99,7 @@ struct qf_handle_s {
     void *p2p = nullptr;          // QfP2P (comm.cu)
     int comm_mode = 0;            // 0: none / emulated, 1: NCCL all-gather (eager only), 2: peer-memory pull kernel,
                                   // 3: GEMM epilogue pushes its tiles to the peers (fused all-gather), double-buffered A/S
+                                  // 4: one push-copy kernel after both GEMMs, double-buffered A/S
     int rank = 0, nranks = 1;     // nranks > 1 with nccl_comm == nullptr: all ranks emulated on this GPU (tests)
     QfGemmPlan *gemm = nullptr;
     // CUDA-graph execution of a step (isomp.cu)
@@ -161,6 +162,7 @@ __host__ __device__ __forceinline__ int qf_prow(int i, int hb, int G)
 }
 int qf_comm_allgather_rows(qf_handle_s *h, double2 *M, cudaStream_t st);   // comm.cu
 int qf_comm_p2p_allgather(qf_handle_s *h, int kind, bool gated, cudaStream_t st);   // comm.cu
+int qf_comm_push_rows(qf_handle_s *h, bool gated, cudaStream_t st);                 // comm.cu: mode 4, copy my rows of A and S to the peers
 int qf_comm_push_barrier(qf_handle_s *h, bool gated, cudaStream_t st);              // comm.cu: all peers' pushed tiles have landed
 int qf_comm_push_args(qf_handle_s *h, int kind, QfGemmPush *out);                    // comm.cu: kind 0 = A, 1 = S
 void qf_p2p_destroy(qf_handle_s *h);

@@ -75,8 +75,8 @@ def attach_row_sharding(handle, dist, mode=None):
         blobs = [None] * world
         dist.all_gather_object(blobs, handle.p2p_export())
         handle.p2p_import(blobs, rank, world)       # picks push or pull by the tile count per rank (csrc/comm.cu)
-        if mode in ("push", "pull"):
-            handle.comm_set_push(mode == "push")
+        if mode in ("push", "pull", "pushcopy"):
+            handle.comm_set_push({"pull": 0, "push": 1, "pushcopy": 2}[mode])
         dist.barrier()              # every rank has mapped every peer before anybody starts signalling
     return handle
 

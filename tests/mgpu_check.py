@@ -21,7 +21,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for N, steps, mode in ((256, 10, "push"), (256, 10, "pull"), (256, 10, "nccl"), (1024, 12, "push"), (1024, 6, "pull")):
+    for N, steps, mode in ((256, 10, "push"), (256, 10, "pull"), (256, 10, "pushcopy"), (256, 10, "nccl"), (1024, 12, "push"),
+                           (1024, 6, "pull"), (1024, 12, "pushcopy")):
         W0 = oracle.random_skewherm(N, 42)
         dt = 0.25 * qf.hbar(N)
         solo = Handle(N, 1, local)

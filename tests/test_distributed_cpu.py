@@ -64,7 +64,7 @@ class _FakeHandle:
         self.calls.append(("import", [b[0] for b in blobs], rank, world))
 
     def comm_set_push(self, enable):
-        self.calls.append(("push", bool(enable)))
+        self.calls.append(("push", bool(enable)))          # 0 pull, 1 fused push, 2 push-copy
 
     def comm_init(self, uid, rank, world):
         self.calls.append(("nccl", len(uid), rank, world))
@@ -88,7 +88,7 @@ def _worker(rank, world, port, out):
         h = _FakeHandle(1024, rank)
         qd.attach_row_sharding(h, dist, mode="p2p")
         ok = ok and h.calls == [("import", list(range(world)), rank, world)]          # default: the library picks push/pull
-        for mode, want in (("push", True), ("pull", False)):
+        for mode, want in (("push", True), ("pull", False), ("pushcopy", True)):
             h = _FakeHandle(1024, rank)
             qd.attach_row_sharding(h, dist, mode=mode)
             ok = ok and h.calls == [("import", list(range(world)), rank, world), ("push", want)]
