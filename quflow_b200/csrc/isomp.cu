@@ -486,7 +486,7 @@ int qf_enqueue_update(qf_handle_s *h, double2 *W, bool compsum, bool reinit, cud
 
 // ------------------------------------------------------------------------------- step graph
 // One CUDA graph per step:  k_step_begin -> [k_zero] -> WHILE(any member active) { one fixed-point iteration } -> k_update.
-// The WHILE node is a CUDA conditional node whose handle is set on the device (k_step_begin / k_loop_cond), so the
+// The WHILE node is a CUDA conditional node whose handle is set on the device (k_step_begin, then k_control or k_loop_cond), so the
 // number of iterations is decided by the GPU and no launch is wasted on iterations after convergence.
 struct QfStepGraph {
     cudaGraph_t graph = nullptr;
