@@ -88,6 +88,11 @@ int qf_laplace(qf_handle_t h, const void *P_dev, void *W_dev, void *stream);
  * scipy.linalg.norm(., ord=inf) (:534).  out_host receives `batch` doubles. Synchronises. */
 int qf_norm_inf(qf_handle_t h, const void *W_dev, double *out_host, void *stream);
 
+/* out_host[b] = sum_ij Re(P_ij conj(W_ij)) per member: N * inner_L2(P, W) (quflow/geometry.py:72-76), the building block
+ * of norm_L2 (:53-68) and of the loggers energy_euler / enstrophy / inner_Hm1 / inner_H1 (quflow/physics.py:9-38).
+ * Deterministic (fixed grid and summation tree).  Synchronises. */
+int qf_inner(qf_handle_t h, const void *P_dev, const void *W_dev, double *out_host, void *stream);
+
 /* C = A @ B for N x N complex128 (batch members) with the hand-written DMMA kernel —
  * the np.matmul / zgemm calls at isospectral.py:496,499.  Exposed for tests and micro-benchmarks. */
 int qf_zgemm(qf_handle_t h, const void *A_dev, const void *B_dev, void *C_dev, void *stream);

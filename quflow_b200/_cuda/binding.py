@@ -61,6 +61,7 @@ SYMBOLS = {
     "qf_solve_poisson": (_i, [_vp, _vp, _vp, _vp]),
     "qf_laplace": (_i, [_vp, _vp, _vp, _vp]),
     "qf_norm_inf": (_i, [_vp, _vp, ctypes.POINTER(_d), _vp]),
+    "qf_inner": (_i, [_vp, _vp, _vp, ctypes.POINTER(_d), _vp]),
     "qf_zgemm": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "qf_isomp": (_i, [_vp, _vp, _d, _i, _d, _i, _i, _u, ctypes.POINTER(qf_stats), ctypes.POINTER(ctypes.c_int32), _vp]),
     "qf_isomp_host": (_i, [_vp, _vp, _d, _i, _d, _i, _i, _u, ctypes.POINTER(qf_stats), ctypes.POINTER(ctypes.c_int32)]),
@@ -209,6 +210,14 @@ class Handle:
         self._shape_ok(W)
         out = (ctypes.c_double * self.batch)()
         _check(self._lib.qf_norm_inf(self._h, _dev_ptr(W), out, _stream_ptr()))
+        return np.array(out[:])
+
+    def inner(self, P, W):
+        """sum_ij Re(P_ij conj(W_ij)) per member (device tensors)."""
+        self._shape_ok(P)
+        self._shape_ok(W)
+        out = (ctypes.c_double * self.batch)()
+        _check(self._lib.qf_inner(self._h, _dev_ptr(P), _dev_ptr(W), out, _stream_ptr()))
         return np.array(out[:])
 
     def zgemm(self, A, B, out=None):

@@ -98,7 +98,7 @@ extern "C" int qf_destroy(qf_handle_t h)
     qf_comm_destroy(h);
     qf_p2p_destroy(h);
     void *ptrs[] = {h->tab_w, h->tab_iu, h->tab_o, h->ptab_w, h->ptab_iu, h->ptab_units, h->dW, h->Wh, h->P, h->A, h->S, h->scratch, h->kahan_c,
-                    h->io, h->io2, h->rowpart, h->trbuf, h->ctrl, h->iters_dev};
+                    h->io, h->io2, h->rowpart, h->trbuf, h->inner_part, h->ctrl, h->iters_dev};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);

@@ -405,7 +405,58 @@ __global__ void k_scale(double2 *X, size_t n, double s, int divide)
     }
 }
 
+// ------------------------------------------------------------------------------- <P, W>_L2
+// sum_ij Re(P_ij conj(W_ij)) per member (quflow/geometry.py:72-76 without the 1/N): fixed grid, fixed tree => the
+// result does not depend on scheduling.  Stage 1: per-block partial sums; stage 2: one block adds them in order.
+constexpr int INNER_BLOCKS = 256;
+__global__ void __launch_bounds__(256)
+k_inner_partial(const double2 *__restrict__ P, const double2 *__restrict__ W, size_t n2, double *__restrict__ part)
+{
+    const int b = blockIdx.y;
+    const double2 *p = P + (size_t)b * n2, *w = W + (size_t)b * n2;
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        const double2 a = p[i], c = w[i];
+        s += a.x * c.x + a.y * c.y;
+    }
+    __shared__ double sh[8];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int q = 0; q < 8; ++q) t += sh[q];
+        part[(size_t)b * gridDim.x + blockIdx.x] = t;
+    }
+}
+__global__ void k_inner_final(const double *__restrict__ part, int nblocks, double *__restrict__ out)
+{
+    const int b = blockIdx.x;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += 32) s += part[(size_t)b * nblocks + i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[b] = s;
+}
+
 }   // namespace
+
+// out_host[b] = sum_ij Re(P_ij conj(W_ij)) of member b; the caller divides by N (inner_L2) or takes the root (norm_L2).
+extern "C" int qf_inner(qf_handle_t h, const void *P_dev, const void *W_dev, double *out_host, void *stream)
+{
+    if (!h || !P_dev || !W_dev || !out_host) { qf_set_error("qf_inner: null argument"); return QF_ERR_INVALID; }
+    QF_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = h->batch;
+    if (!h->inner_part) QF_CUDA(cudaMalloc(&h->inner_part, sizeof(double) * (size_t)B * (INNER_BLOCKS + 1)));
+    double *part = h->inner_part, *res = h->inner_part + (size_t)B * INNER_BLOCKS;
+    k_inner_partial<<<dim3(INNER_BLOCKS, B), 256, 0, st>>>((const double2 *)P_dev, (const double2 *)W_dev, h->mat_elems, part);
+    k_inner_final<<<B, 32, 0, st>>>(part, INNER_BLOCKS, res);
+    h->launches += 2;
+    QF_CUDA(cudaGetLastError());
+    QF_CUDA(cudaMemcpyAsync(out_host, res, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    QF_CUDA(cudaStreamSynchronize(st));
+    return QF_OK;
+}
 
 // ------------------------------------------------------------------------------- launchers
 int qf_launch_norm_inf(qf_handle_s *h, const double2 *W, cudaStream_t st)

@@ -88,6 +88,7 @@ struct qf_handle_s {
     // residual partial row sums: [batch][2][nslots][N]
     double *rowpart = nullptr;
     double2 *trbuf = nullptr;     // [batch] mean of diag(W~)
+    double *inner_part = nullptr; // qf_inner partial sums, lazily allocated
     int nslots = 0;
     QfCtrl *ctrl = nullptr;       // [batch] device
     int32_t *iters_dev = nullptr; // [batch * steps_cap]

@@ -114,3 +114,30 @@ def test_zgemm_batched(qf):
     B = rng.randn(k, N, N) + 1j * rng.randn(k, N, N)
     C = get_handle(N, k).zgemm(to_dev(A), to_dev(B)).cpu().numpy()
     assert relfro(C, A @ B) < 1e-14
+
+
+def test_inner_products_and_loggers(qf):
+    """quflow/geometry.py:53-76 and quflow/physics.py:9-38 on the device: inner_L2, norm_L2, energy_euler, enstrophy,
+    H^-1 / H^1 inner products.  Tolerance 1e-13 relative (only the summation order differs from numpy)."""
+    import torch
+    N = 96
+    W = oracle.random_skewherm(N, 4)
+    V = oracle.random_skewherm(N, 5)
+    P = oracle.solve_poisson(W)
+    ref_inner = float((V * W.conj()).sum().real / N)
+    assert qf.inner_L2(V, W) == pytest.approx(ref_inner, rel=1e-13)
+    assert qf.norm_L2(W) == pytest.approx(np.linalg.norm(W) / np.sqrt(N), rel=1e-14)
+    assert qf.enstrophy(W) == pytest.approx(float((W * W.conj()).sum().real / N) / 2.0, rel=1e-14)
+    e_ref = -float((W * P.conj()).sum().real / N) / 2.0
+    assert qf.energy_euler(W) == pytest.approx(e_ref, rel=1e-12)
+    assert qf.energy_euler(torch.from_numpy(W).to("cuda:0")) == qf.energy_euler(W)      # deterministic, same path
+    assert qf.inner_Hm1(V, W) == pytest.approx(-float((V * P.conj()).sum().real / N), rel=1e-11)
+    assert qf.norm_Hm1(W) == pytest.approx(np.sqrt(2.0 * e_ref), rel=1e-12)
+    LW = oracle.laplace(P)
+    assert qf.inner_H1(V, P) == pytest.approx(-float((V * LW.conj()).sum().real / N), rel=1e-11)
+    assert qf.norm_H1(P) == pytest.approx(np.sqrt(-float((P * LW.conj()).sum().real / N)), rel=1e-12)
+    # energy and enstrophy are invariants of the flow: conserved by isomp to the fixed-point tolerance
+    W1 = W.copy()
+    qf.isomp(W1, 0.25 * qf.hbar(N), steps=20)
+    assert qf.enstrophy(W1) == pytest.approx(qf.enstrophy(W), rel=1e-9)
+    assert qf.energy_euler(W1) == pytest.approx(qf.energy_euler(W), rel=1e-8)      # near-conserved (oracle: -7e-10)
