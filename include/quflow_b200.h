@@ -80,6 +80,13 @@ int qf_destroy(qf_handle_t h);
  * skew-Hermitian.  W_dev and P_dev hold `batch` matrices; they may not alias. */
 int qf_solve_poisson(qf_handle_t h, const void *W_dev, void *P_dev, void *stream);
 
+/* Work plan of the Poisson kernel for size N (pure host code, no CUDA call; exported for tests and tooling):
+ * params_out[6] = positions per thread, diagonals per band, threads per CTA, CTAs per cluster, positions per CTA,
+ * number of units; units_out (may be NULL) receives 8 ints per unit: band of the long piece, its first position, band
+ * of the short piece (-1: none), local position where it starts, cluster ranks the long band spans, 0, 0, 0.
+ * Returns the number of units (0: N is served by the fallback kernel) or a negative qf_status. */
+int qf_poisson_plan(int N, int *params_out, int *units_out, int cap);
+
 /* W = Delta_N P        — replaces quflow.laplacian.cpu.laplace (cpu.py:628-669, kernel
  * `_dot_cpu_generic` :98-108), dense branch, general (not necessarily skew-Hermitian) P. */
 int qf_laplace(qf_handle_t h, const void *P_dev, void *W_dev, void *stream);

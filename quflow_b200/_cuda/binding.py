@@ -59,6 +59,7 @@ SYMBOLS = {
     "qf_create": (_i, [_i, _i, _i, ctypes.POINTER(_vp)]),
     "qf_destroy": (_i, [_vp]),
     "qf_solve_poisson": (_i, [_vp, _vp, _vp, _vp]),
+    "qf_poisson_plan": (_i, [_i, ctypes.POINTER(_i), ctypes.POINTER(_i), _i]),
     "qf_laplace": (_i, [_vp, _vp, _vp, _vp]),
     "qf_norm_inf": (_i, [_vp, _vp, ctypes.POINTER(_d), _vp]),
     "qf_inner": (_i, [_vp, _vp, _vp, ctypes.POINTER(_d), _vp]),
@@ -118,6 +119,21 @@ def library():
 def _check(rc):
     if rc != QF_OK:
         raise QfError(rc, library().qf_last_error().decode())
+
+
+def poisson_plan(N: int):
+    """Work plan of the Poisson kernel (host code only): (params dict, units array (n, 8)) or None for the fallback."""
+    lib = library()
+    params = (ctypes.c_int * 6)()
+    n = lib.qf_poisson_plan(int(N), params, None, 0)
+    if n < 0:
+        raise QfError(n, lib.qf_last_error().decode())
+    if n == 0:
+        return None
+    units = (ctypes.c_int * (8 * n))()
+    lib.qf_poisson_plan(int(N), params, units, 8 * n)
+    keys = ("L", "M", "NT", "CL", "PC", "nunits")
+    return dict(zip(keys, params[:])), np.array(units[:], dtype=np.int32).reshape(n, 8)
 
 
 def device_count() -> int:

@@ -18,6 +18,93 @@
 #include "qf_common.cuh"
 
 // ---------------------------------------------------------------------------------------
+// host: the work plan of k_poisson_band (pure host code, also exported for the CPU tests: qf_poisson_plan)
+// ---------------------------------------------------------------------------------------
+// A band is M adjacent diagonals m = M b + s.  The triangle is cut into UNITS of PC positions x M diagonals, one per
+// CTA: a "long piece" (positions [posbase, posbase + PC) of band bL) followed, from local position PS on, by a whole
+// short band bS that fills the space the long piece leaves (diagonal lengths fall linearly, so band b and band
+// nbands - b together have about N positions: every CTA is full).  A band longer than PC spans the first `nlink`
+// CTAs of one thread-block cluster (cluster-aligned, consecutive ranks); the other CTAs of that cluster take
+// independent units.  Returns false when N needs more than 8 CTAs per band (no cluster that large).
+static bool qf_poisson_plan_host(int N, int &L, int &M, int &NT, int &CL, std::vector<int> &units)
+{
+    // Measured at N = 2048: 16 positions per thread, 4 diagonals per band and CTAs of up to 512
+    // threads are the fastest combination (8 positions: +13 us; 8 diagonals: +7 us; 256-thread cluster pairs: +3 us).
+    L = 16;
+    M = 4;
+    const int NTMAX = 512;
+    const int chunks = (N + L - 1) / L;
+    NT = NTMAX;
+    CL = 1;
+    if (M * chunks <= NTMAX) {
+        NT = ((M * chunks + 31) / 32) * 32;
+    } else {
+        const int need = (M * chunks + NTMAX - 1) / NTMAX;
+        while (CL < need) CL *= 2;
+    }
+    if (CL > 8) return false;
+    const int PC = (NT / M) * L;
+    const int nbands = (N + M - 1) / M;
+    std::vector<char> taken(nbands, 0);
+    units.clear();
+    auto filler = [&](int used) -> int {      // longest free band that fits into PC - used positions
+        const int room = PC - used;
+        if (room <= 0) return -1;
+        int b0 = (N - room + M - 1) / M;
+        if (b0 < 0) b0 = 0;
+        for (int bb = b0; bb < nbands; ++bb)
+            if (!taken[bb] && N - M * bb <= room) return bb;
+        return -1;
+    };
+    auto push_single = [&](int bb) {
+        taken[bb] = 1;
+        const int used = N - M * bb;
+        int bS = filler(used), PS = PC;
+        if (bS >= 0) { taken[bS] = 1; PS = used; }
+        units.insert(units.end(), {bb, 0, bS, PS, 1, 0, 0, 0});
+    };
+    for (int bb = 0; bb < nbands && N - M * bb > PC; ++bb) {          // clusters that hold a linked band
+        const int len = N - M * bb;
+        const int k = (len + PC - 1) / PC;
+        taken[bb] = 1;
+        for (int r = 0; r < k; ++r) {
+            int bS = -1, PS = PC;
+            if (r == k - 1) {
+                const int used = len - r * PC;
+                bS = filler(used);
+                if (bS >= 0) { taken[bS] = 1; PS = used; }
+            }
+            units.insert(units.end(), {bb, r * PC, bS, PS, k, 0, 0, 0});
+        }
+        for (int r = k; r < CL; ++r) {                                 // spare ranks: independent short bands
+            int nb = -1;
+            for (int q = nbands - 1; q >= 0; --q) if (!taken[q] && N - M * q <= PC) nb = q;   // longest free short band
+            if (nb >= 0) push_single(nb); else units.insert(units.end(), {-1, 0, -1, PC, 1, 0, 0, 0});
+        }
+    }
+    for (int bb = 0; bb < nbands; ++bb)                                // the rest: one band (+ filler) per CTA
+        if (!taken[bb]) push_single(bb);
+    while ((units.size() / 8) % CL) units.insert(units.end(), {-1, 0, -1, PC, 1, 0, 0, 0});
+    return true;
+}
+
+// params_out[6] = L, M, NT (threads per CTA), CL (CTAs per cluster), PC (positions per CTA), number of units;
+// units_out receives 8 ints per unit (bL, posbase, bS, PS, nlink, 0, 0, 0) if it has room for them (cap ints).
+// Returns the number of units, 0 if N is served by the fallback kernel, or a negative qf_status.  No CUDA call.
+extern "C" int qf_poisson_plan(int N, int *params_out, int *units_out, int cap)
+{
+    if (N < 2 || !params_out) { qf_set_error("qf_poisson_plan: bad arguments"); return QF_ERR_INVALID; }
+    int L, M, NT, CL;
+    std::vector<int> units;
+    if (!qf_poisson_plan_host(N, L, M, NT, CL, units)) return 0;
+    const int nunits = (int)(units.size() / 8);
+    const int p[6] = {L, M, NT, CL, (NT / M) * L, nunits};
+    memcpy(params_out, p, sizeof(p));
+    if (units_out && cap >= (int)units.size()) memcpy(units_out, units.data(), units.size() * sizeof(int));
+    return nunits;
+}
+
+// ---------------------------------------------------------------------------------------
 // host: coefficient / factor tables
 // ---------------------------------------------------------------------------------------
 int qf_build_tables(qf_handle_s *h)
@@ -56,69 +143,15 @@ int qf_build_tables(qf_handle_s *h)
         return QF_OK;
     };
 
-    // ---- unit-packed tables for k_poisson_band.  A band is M adjacent diagonals m = M b + s (M = 8: a row piece of
-    // a band is one 128-byte line).  The work is cut into UNITS of PC positions x M diagonals, one per CTA: a "long
-    // piece" (positions [posbase, posbase + PC) of band bL) followed, from local position PS on, by a whole short
-    // band bS that fills the space the long piece leaves (diagonal lengths fall linearly, so band b and band
-    // nbands - b together have about N positions: every CTA is full).  A band longer than PC spans the first
-    // `nlink` CTAs of one thread-block cluster; the other CTAs of that cluster take independent units.  The factor
-    // entries of a unit are contiguous and ordered [warp block][i][chunk in block][s]: the 32 lanes of a warp read
-    // 32 consecutive doubles for every i.  Entries outside the diagonals are 0 (which also decouples the pieces).
+    // ---- unit-packed tables for k_poisson_band (work plan: qf_poisson_plan_host above).  The factor entries of a unit
+    // are contiguous and ordered [warp block][i][chunk in block][s]: the 32 lanes of a warp read 32 consecutive doubles
+    // for every i.  Entries outside the diagonals are 0 (which also decouples the pieces of a unit).
     {
-        // Measured at N = 2048: 16 positions per thread, 4 diagonals per band and CTAs of up to 512
-        // threads are the fastest combination (8 positions: +13 us; 8 diagonals: +7 us; 256-thread cluster pairs: +3 us).
-        const int L = 16, M = 4, NTMAX = 512;
-        const int chunks = (N + L - 1) / L;
-        int NT = NTMAX, CL = 1;
-        if (M * chunks <= NTMAX) {
-            NT = ((M * chunks + 31) / 32) * 32;
-        } else {
-            const int need = (M * chunks + NTMAX - 1) / NTMAX;
-            while (CL < need) CL *= 2;
-        }
-        if (CL > 8) return upload_dense();   // N too large for one cluster: k_thomas path
-        const int PC = (NT / M) * L, WB = (32 / M) * L;
-        const int nbands = (N + M - 1) / M;
-        std::vector<char> taken(nbands, 0);
+        int L, M, NT, CL;
         std::vector<int> units;     // 8 ints per unit: bL, posbase, bS, PS, nlink, 0, 0, 0
-        auto filler = [&](int used) -> int {      // longest free band that fits into PC - used positions
-            const int room = PC - used;
-            if (room <= 0) return -1;
-            int b0 = (N - room + M - 1) / M;
-            if (b0 < 0) b0 = 0;
-            for (int bb = b0; bb < nbands; ++bb)
-                if (!taken[bb] && N - M * bb <= room) return bb;
-            return -1;
-        };
-        auto push_single = [&](int bb) {
-            taken[bb] = 1;
-            const int used = N - M * bb;
-            int bS = filler(used), PS = PC;
-            if (bS >= 0) { taken[bS] = 1; PS = used; }
-            units.insert(units.end(), {bb, 0, bS, PS, 1, 0, 0, 0});
-        };
-        for (int bb = 0; bb < nbands && N - M * bb > PC; ++bb) {          // clusters that hold a linked band
-            const int len = N - M * bb;
-            const int k = (len + PC - 1) / PC;
-            taken[bb] = 1;
-            for (int r = 0; r < k; ++r) {
-                int bS = -1, PS = PC;
-                if (r == k - 1) {
-                    const int used = len - r * PC;
-                    bS = filler(used);
-                    if (bS >= 0) { taken[bS] = 1; PS = used; }
-                }
-                units.insert(units.end(), {bb, r * PC, bS, PS, k, 0, 0, 0});
-            }
-            for (int r = k; r < CL; ++r) {                                 // spare ranks: independent short bands
-                int nb = -1;
-                for (int q = nbands - 1; q >= 0; --q) if (!taken[q] && N - M * q <= PC) nb = q;   // longest free short band
-                if (nb >= 0) push_single(nb); else units.insert(units.end(), {-1, 0, -1, PC, 1, 0, 0, 0});
-            }
-        }
-        for (int bb = 0; bb < nbands; ++bb)                                // the rest: one band (+ filler) per CTA
-            if (!taken[bb]) push_single(bb);
-        while ((units.size() / 8) % CL) units.insert(units.end(), {-1, 0, -1, PC, 1, 0, 0, 0});
+        if (!qf_poisson_plan_host(N, L, M, NT, CL, units)) return upload_dense();   // N too large for one cluster: k_thomas path
+        const int NTMAX = 512;
+        const int PC = (NT / M) * L, WB = (32 / M) * L;
         const size_t nunits = units.size() / 8;
         const size_t total = nunits * (size_t)PC * M;
         if (total >= (1ull << 31)) return upload_dense();
