@@ -80,7 +80,6 @@ extern "C" int qf_create(int N, int batch, int device, qf_handle_t *out)
     const size_t rp = sizeof(double) * (size_t)batch * 2 * h->nslots * N;
     QF_CUDA(cudaMalloc(&h->rowpart, rp));
     QF_CUDA(cudaMemset(h->rowpart, 0, rp));
-    QF_CUDA(cudaMalloc(&h->trbuf, sizeof(double2) * batch));
     QF_CUDA(cudaMalloc(&h->ctrl, sizeof(QfCtrl) * batch));
     QF_CUDA(cudaMemset(h->ctrl, 0, sizeof(QfCtrl) * batch));
     QF_CUDA(cudaMallocHost(&h->ctrl_host, sizeof(QfCtrl) * batch));
@@ -97,8 +96,8 @@ extern "C" int qf_destroy(qf_handle_t h)
     qf_gemm_destroy(h);
     qf_comm_destroy(h);
     qf_p2p_destroy(h);
-    void *ptrs[] = {h->tab_w, h->tab_iu, h->tab_o, h->ptab_w, h->ptab_iu, h->ptab_units, h->dW, h->Wh, h->P, h->A, h->S, h->scratch, h->kahan_c,
-                    h->io, h->io2, h->rowpart, h->trbuf, h->inner_part, h->ctrl, h->iters_dev};
+    void *ptrs[] = {h->ptab_w, h->ptab_iu, h->ptab_units, h->dW, h->Wh, h->P, h->A, h->S, h->scratch, h->kahan_c,
+                    h->io, h->io2, h->rowpart, h->inner_part, h->ctrl, h->iters_dev};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);

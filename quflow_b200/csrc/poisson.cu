@@ -111,7 +111,7 @@ int qf_build_tables(qf_handle_s *h)
 {
     const int N = h->N;
     const size_t n2 = (size_t)N * N;
-    std::vector<double> tw(n2, 0.0), tiu(n2, 0.0), to(n2, 0.0);
+    std::vector<double> tw(n2, 0.0), tiu(n2, 0.0);
     const double dN = (double)N;
     for (int m = 0; m < N; ++m) {
         double u_prev = 0.0;
@@ -128,33 +128,24 @@ int qf_build_tables(qf_handle_s *h)
             }
             tw[idx] = w;
             tiu[idx] = 1.0 / u;
-            to[idx] = o;
             u_prev = u;
         }
     }
-    // dense [k][k+m] tables: only the one-thread-per-diagonal fallback (very large N) reads them
-    auto upload_dense = [&]() -> int {
-        QF_CUDA(cudaMalloc(&h->tab_w, n2 * sizeof(double)));
-        QF_CUDA(cudaMalloc(&h->tab_iu, n2 * sizeof(double)));
-        QF_CUDA(cudaMalloc(&h->tab_o, n2 * sizeof(double)));
-        QF_CUDA(cudaMemcpy(h->tab_w, tw.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
-        QF_CUDA(cudaMemcpy(h->tab_iu, tiu.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
-        QF_CUDA(cudaMemcpy(h->tab_o, to.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
-        return QF_OK;
-    };
-
     // ---- unit-packed tables for k_poisson_band (work plan: qf_poisson_plan_host above).  The factor entries of a unit
     // are contiguous and ordered [warp block][i][chunk in block][s]: the 32 lanes of a warp read 32 consecutive doubles
     // for every i.  Entries outside the diagonals are 0 (which also decouples the pieces of a unit).
     {
         int L, M, NT, CL;
         std::vector<int> units;     // 8 ints per unit: bL, posbase, bS, PS, nlink, 0, 0, 0
-        if (!qf_poisson_plan_host(N, L, M, NT, CL, units)) return upload_dense();   // N too large for one cluster: k_thomas path
+        if (!qf_poisson_plan_host(N, L, M, NT, CL, units)) {
+            qf_set_error("N=%d needs more than 8 CTAs per band of diagonals: not supported", N);
+            return QF_ERR_UNSUPPORTED;
+        }
         const int NTMAX = 512;
         const int PC = (NT / M) * L, WB = (32 / M) * L;
         const size_t nunits = units.size() / 8;
         const size_t total = nunits * (size_t)PC * M;
-        if (total >= (1ull << 31)) return upload_dense();
+        if (total >= (1ull << 31)) { qf_set_error("factor tables of N=%d exceed 2^31 entries", N); return QF_ERR_UNSUPPORTED; }
         const int CPW = 32 / M;
         std::vector<double> pw(total, 0.0), piu(total, 0.0);
         for (size_t u = 0; u < nunits; ++u) {
@@ -194,7 +185,7 @@ int qf_build_tables(qf_handle_s *h)
 }
 
 // ---------------------------------------------------------------------------------------
-// fallback kernels for N beyond one cluster's reach (one thread per diagonal, row-coalesced) and helpers
+// helpers
 // ---------------------------------------------------------------------------------------
 // Wh = W + dW over the full matrix (GEMM 1 needs all of W~), fused with the trace of W~.
 __global__ void k_whalf(const double2 *__restrict__ W, const double2 *__restrict__ dW, double2 *__restrict__ Wh,
@@ -207,112 +198,6 @@ __global__ void k_whalf(const double2 *__restrict__ W, const double2 *__restrict
         double2 w = W[off + i];
         if (dW) w = zadd(w, dW[off + i]);
         Wh[off + i] = w;
-    }
-}
-
-// mean of the diagonal of Wh -> ctrl[b].trW (complex kept in trW / trW_im)
-__global__ void k_trace(const double2 *__restrict__ Wh, int N, QfCtrl *ctrl, double2 *trbuf, int gated)
-{
-    const int b = blockIdx.x;
-    if (gated && !ctrl[b].active) return;
-    __shared__ double sre[32], sim[32];
-    const double2 *M = Wh + (size_t)b * N * N;
-    double re = 0.0, im = 0.0;
-    for (int k = threadIdx.x; k < N; k += blockDim.x) {
-        double2 v = M[(size_t)k * N + k];
-        re += v.x;
-        im += v.y;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        re += __shfl_xor_sync(0xffffffffu, re, o);
-        im += __shfl_xor_sync(0xffffffffu, im, o);
-    }
-    if ((threadIdx.x & 31) == 0) { sre[threadIdx.x >> 5] = re; sim[threadIdx.x >> 5] = im; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double r = 0.0, i = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { r += sre[w]; i += sim[w]; }
-        trbuf[b] = make_double2(r / N, i / N);
-    }
-}
-
-__global__ void k_thomas(const double2 *__restrict__ Wh, double2 *__restrict__ P, double2 *__restrict__ scratch,
-                         const double *__restrict__ tw, const double *__restrict__ tiu, const double *__restrict__ to,
-                         int N, double eps, const QfCtrl *__restrict__ ctrl, const double2 *__restrict__ trbuf, int gated)
-{
-    const int b = blockIdx.y;
-    if (gated && !ctrl[b].active) return;
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= N) return;
-    const size_t off = (size_t)b * N * N;
-    const double2 *R = Wh + off;
-    double2 *X = P + off;
-    double2 *C = scratch + off;
-    const int n = N - m;
-    double2 tr = make_double2(0.0, 0.0);
-    if (m == 0) tr = trbuf[b];
-    // forward sweep  c_k = r_k - w_k c_{k-1}
-    double2 c = make_double2(0.0, 0.0);
-#pragma unroll 4
-    for (int k = 0; k < n; ++k) {
-        const size_t idx = (size_t)k * N + (k + m);
-        double2 r = R[idx];
-        const double w = tw[idx];
-        r.x -= tr.x;
-        r.y -= tr.y;
-        c.x = r.x - w * c.x;
-        c.y = r.y - w * c.y;
-        C[idx] = c;
-    }
-    // backward sweep  x_k = (c_k - o_{k+1} x_{k+1}) / u_k
-    double2 x = make_double2(0.0, 0.0);
-    double o_next = 0.0;
-#pragma unroll 4
-    for (int k = n - 1; k >= 0; --k) {
-        const size_t idx = (size_t)k * N + (k + m);
-        const double2 ck = C[idx];
-        const double iu = tiu[idx];
-        x.x = (ck.x - o_next * x.x) * iu;
-        x.y = (ck.y - o_next * x.y) * iu;
-        o_next = to[idx];
-        if (m == 0) {
-            X[idx] = x;   // unscaled: the trace of P is removed (and eps applied) by k_fix_trace
-        } else {
-            X[idx] = make_double2(eps * x.x, eps * x.y);
-            X[(size_t)(k + m) * N + k] = make_double2(-eps * x.x, eps * x.y);   // P[j,i] = -conj(P[i,j]), cpu.py:334,340
-        }
-    }
-}
-
-// P_kk <- eps * (P_kk - mean(diag P))   cpu.py:342-352 followed by isospectral.py:492
-__global__ void k_fix_trace(double2 *P, int N, double eps, const QfCtrl *__restrict__ ctrl, int gated)
-{
-    const int b = blockIdx.x;
-    if (gated && !ctrl[b].active) return;
-    __shared__ double sre[32], sim[32];
-    __shared__ double2 mean;
-    double2 *M = P + (size_t)b * N * N;
-    double re = 0.0, im = 0.0;
-    for (int k = threadIdx.x; k < N; k += blockDim.x) {
-        double2 v = M[(size_t)k * N + k];
-        re += v.x;
-        im += v.y;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        re += __shfl_xor_sync(0xffffffffu, re, o);
-        im += __shfl_xor_sync(0xffffffffu, im, o);
-    }
-    if ((threadIdx.x & 31) == 0) { sre[threadIdx.x >> 5] = re; sim[threadIdx.x >> 5] = im; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double r = 0.0, i = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { r += sre[w]; i += sim[w]; }
-        mean = make_double2(r / N, i / N);
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < N; k += blockDim.x) {
-        double2 v = M[(size_t)k * N + k];
-        M[(size_t)k * N + k] = make_double2(eps * (v.x - mean.x), eps * (v.y - mean.y));
     }
 }
 
@@ -903,7 +788,7 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
         const double *a2 = h->ptab_w, *a3 = h->ptab_iu;
         const int4 *a4 = reinterpret_cast<const int4 *>(h->ptab_units);
         int a5 = N, a6 = h->p_nunits;
-        // L2 prefetch distance = units resident at once: 2 CTAs per SM, a multiple of the cluster size
+        // L2 prefetch distance = units resident at once (one 512-thread CTA per SM), a multiple of the cluster size
         int a7 = pf ? (pf > 1 ? pf : (512 / h->p_NTMAX) * h->sm_count) / CL * CL : 0;
         double a8 = eps;
         const QfCtrl *a9 = h->ctrl;
@@ -912,12 +797,8 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
         QF_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
         h->launches++;
     } else {
-        // large-N fallback: one thread per diagonal
-        k_trace<<<nmem, 256, 0, st>>>(Wh, N, h->ctrl, h->trbuf, g);
-        dim3 gt((N + 63) / 64, nmem);
-        k_thomas<<<gt, 64, 0, st>>>(Wh, P, h->scratch, h->tab_w, h->tab_iu, h->tab_o, N, eps, h->ctrl, h->trbuf, g);
-        k_fix_trace<<<nmem, 256, 0, st>>>(P, N, eps, h->ctrl, g);
-        h->launches += 3;
+        qf_set_error("qf_launch_poisson: no work plan for N=%d", N);
+        return QF_ERR_UNSUPPORTED;
     }
     QF_CUDA(cudaGetLastError());
     return QF_OK;

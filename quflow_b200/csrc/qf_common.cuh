@@ -65,12 +65,7 @@ struct qf_handle_s {
     int device = 0;
     int sm_count = 148;
     size_t mat_elems = 0;      // N*N
-    // Poisson factors, all (N, N) float64 in matrix layout [k][k+m] (upper triangle used)
-    double *tab_w = nullptr;   // w_k   = o_k / u_{k-1}          (0 at k = 0)
-    double *tab_iu = nullptr;  // 1/u_k,  u_k = d_k - w_k o_k
-    double *tab_o = nullptr;   // o_k   (coupling to position k-1; quflow lap[...,1])
-    double *tab_d = nullptr;   // d_k   (quflow lap[...,0], bc=False) — for laplace()
-    // band-packed factor tables of the clustered band kernel (poisson.cu: k_poisson_band)
+    // unit-packed LDL^T factors of the Hoppe-Yau tridiagonal systems: w_k = o_k / u_{k-1}, 1/u_k (poisson.cu)
     double *ptab_w = nullptr, *ptab_iu = nullptr;
     int *ptab_units = nullptr;      // [nunits][8] = bL, posbase, bS, PS, nlink, 0, 0, 0 (poisson.cu: qf_build_tables)
     int p_L = 0;                    // positions per thread (0: band kernel not available for this N)
@@ -87,7 +82,6 @@ struct qf_handle_s {
     double2 *io2 = nullptr;
     // residual partial row sums: [batch][2][nslots][N]
     double *rowpart = nullptr;
-    double2 *trbuf = nullptr;     // [batch] mean of diag(W~)
     double *inner_part = nullptr; // qf_inner partial sums, lazily allocated
     int nslots = 0;
     QfCtrl *ctrl = nullptr;       // [batch] device
