@@ -23,9 +23,9 @@
 // A band is M adjacent diagonals m = M b + s.  The triangle is cut into UNITS of PC positions x M diagonals, one per
 // CTA: a "long piece" (positions [posbase, posbase + PC) of band bL) followed, from local position PS on, by a whole
 // short band bS that fills the space the long piece leaves (diagonal lengths fall linearly, so band b and band
-// nbands - b together have about N positions: every CTA is full).  A band longer than PC spans the first `nlink`
-// CTAs of one thread-block cluster (cluster-aligned, consecutive ranks); the other CTAs of that cluster take
-// independent units.  Returns false when N needs more than 8 CTAs per band (no cluster that large).
+// nbands - b together have about N positions: every CTA is full).  A band longer than PC spans `nlink` consecutive
+// ranks of one thread-block cluster, starting at rank `rank0`; several such groups and independent units share a
+// cluster.  Returns false when N needs more than 8 CTAs per band (no cluster that large).
 static bool qf_poisson_plan_host(int N, int &L, int &M, int &NT, int &CL, std::vector<int> &units)
 {
     // Measured at N = 2048: 16 positions per thread, 4 diagonals per band and CTAs of up to 512
@@ -63,20 +63,37 @@ static bool qf_poisson_plan_host(int N, int &L, int &M, int &NT, int &CL, std::v
         if (bS >= 0) { taken[bS] = 1; PS = used; }
         units.insert(units.end(), {bb, 0, bS, PS, 1, 0, 0, 0});
     };
-    for (int bb = 0; bb < nbands && N - M * bb > PC; ++bb) {          // clusters that hold a linked band
-        const int len = N - M * bb;
-        const int k = (len + PC - 1) / PC;
+    // Linked bands (longer than PC) take k = ceil(len / PC) consecutive ranks of a cluster; several of them share a
+    // cluster when they fit (largest first, then the largest that still fits), the remaining ranks take single bands.
+    std::vector<int> linked_bands;
+    for (int bb = 0; bb < nbands && N - M * bb > PC; ++bb) {
+        linked_bands.push_back(bb);
         taken[bb] = 1;
-        for (int r = 0; r < k; ++r) {
-            int bS = -1, PS = PC;
-            if (r == k - 1) {
-                const int used = len - r * PC;
-                bS = filler(used);
-                if (bS >= 0) { taken[bS] = 1; PS = used; }
+    }
+    std::vector<char> placed(linked_bands.size(), 0);
+    for (size_t g0 = 0; g0 < linked_bands.size(); ++g0) {
+        if (placed[g0]) continue;
+        int room = CL;
+        for (size_t g = g0; g < linked_bands.size() && room >= 2; ++g) {
+            if (placed[g]) continue;
+            const int bb = linked_bands[g];
+            const int len = N - M * bb;
+            const int k = (len + PC - 1) / PC;
+            if (k > room) continue;
+            placed[g] = 1;
+            const int rank0 = CL - room;
+            for (int r = 0; r < k; ++r) {
+                int bS = -1, PS = PC;
+                if (r == k - 1) {
+                    const int used = len - r * PC;
+                    bS = filler(used);
+                    if (bS >= 0) { taken[bS] = 1; PS = used; }
+                }
+                units.insert(units.end(), {bb, r * PC, bS, PS, k, rank0, 0, 0});
             }
-            units.insert(units.end(), {bb, r * PC, bS, PS, k, 0, 0, 0});
+            room -= k;
         }
-        for (int r = k; r < CL; ++r) {                                 // spare ranks: independent short bands
+        for (; room > 0; --room) {                                     // spare ranks: independent short bands
             int nb = -1;
             for (int q = nbands - 1; q >= 0; --q) if (!taken[q] && N - M * q <= PC) nb = q;   // longest free short band
             if (nb >= 0) push_single(nb); else units.insert(units.end(), {-1, 0, -1, PC, 1, 0, 0, 0});
@@ -89,7 +106,7 @@ static bool qf_poisson_plan_host(int N, int &L, int &M, int &NT, int &CL, std::v
 }
 
 // params_out[6] = L, M, NT (threads per CTA), CL (CTAs per cluster), PC (positions per CTA), number of units;
-// units_out receives 8 ints per unit (bL, posbase, bS, PS, nlink, 0, 0, 0) if it has room for them (cap ints).
+// units_out receives 8 ints per unit (bL, posbase, bS, PS, nlink, rank0, 0, 0) if it has room for them (cap ints).
 // Returns the number of units, 0 if N is served by the fallback kernel, or a negative qf_status.  No CUDA call.
 extern "C" int qf_poisson_plan(int N, int *params_out, int *units_out, int cap)
 {
@@ -136,7 +153,7 @@ int qf_build_tables(qf_handle_s *h)
     // for every i.  Entries outside the diagonals are 0 (which also decouples the pieces of a unit).
     {
         int L, M, NT, CL;
-        std::vector<int> units;     // 8 ints per unit: bL, posbase, bS, PS, nlink, 0, 0, 0
+        std::vector<int> units;     // 8 ints per unit: bL, posbase, bS, PS, nlink, rank0, 0, 0
         if (!qf_poisson_plan_host(N, L, M, NT, CL, units)) {
             qf_set_error("N=%d needs more than 8 CTAs per band of diagonals: not supported", N);
             return QF_ERR_UNSUPPORTED;
@@ -296,8 +313,11 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
     const int rank = (CL > 1) ? unit % CL : 0;   // cluster dims are (CL, 1, 1): this is %cluster_ctarank
     const int4 ud = __ldg(units + 2 * unit);
     const int bL = ud.x, posbase = ud.y, bS = ud.z, PS = ud.w;
-    const int nlink = (CL > 1) ? __ldg(reinterpret_cast<const int *>(units + 2 * unit + 1)) : 1;
-    const bool linked = (CL > 1) && nlink > 1;   // this CTA holds part of a band that spans ranks 0 .. nlink-1
+    const int4 ue = (CL > 1) ? __ldg(units + 2 * unit + 1) : make_int4(1, 0, 0, 0);
+    const int nlink = ue.x;                      // ranks of the cluster that share this CTA's long band ...
+    const int rank0 = ue.y;                      // ... starting at this cluster rank
+    const int grank = rank - rank0;              // this CTA's place among them
+    const bool linked = (CL > 1) && nlink > 1;
     const bool diag0 = (bL == 0);                // the band of the main diagonal (all its ranks see bL == 0)
 
     __shared__ double totA[NTMAX / 32][M], totBx[NTMAX / 32][M], totBy[NTMAX / 32][M];
@@ -311,7 +331,7 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
 
     if (CL > 1) {
         if (tid == 0) {
-            const uint32_t nF = linked ? rank * M * 24 : 0, nB = linked ? (nlink - 1 - rank) * M * 24 : 0;
+            const uint32_t nF = linked ? grank * M * 24 : 0, nB = linked ? (nlink - 1 - grank) * M * 24 : 0;
             const uint32_t nS = (linked && diag0) ? (nlink - 1) * 16 : 0;
             const uint32_t tx[4] = {nF, nB, nS, nS};
             for (int q = 0; q < 4; ++q) {
@@ -384,7 +404,7 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
         if (plo + L < PC) {
             const int cn = c + 1;
             w[L] = __ldg(tw + (size_t)unit * PC * M + (size_t)(cn / CPW) * (WB * M) + (cn % CPW) * M + s);
-        } else if (linked && rank + 1 < nlink) {
+        } else if (linked && grank + 1 < nlink) {
             w[L] = __ldg(tw + (size_t)(unit + 1) * PC * M + s);
         }
     } else {
@@ -413,13 +433,13 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
         if (tid == 0) {
             double ax = 0.0, ay = 0.0;
             for (int q = 0; q < nwarps; ++q) { ax += redx[q]; ay += redy[q]; }
-            sumR[rank][0] = ax;
-            sumR[rank][1] = ay;
+            sumR[grank][0] = ax;
+            sumR[grank][1] = ay;
             if (linked) {
                 for (int d = 0; d < nlink; ++d) {
-                    if (d == rank) continue;
-                    pb_send(&sumR[rank][0], &mbar[2], d, ax);
-                    pb_send(&sumR[rank][1], &mbar[2], d, ay);
+                    if (d == grank) continue;
+                    pb_send(&sumR[grank][0], &mbar[2], rank0 + d, ax);
+                    pb_send(&sumR[grank][1], &mbar[2], rank0 + d, ay);
                 }
             }
         }
@@ -474,7 +494,7 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
     __syncthreads();
     PT(3);
     if (linked) {
-        if (tid < M && rank + 1 < nlink) {         // the map of this CTA's whole part of diagonal s -> higher ranks
+        if (tid < M && grank + 1 < nlink) {        // the map of this CTA's whole part of diagonal s -> higher ranks
             double tA = 1.0, tBx = 0.0, tBy = 0.0;
             for (int q = 0; q < nwarps; ++q) {
                 const double a = totA[q][s];
@@ -482,20 +502,20 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
                 tBy = a * tBy + totBy[q][s];
                 tA = a * tA;
             }
-            for (int d = rank + 1; d < nlink; ++d) {
-                pb_send(&xchF[rank][s][0], &mbar[0], d, tA);
-                pb_send(&xchF[rank][s][1], &mbar[0], d, tBx);
-                pb_send(&xchF[rank][s][2], &mbar[0], d, tBy);
+            for (int d = grank + 1; d < nlink; ++d) {
+                pb_send(&xchF[grank][s][0], &mbar[0], rank0 + d, tA);
+                pb_send(&xchF[grank][s][1], &mbar[0], rank0 + d, tBx);
+                pb_send(&xchF[grank][s][2], &mbar[0], rank0 + d, tBy);
             }
         }
-        if (rank > 0) pb_mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar[0]));
+        if (grank > 0) pb_mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar[0]));
     }
     PT(4);
     double2 carry;
     {
         double pBx = 0.0, pBy = 0.0;
         if (linked) {
-            for (int d = 0; d < rank; ++d) {
+            for (int d = 0; d < grank; ++d) {
                 const double a = xchF[d][s][0];
                 pBx = a * pBx + xchF[d][s][1];
                 pBy = a * pBy + xchF[d][s][2];
@@ -557,7 +577,7 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
     __syncthreads();
     PT(8);
     if (linked) {
-        if (tid < M && rank > 0) {                 // -> lower ranks
+        if (tid < M && grank > 0) {                // -> lower ranks
             double tA = 1.0, tBx = 0.0, tBy = 0.0;
             for (int q = nwarps - 1; q >= 0; --q) {
                 const double a = totA[q][s];
@@ -565,19 +585,19 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
                 tBy = a * tBy + totBy[q][s];
                 tA = a * tA;
             }
-            for (int d = 0; d < rank; ++d) {
-                pb_send(&xchB[rank][s][0], &mbar[1], d, tA);
-                pb_send(&xchB[rank][s][1], &mbar[1], d, tBx);
-                pb_send(&xchB[rank][s][2], &mbar[1], d, tBy);
+            for (int d = 0; d < grank; ++d) {
+                pb_send(&xchB[grank][s][0], &mbar[1], rank0 + d, tA);
+                pb_send(&xchB[grank][s][1], &mbar[1], rank0 + d, tBx);
+                pb_send(&xchB[grank][s][2], &mbar[1], rank0 + d, tBy);
             }
         }
-        if (rank + 1 < nlink) pb_mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar[1]));
+        if (grank + 1 < nlink) pb_mbar_wait((uint32_t)__cvta_generic_to_shared(&mbar[1]));
     }
     PT(9);
     {
         double pBx = 0.0, pBy = 0.0;
         if (linked) {
-            for (int d = nlink - 1; d > rank; --d) {
+            for (int d = nlink - 1; d > grank; --d) {
                 const double a = xchB[d][s][0];
                 pBx = a * pBx + xchB[d][s][1];
                 pBy = a * pBy + xchB[d][s][2];
@@ -618,13 +638,13 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
         if (tid == 0) {
             double ax = 0.0, ay = 0.0;
             for (int q = 0; q < nwarps; ++q) { ax += redx[q]; ay += redy[q]; }
-            sumX[rank][0] = ax;
-            sumX[rank][1] = ay;
+            sumX[grank][0] = ax;
+            sumX[grank][1] = ay;
             if (linked) {
                 for (int d = 0; d < nlink; ++d) {
-                    if (d == rank) continue;
-                    pb_send(&sumX[rank][0], &mbar[3], d, ax);
-                    pb_send(&sumX[rank][1], &mbar[3], d, ay);
+                    if (d == grank) continue;
+                    pb_send(&sumX[grank][0], &mbar[3], rank0 + d, ax);
+                    pb_send(&sumX[grank][1], &mbar[3], rank0 + d, ay);
                 }
             }
         }

@@ -106,7 +106,7 @@ def test_poisson_work_plan_covers_the_triangle_exactly_once(N):
     nbands = (N + M - 1) // M
     covered = np.zeros(nbands, dtype=np.int64)           # positions of slot 0 covered per band
     seen_long = {}
-    for u, (bL, posbase, bS, PS, nlink, *_rest) in enumerate(units):
+    for u, (bL, posbase, bS, PS, nlink, rank0, *_rest) in enumerate(units):
         rank = u % CL
         assert 0 <= PS <= PC
         if bL >= 0:
@@ -114,9 +114,10 @@ def test_poisson_work_plan_covers_the_triangle_exactly_once(N):
             piece = min(PC, lenL - posbase)
             assert piece > 0 and posbase % PC == 0 and piece <= PS
             covered[bL] += piece
-            if nlink > 1:                                # linked band: rank r holds positions [r PC, (r+1) PC)
-                assert posbase == rank * PC and rank < nlink and nlink == -(-lenL // PC) <= CL
-                seen_long.setdefault(bL, []).append((u, rank))
+            if nlink > 1:                                # linked band: group rank g holds positions [g PC, (g+1) PC)
+                g = rank - rank0
+                assert 0 <= g < nlink and posbase == g * PC and rank0 + nlink <= CL and nlink == -(-lenL // PC)
+                seen_long.setdefault(bL, []).append((u, g))
             else:
                 assert posbase == 0 and lenL <= PC
         if bS >= 0:
@@ -125,12 +126,13 @@ def test_poisson_work_plan_covers_the_triangle_exactly_once(N):
             covered[bS] += lenS
     for b in range(nbands):
         assert covered[b] == N - M * b, f"band {b} of N={N}"
-    for b, lst in seen_long.items():                     # consecutive units, ranks 0..k-1, cluster-aligned
+    for b, lst in seen_long.items():                     # consecutive units of ONE cluster, group ranks 0..k-1
         us = [u for u, _ in lst]
-        assert us == list(range(us[0], us[0] + len(us))) and us[0] % CL == 0 and [r for _, r in lst] == list(range(len(lst)))
+        assert us == list(range(us[0], us[0] + len(us))) and us[0] // CL == us[-1] // CL
+        assert [g for _, g in lst] == list(range(len(lst)))
     if N >= 512 and N % 64 == 0:
         used = sum(N - M * b for b in range(nbands))
-        # the folding keeps the CTAs full; beyond N = 4096 (clusters of 4 and 8) bands that need 2 or 3 ranks leave
-        # spare ranks that only partly find short bands to take: correct, but a known inefficiency
-        assert used / (n * PC) > (0.9 if CL <= 2 else 0.5)
+        # the folding and the group packing keep the CTAs full; beyond N = 4096 there are too few short bands to fill
+        # the last rank of every long band (on average half empty): 79-89 % there
+        assert used / (n * PC) > (0.9 if CL <= 2 else 0.75)
     assert binding.poisson_plan(20000) is None           # beyond 8 CTAs per band: fallback kernel
