@@ -37,7 +37,9 @@ def test_solve_poisson_golden(qf, name, N):
     assert abs(np.trace(P)) < 1e-12
 
 
-@pytest.mark.parametrize("N", [2, 3, 5, 16, 31, 32, 33, 64, 127, 128, 129, 200, 257, 512])
+# 2050 / 3000: bands longer than one CTA -> thread-block clusters of 2 with DSMEM carry exchange; 5000: clusters of 4 that
+# hold several linked groups
+@pytest.mark.parametrize("N", [2, 3, 5, 16, 31, 32, 33, 64, 127, 128, 129, 200, 257, 512, 1100, 2048, 2050, 3000, 5000])
 def test_solve_poisson_vs_oracle(qf, N):
     W = oracle.random_skewherm(N, seed=N)
     P = qf.solve_poisson(W)
