@@ -320,10 +320,10 @@ def gpu_arm(args):
         "metric": "isomp steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
-        "config": dict(workload_config(N, mode, kw, its),
-                       parallelism=("single GPU" if world == 1 else
-                                    f"{world} GPUs: GEMMs sharded by row blocks, state replicated, {handle.comm_mode()} "
-                                    f"all-gather over NVLink peer memory (DESIGN.md section 4)")),
+        "config": workload_config(N, mode, kw, its),
+        "parallelism": ("single GPU" if world == 1 else
+                        f"{world} GPUs: GEMMs sharded by row blocks, state replicated, {handle.comm_mode()} "
+                        f"all-gather over NVLink peer memory (DESIGN.md section 4)"),
         "iterations_per_sec": value * its,
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": 16 * N * N, "d2h_bytes_per_step": 16 * N * N,
