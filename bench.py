@@ -10,7 +10,9 @@ A "step" is one isospectral-midpoint time step.
 
 * ``value``  : steps/s with W resident in HBM, timed with CUDA events over exactly K steps (max over ranks).
 * ``e2e``    : the same metric through the public Python API with HOST buffers (numpy in pinned memory): every step
-               is one ``qf.isomp(W_host, dt, steps=1)`` call = H2D copy of W + one step + D2H copy of W.
+               is one ``qf.isomp(W_host, dt, steps=1)`` call = H2D copy of W + one step + D2H copy of W.  On several
+               GPUs the same host-buffer call goes to the row-sharded handle: every rank copies the replicated state
+               in over its own PCIe link, the step runs sharded, every rank reads the result back.
 * ``roofline``: the dominant kernel (k_zgemm3m_ws, FP64 DMMA) — EXECUTED flops per launch / CUDA-event launch time,
                against the FP64 tensor peak measured on this pool (MEASURED_PEAKS.json has no FP64 entry; see
                profiles/r01_fp64_pipes.txt).  ``roofline_poisson`` reports the HBM-bound Poisson solve against
