@@ -56,6 +56,50 @@ def test_isomp_config1_N128_1000_steps(qf):
     assert st["total_iterations"] / 1000 == float(g["mean_iterations"])
 
 
+def _casimirs_by_products(W):
+    """C_2, C_3, C_4 of H = iW from one matrix product (cheap at N = 2048): tr(H^2) = |H|_F^2, tr(H^3) = sum(H^2 o H^T),
+    tr(H^4) = |H^2|_F^2 for Hermitian H."""
+    H = 1j * W
+    H2 = H @ H
+    N = W.shape[-1]
+    return np.array([np.linalg.norm(H) ** 2, float(np.sum(H2 * H.T).real), np.linalg.norm(H2) ** 2]) / N
+
+
+def test_isomp_config3_N1024_100_steps_vs_oracle(qf):
+    """BASELINE config 3 size: R(1024, 42), 100 steps against the CPU oracle run live on the same input — the
+    north-star bar: relative Frobenius error <= 1e-10, identical per-step iteration counts."""
+    N = 1024
+    W0 = oracle.random_skewherm(N, 42)
+    dt = 0.25 * oracle.hbar(N)
+    W, st, iters = run_gpu(qf, W0, dt, 100)
+    rec = {}
+    Wref = oracle.isomp(W0.copy(), dt, 100, record=rec)
+    assert list(iters) == rec["iterations"]
+    assert relfro(W, Wref) < TOL_100_STEPS
+    assert np.abs(W + W.conj().T).max() == 0.0
+
+
+def test_isomp_config4_N2048_properties(qf):
+    """BASELINE config 4 size: R(2048, 42).  The oracle needs ~0.7 s per step here, so: 8 steps against the oracle
+    (<= 1e-10, same iteration counts), then size-independent properties over 40 steps — exact skew-Hermitian symmetry,
+    zero trace, Casimirs C_2..C_4 conserved to the fixed-point tolerance (the reference's own drift over 100 steps is
+    1e-12 ... 3e-10)."""
+    N = 2048
+    W0 = oracle.random_skewherm(N, 42)
+    dt = 0.25 * oracle.hbar(N)
+    W, st, iters = run_gpu(qf, W0, dt, 8)
+    rec = {}
+    Wref = oracle.isomp(W0.copy(), dt, 8, record=rec)
+    assert list(iters) == rec["iterations"]
+    assert relfro(W, Wref) < TOL_100_STEPS
+    W40, st40, it40 = run_gpu(qf, W0, dt, 40)
+    assert np.abs(W40 + W40.conj().T).max() == 0.0
+    assert abs(np.trace(W40)) < 1e-12 * np.linalg.norm(W40)
+    c0, c1 = _casimirs_by_products(W0), _casimirs_by_products(W40)
+    assert np.all(np.abs(c1 - c0) <= 1e-9 * np.abs(c0) + 1e-12)
+    assert 2 <= it40.mean() <= 4 and st40["number_of_maxit"] == 0
+
+
 def test_reference_golden_vector_head_semantics(qf):
     """The reference's N=16 golden W0 (trace != 0) at HEAD semantics: compare with the reference's HEAD output."""
     g = golden("ref_isomp_golden_N16.npz")
