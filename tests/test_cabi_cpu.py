@@ -77,6 +77,17 @@ def test_python_signatures_mirror_the_reference():
     assert qf.hbar(512) == 2.0 / np.sqrt(512.0 ** 2 - 1)             # geometry.py:7-9
 
 
+def test_logger_signatures_mirror_the_reference():
+    """quflow/geometry.py:53-76 and quflow/physics.py:9-38: same names and argument lists."""
+    import quflow_b200 as qf
+    sig = lambda f: inspect.getfullargspec(f).args   # noqa: E731
+    assert sig(qf.inner_L2) == ['P', 'W'] and sig(qf.norm_L2) == ['W']
+    assert sig(qf.energy_euler) == ['W'] and sig(qf.enstrophy) == ['W']
+    assert sig(qf.inner_Hm1) == ['W1', 'W2'] and sig(qf.norm_Hm1) == ['W']
+    assert sig(qf.inner_H1) == ['P1', 'P2'] and sig(qf.norm_H1) == ['P']
+    assert qf.physics.energy_euler is qf.energy_euler
+
+
 def test_argument_validation_happens_before_any_device_work():
     import quflow_b200 as qf
     W = np.zeros((8, 8), dtype=np.complex128)
