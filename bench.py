@@ -30,9 +30,71 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+def cpu_threads():
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    return n
+
+
+def _reference_arm_requested(argv):
+    return any(a == "--impl=reference" or (a == "--impl" and i + 1 < len(argv) and argv[i + 1] == "reference")
+               for i, a in enumerate(argv))
+
+
+if _reference_arm_requested(sys.argv):
+    # The CPU arm uses every host core.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, and the BLAS /
+    # OpenMP / numba pools read their sizes when the libraries load, so the counts are forced HERE, before numpy is imported.
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMBA_NUM_THREADS"):
+        os.environ[_v] = str(cpu_threads())
+
 import numpy as np  # noqa: E402
 
-FP64_TENSOR_PEAK_TFLOPS = 37.15   # measured DMMA m8n8k4 issue peak, 148 SMs @ 1965 MHz (profiles/r01_fp64_pipes.txt)
+FP64_TENSOR_PEAK_TFLOPS_R01 = 37.15   # round-1 measurement (profiles/r01_fp64_pipes.txt); bench.py now measures it live
+
+
+def incumbents(N, dev):
+    """The library kernels the reference's own GPU prototype calls for this path (quflow/experimental/
+    isospectral_cuda.py: cuBLASLt ZGEMM; quflow/experimental/cuda.py:123-166: cusparseDgtsv2StridedBatch), timed on the
+    same GPU in the same run.  Comparators only: nothing here is on the product path."""
+    import re
+    import torch
+    out = {}
+    try:
+        A = torch.randn(N, N, dtype=torch.complex128, device=dev)
+        B = torch.randn(N, N, dtype=torch.complex128, device=dev)
+        C = torch.empty_like(A)
+        for _ in range(2):
+            torch.matmul(A, B, out=C)
+        best = 1e30
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(5):
+            e0.record()
+            torch.matmul(A, B, out=C)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out["cublas_zgemm_ms"] = best
+        out["cublas_zgemm_tflops_8n3"] = 8.0 * N ** 3 / (best * 1e-3) / 1e12
+        del A, B, C
+    except Exception as e:
+        out["cublas_zgemm_error"] = str(e)[:200]
+    exe = os.path.join(ROOT, "tools", "microbench", "cusparse_gtsv_ref")
+    if os.path.exists(exe):
+        try:
+            txt = subprocess.run([exe, str(N)], capture_output=True, text=True, timeout=120).stdout
+            m = re.search(r"N=%d .*?: ([0-9.]+) us" % N, txt)
+            if m:
+                out["cusparse_gtsv2_strided_batch_x2_us"] = float(m.group(1))
+                out["cusparse_note"] = "two library solves (re, im) with the prototype's packing; its pack/unpack kernels not included"
+        except Exception as e:
+            out["cusparse_error"] = str(e)[:200]
+    else:
+        out["cusparse_error"] = "tools/microbench/cusparse_gtsv_ref not built"
+    return out
 
 
 def log(*a):
@@ -130,16 +192,71 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path, all host cores
 # ----------------------------------------------------------------------------------------------------
-def cpu_threads():
-    n = os.cpu_count() or 1
+def thread_report():
+    """Thread counts the CPU arm actually runs with (BLAS / OpenMP pools via threadpoolctl, numba's prange pool)."""
+    rep = {}
     try:
-        n = len(os.sched_getaffinity(0))
+        import threadpoolctl
+        for lib in threadpoolctl.threadpool_info():
+            rep[f"{lib.get('user_api')}:{lib.get('internal_api')}"] = lib.get("num_threads")
+    except Exception as e:       # pragma: no cover
+        rep["threadpoolctl"] = f"unavailable ({e})"
+    try:
+        import numba
+        rep["numba"] = numba.get_num_threads()
     except Exception:
         pass
-    return n
+    return rep
 
 
-def run_cpu_port(N, mode, steps, warmup):
+def force_cpu_threads(n):
+    """Run-time counterpart of the environment set-up at the top of this file (cpu_baseline leg of the GPU arm, where
+    numpy is already loaded): resize the BLAS/OpenMP pools through threadpoolctl and numba's pool."""
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+    except Exception:
+        pass
+    try:
+        import numba
+        numba.set_num_threads(min(n, numba.config.NUMBA_NUM_THREADS))
+    except Exception:
+        pass
+
+
+def run_cpu_reference(N, mode, steps, warmup, keep=None):
+    """Time the UNMODIFIED reference isomp_fixedpoint (numba Thomas solve + BLAS zgemm, quflow/integrators/
+    isospectral.py:338-613) staged under oracle/_ref by oracle/make_ref.py.  JIT compilation is excluded by one
+    throw-away step at N=64 (numba compiles per signature, not per size).  Returns None when it is not staged."""
+    from oracle import refshim, make_ref
+    if not (make_ref.staged() or refshim.available()):
+        return None
+    refshim.load()
+    from quflow.integrators.isospectral import isomp_fixedpoint
+    kw = mode_kwargs(mode, N)
+    isomp_fixedpoint(workload(64), 0.25 * hbar(64), steps=1)          # JIT warm-up
+    W = workload(N)
+    if warmup > 0:
+        W = isomp_fixedpoint(W, kw["dt"], steps=warmup, maxit=kw["maxit"], minit=kw["minit"])
+    stats = {'iterations': 0.0}
+    t0 = time.perf_counter()
+    W = isomp_fixedpoint(W, kw["dt"], steps=steps, maxit=kw["maxit"], minit=kw["minit"], stats=stats)
+    dt = time.perf_counter() - t0
+    if keep is not None:
+        keep["W"] = W
+    return steps / dt, dt, stats['iterations']
+
+
+def run_cpu(N, mode, steps, warmup, keep=None):
+    """(value, seconds, iterations/step, kind, description): the real reference when staged, else the oracle port.
+    `keep` (a dict) receives the final state, for the parity check of the GPU arm."""
+    r = run_cpu_reference(N, mode, steps, warmup, keep)
+    if r is not None:
+        return r + ("reference", "unmodified reference isomp_fixedpoint (numba prange Thomas solve + numpy BLAS zgemm) from oracle/_ref")
+    return run_cpu_port(N, mode, steps, warmup, keep) + ("port", "oracle port: numpy BLAS zgemm + OpenMP Thomas (oracle/)")
+
+
+def run_cpu_port(N, mode, steps, warmup, keep=None):
     """Time the CPU oracle (port of isospectral.py:338-613 + cpu.py:281-362) on `steps` steps."""
     import oracle
     kw = mode_kwargs(mode, N)
@@ -150,6 +267,8 @@ def run_cpu_port(N, mode, steps, warmup):
     t0 = time.perf_counter()
     oracle.isomp(W, kw["dt"], steps=steps, maxit=kw["maxit"], minit=kw["minit"], stats=stats)
     dt = time.perf_counter() - t0
+    if keep is not None:
+        keep["W"] = W
     return steps / dt, dt, stats['iterations']
 
 
@@ -159,18 +278,20 @@ def reference_arm(args):
         return
     N = args.n
     cores = cpu_threads()
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    # bounded: at N=2048 one CPU step costs seconds; keep the whole run within a few minutes
+    force_cpu_threads(cores)     # the environment was already forced before numpy loaded (top of this file)
+    # bounded: at N=2048 one CPU step costs about half a second; keep the whole run within a few minutes
     warm = min(args.warmup, 1)
-    val, secs, its = run_cpu_port(N, args.mode, args.steps, warm)
-    sample = f"{args.steps} steps (+{warm} warm-up) of R({N},42), {args.mode} mode, {its:.2f} it/step, {secs:.1f} s"
+    val, secs, its, kind, what = run_cpu(N, args.mode, args.steps, warm)
+    sample = (f"{args.steps} steps (+{warm} warm-up) of R({N},42), {args.mode} mode, {its:.2f} it/step, {secs:.1f} s; {what}; "
+              f"threads {json.dumps(thread_report())}")
     kw = mode_kwargs(args.mode, N)
     line = {
         "impl": "reference", "metric": "isomp steps/sec", "value": val, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
         "config": workload_config(N, args.mode, kw, its),
-        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": kind, "sample": sample,
+                         "threads": thread_report()},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -271,6 +392,28 @@ def gpu_arm(args):
     if world > 1:
         # collective: per-phase device times of the SHARDED iteration (eager launches, gathers not overlapped)
         ph_sharded = handle.profile_iteration(torch.from_numpy(W0).to(dev), kw["dt"], reps=5)
+    # ---- parity of the timed configuration on several GPUs: the sharded handle against a solo handle -----
+    parity = None
+    if world > 1:
+        import hashlib
+        psteps = 10
+        Wp = torch.from_numpy(W0).to(dev)
+        rsh, its_sh = handle.isomp(Wp, kw["dt"], psteps, maxit=kw["maxit"], minit=kw["minit"], want_iters=True)
+        Wp_host = Wp.cpu().numpy()
+        digests = [None] * world
+        dist.all_gather_object(digests, hashlib.sha256(Wp_host.tobytes()).hexdigest())
+        if rank == 0:
+            hs = Handle(N, 1, local_rank)
+            Ws = torch.from_numpy(W0).to(dev)
+            rso, its_so = hs.isomp(Ws, kw["dt"], psteps, maxit=kw["maxit"], minit=kw["minit"], want_iters=True)
+            Ws_host = Ws.cpu().numpy()
+            hs.close()
+            parity = {"against": f"a single-GPU handle on rank 0, {psteps} steps of the same R({N},42) workload",
+                      "steps": psteps,
+                      "rel_err": float(np.linalg.norm(Wp_host - Ws_host) / np.linalg.norm(Ws_host)),
+                      "iterations_equal": bool(list(its_sh[0]) == list(its_so[0])),
+                      "iterations": [int(x) for x in its_sh[0]],
+                      "ranks_bit_identical": bool(all(d == digests[0] for d in digests))}
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -291,18 +434,21 @@ def gpu_arm(args):
              "(algorithmic 8 N^3 = %.4g)") % ("3M" if is3m else "4M", flops1, 8.0 * N ** 3)
     peaks = measured_peaks()
     hbm = peaks["hbm_gbs"] if peaks else 6650.0
+    from quflow_b200._cuda.binding import measure_fp64_tensor_peak
+    fp64_peak = measure_fp64_tensor_peak(local_rank, reps=5)
     pois_gbs = 32.0 * N * N / (ph["poisson_ms"] * 1e-3) / 1e9
     iter_ms = ph["poisson_ms"] + ph["gemm1_ms"] + ph["gemm2_ms"] + ph["post_ms"]
     roofline = {
         "bound": "tensor", "kernel": kname,
-        "achieved": gemm1_tf, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gemm1_tf / FP64_TENSOR_PEAK_TFLOPS,
+        "achieved": gemm1_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": gemm1_tf / fp64_peak,
         "traffic": ncu_traffic("k_zgemm3m_ws") if (N == 2048 and is3m) else None,
         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full capture at N=2048 "
                         "(profiles/r01_ncu_full_kernels.json); algorithmic operand bytes 3*16*N^2",
-        "peak_source": "measured FP64 DMMA issue peak on this pool's B200 (profiles/r01_fp64_pipes.txt); "
-                       "MEASURED_PEAKS.json has no FP64 entry, datasheet ~37-40 TF/s",
+        "peak_source": "FP64 DMMA (mma.sync.m8n8k4.f64) issue peak measured on this GPU in this run "
+                       "(qf_measure_fp64_tensor_peak, 16 warps/SM x 8 chains, best of 5); MEASURED_PEAKS.json has no FP64 "
+                       f"entry; round-1 value {FP64_TENSOR_PEAK_TFLOPS_R01} TF/s, datasheet ~37-40 TF/s",
         "launch_ms": ph["gemm1_ms"],
-        "second_gemm": {"achieved": gemm2_tf, "frac": gemm2_tf / FP64_TENSOR_PEAK_TFLOPS, "launch_ms": ph["gemm2_ms"],
+        "second_gemm": {"achieved": gemm2_tf, "frac": gemm2_tf / fp64_peak, "launch_ms": ph["gemm2_ms"],
                         "executed_flop": flops2, "note": "S = A P~ is skew-Hermitian: lower-triangle tiles skipped"},
         "executed_flop": flops1, "algorithmic_tflops_equiv": 8.0 * N ** 3 / (ph["gemm1_ms"] * 1e-3) / 1e12,
         "share_of_iteration": (ph["gemm1_ms"] + ph["gemm2_ms"]) / iter_ms,
@@ -318,12 +464,22 @@ def gpu_arm(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = cpu_threads()
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-        n_cpu = 3 if N >= 2048 else (6 if N >= 1024 else 20)
-        cval, secs, cits = run_cpu_port(N, mode, n_cpu, 1)
-        cpu = {"value": cval, "unit": "steps/s", "cores": cores, "kind": "port",
-               "sample": f"{n_cpu} steps (+1 warm-up) of the same R({N},42) workload, {cits:.2f} it/step, {secs:.1f} s; "
-                         f"numpy BLAS zgemm + OpenMP Thomas (oracle/)"}
+        force_cpu_threads(cores)
+        n_cpu = 20 if N >= 2048 else (60 if N >= 1024 else 200)       # about 10-20 s of CPU work
+        keep = {}
+        cval, secs, cits, ckind, cwhat = run_cpu(N, mode, n_cpu, 1, keep)
+        cpu = {"value": cval, "unit": "steps/s", "cores": cores, "kind": ckind, "threads": thread_report(),
+               "sample": f"{n_cpu} steps (+1 warm-up) of the same R({N},42) workload, {cits:.2f} it/step, {secs:.1f} s; {cwhat}"}
+        # parity of the timed configuration: the same two calls (1 step, then n_cpu steps) on the GPU against the CPU result
+        Wg = torch.from_numpy(W0).to(dev)
+        handle.isomp(Wg, kw["dt"], 1, maxit=kw["maxit"], minit=kw["minit"])
+        rg, _ = handle.isomp(Wg, kw["dt"], n_cpu, maxit=kw["maxit"], minit=kw["minit"])
+        Wg_host = Wg.cpu().numpy()
+        parity = {"against": f"the CPU arm ({ckind}) on the same R({N},42) workload: 1 + {n_cpu} steps in two calls",
+                  "steps": n_cpu + 1,
+                  "rel_err": float(np.linalg.norm(Wg_host - keep["W"]) / np.linalg.norm(keep["W"])),
+                  "iterations_equal": bool(rg[0]["total_iterations"] / n_cpu == cits),
+                  "iterations_per_step": [rg[0]["total_iterations"] / n_cpu, cits]}
 
     line = {
         "metric": "isomp steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
@@ -344,7 +500,9 @@ def gpu_arm(args):
         "roofline_poisson": roofline_poisson,
         "phase_ms": ph,
         "phase_ms_sharded": ph_sharded,
+        "incumbent": incumbents(N, dev) if world == 1 else None,
         "cpu_baseline": cpu,
+        "parity": parity,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

@@ -84,7 +84,7 @@ int qf_solve_poisson(qf_handle_t h, const void *W_dev, void *P_dev, void *stream
  * params_out[6] = positions per thread, diagonals per band, threads per CTA, CTAs per cluster, positions per CTA,
  * number of units; units_out (may be NULL) receives 8 ints per unit: band of the long piece, its first position, band
  * of the short piece (-1: none), local position where it starts, cluster ranks the long band spans, 0, 0, 0.
- * Returns the number of units (0: N is served by the fallback kernel) or a negative qf_status. */
+ * Returns the number of units (0: N needs more than 8 CTAs per band, which qf_create rejects) or a negative qf_status. */
 int qf_poisson_plan(int N, int *params_out, int *units_out, int cap);
 
 /* W = Delta_N P        — replaces quflow.laplacian.cpu.laplace (cpu.py:628-669, kernel
@@ -167,6 +167,12 @@ int64_t qf_launch_count(qf_handle_t h);
  * variant, and whether the 3-multiplication (Karatsuba) complex arithmetic is active. For roofline accounting. */
 double qf_gemm_executed_flops(qf_handle_t h, int upper_only);
 int qf_gemm_is_3m(qf_handle_t h);
+
+/* Roofline denominator of the two GEMMs, measured on `device` at the clocks of the calling run: issue peak of
+ * mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) in TFLOP/s, best of `reps` launches timed with CUDA events on `stream`.
+ * No reference counterpart (the reference reports no roofline); used by bench.py because MEASURED_PEAKS.json has no
+ * FP64 entry. */
+int qf_measure_fp64_tensor_peak(int device, int reps, double *tflops_out, void *stream);
 
 typedef struct {
     float poisson_ms;   /* W~ = W + dW, P~ = eps * Delta^{-1} W~ */

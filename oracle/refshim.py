@@ -7,20 +7,40 @@ appdirs, ducc0/pyssht and matplotlib, none of which is installed (SURVEY.md
 runs) plus empty stand-ins for the absent third-party modules, after which the
 hot-path modules import unmodified.
 
-Used only by ``oracle/gen_golden.py`` (fixture generation) and by tests that
-are skipped when ``/root/reference`` does not exist (it does not on the GPU
-box).  Nothing at run time of the product, ``-m gpu`` tests, ``smoke()`` or
-``bench.py`` touches this.
+Used by ``oracle/gen_golden.py`` (fixture generation), by tests that are
+skipped when no reference is present, and by ``bench.py``'s reference arm /
+``cpu_baseline`` leg, which time the real numba/BLAS ``isomp_fixedpoint``.
+On the GPU box ``/root/reference`` does not exist: there the shim loads the
+unmodified hot-path modules staged under ``oracle/_ref/`` by
+``oracle/make_ref.py`` (git-ignored, shipped with the snapshot).  Nothing on
+the product path (``quflow_b200/``) touches this.
 """
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("QUFLOW_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/make_ref.py
+
+
+def _pick_root() -> str:
+    env = os.environ.get("QUFLOW_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/quflow"):
+        return "/root/reference"
+    return _STAGED          # the GPU box: only the staged hot-path modules exist (no quantization / analysis)
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "quflow"))
+
+
+def full_tree() -> bool:
+    """True when the whole reference tree is present (build container), not just the staged hot-path modules."""
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "quflow", "quantization.py"))
 
 
 def load(with_quantization: bool = False):

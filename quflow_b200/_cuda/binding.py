@@ -81,6 +81,7 @@ SYMBOLS = {
     "qf_launch_count": (ctypes.c_int64, [_vp]),
     "qf_gemm_executed_flops": (_d, [_vp, _i]),
     "qf_gemm_is_3m": (_i, [_vp]),
+    "qf_measure_fp64_tensor_peak": (_i, [_i, _i, ctypes.POINTER(_d), _vp]),
     "qf_profile_iteration": (_i, [_vp, _vp, _d, _i, ctypes.POINTER(qf_phase_times), _vp]),
     "qf_comm_get_unique_id": (_i, [_vp]),
     "qf_comm_init": (_i, [_vp, _vp, _i, _i]),
@@ -122,7 +123,8 @@ def _check(rc):
 
 
 def poisson_plan(N: int):
-    """Work plan of the Poisson kernel (host code only): (params dict, units array (n, 8)) or None for the fallback."""
+    """Work plan of the Poisson kernel (host code only): (params dict, units array (n, 8)), or None when N is too large
+    for the band kernel (qf_create rejects such N)."""
     lib = library()
     params = (ctypes.c_int * 6)()
     n = lib.qf_poisson_plan(int(N), params, None, 0)
@@ -134,6 +136,13 @@ def poisson_plan(N: int):
     lib.qf_poisson_plan(int(N), params, units, 8 * n)
     keys = ("L", "M", "NT", "CL", "PC", "nunits")
     return dict(zip(keys, params[:])), np.array(units[:], dtype=np.int32).reshape(n, 8)
+
+
+def measure_fp64_tensor_peak(device: int = 0, reps: int = 5) -> float:
+    """FP64 DMMA issue peak of `device` in TFLOP/s, measured now (roofline denominator of the GEMMs)."""
+    out = _d(0.0)
+    _check(library().qf_measure_fp64_tensor_peak(int(device), int(reps), ctypes.byref(out), _stream_ptr()))
+    return out.value
 
 
 def device_count() -> int:
@@ -149,9 +158,10 @@ def _dev_ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def _stream_ptr():
+def _stream_ptr(device=None):
+    """torch's current stream ON THE GIVEN DEVICE (default: the current device) as a cudaStream_t."""
     import torch
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class Handle:
@@ -166,6 +176,7 @@ class Handle:
         _check(lib.qf_create(self.N, self.batch, self.device, ctypes.byref(h)))
         self._h = h
         self._lib = lib
+        self._busy = 0
 
     def close(self):
         if getattr(self, "_h", None):
@@ -179,6 +190,24 @@ class Handle:
             pass
 
     # -- helpers -----------------------------------------------------------------------
+    def _stream(self):
+        return _stream_ptr(self.device)     # the handle's device, whatever torch's current device is
+
+    def use(self):
+        """Context manager that pins the handle while a multi-call sequence (host-stepped driver, views of its buffers)
+        is in flight: get_handle's LRU eviction never destroys a pinned handle."""
+        handle = self
+
+        class _Pin:
+            def __enter__(self):
+                handle._busy += 1
+                return handle
+
+            def __exit__(self, *exc):
+                handle._busy -= 1
+                return False
+        return _Pin()
+
     def _shape_ok(self, a):
         shp = tuple(a.shape)
         want2, want3 = (self.N, self.N), (self.batch, self.N, self.N)
@@ -208,7 +237,7 @@ class Handle:
             return out
         import torch
         out = torch.empty_like(W) if out is None else out
-        _check(self._lib.qf_solve_poisson(self._h, _dev_ptr(W), _dev_ptr(out), _stream_ptr()))
+        _check(self._lib.qf_solve_poisson(self._h, _dev_ptr(W), _dev_ptr(out), self._stream()))
         return out
 
     def laplace(self, P, out=None):
@@ -219,13 +248,13 @@ class Handle:
             return out
         import torch
         out = torch.empty_like(P) if out is None else out
-        _check(self._lib.qf_laplace(self._h, _dev_ptr(P), _dev_ptr(out), _stream_ptr()))
+        _check(self._lib.qf_laplace(self._h, _dev_ptr(P), _dev_ptr(out), self._stream()))
         return out
 
     def norm_inf(self, W):
         self._shape_ok(W)
         out = (ctypes.c_double * self.batch)()
-        _check(self._lib.qf_norm_inf(self._h, _dev_ptr(W), out, _stream_ptr()))
+        _check(self._lib.qf_norm_inf(self._h, _dev_ptr(W), out, self._stream()))
         return np.array(out[:])
 
     def inner(self, P, W):
@@ -233,7 +262,7 @@ class Handle:
         self._shape_ok(P)
         self._shape_ok(W)
         out = (ctypes.c_double * self.batch)()
-        _check(self._lib.qf_inner(self._h, _dev_ptr(P), _dev_ptr(W), out, _stream_ptr()))
+        _check(self._lib.qf_inner(self._h, _dev_ptr(P), _dev_ptr(W), out, self._stream()))
         return np.array(out[:])
 
     def zgemm(self, A, B, out=None):
@@ -241,7 +270,7 @@ class Handle:
         self._shape_ok(A)
         self._shape_ok(B)
         out = torch.empty_like(A) if out is None else out
-        _check(self._lib.qf_zgemm(self._h, _dev_ptr(A), _dev_ptr(B), _dev_ptr(out), _stream_ptr()))
+        _check(self._lib.qf_zgemm(self._h, _dev_ptr(A), _dev_ptr(B), _dev_ptr(out), self._stream()))
         return out
 
     def isomp(self, W, dt, steps, tol=-1.0, maxit=10, minit=1, compsum=False, reinitialize=False, want_iters=False,
@@ -261,7 +290,7 @@ class Handle:
                                          int(minit), flags, stats, iters_p)
         else:
             rc = self._lib.qf_isomp(self._h, _dev_ptr(W), float(dt), int(steps), float(tol), int(maxit), int(minit),
-                                    flags, stats, iters_p, _stream_ptr())
+                                    flags, stats, iters_p, self._stream())
         if rc == QF_ERR_NONFINITE:
             raise ValueError("array must not contain infs or NaNs")
         if rc == QF_ERR_INVALID:
@@ -289,50 +318,50 @@ class Handle:
     def step_open(self, W, dt, tol=-1.0, compsum=False, reinitialize=False) -> float:
         flags = (QF_FLAG_COMPSUM if compsum else 0) | (QF_FLAG_REINITIALIZE if reinitialize else 0)
         used = _d(0.0)
-        _check(self._lib.qf_step_open(self._h, _dev_ptr(W), float(dt), float(tol), flags, ctypes.byref(used), _stream_ptr()))
+        _check(self._lib.qf_step_open(self._h, _dev_ptr(W), float(dt), float(tol), flags, ctypes.byref(used), self._stream()))
         return used.value
 
     def step_begin(self, W):
-        _check(self._lib.qf_step_begin(self._h, _dev_ptr(W), _stream_ptr()))
+        _check(self._lib.qf_step_begin(self._h, _dev_ptr(W), self._stream()))
 
     def step_hamiltonian(self):
-        _check(self._lib.qf_step_hamiltonian(self._h, _stream_ptr()))
+        _check(self._lib.qf_step_hamiltonian(self._h, self._stream()))
 
     def step_scale_p(self, divide: bool):
-        _check(self._lib.qf_step_scale_p(self._h, 1 if divide else 0, _stream_ptr()))
+        _check(self._lib.qf_step_scale_p(self._h, 1 if divide else 0, self._stream()))
 
     def step_products(self):
-        _check(self._lib.qf_step_products(self._h, _stream_ptr()))
+        _check(self._lib.qf_step_products(self._h, self._stream()))
 
     def step_close_iteration(self, W, F, fscale, maxit, minit):
         """Returns (loop continues?, residual).  Raises ValueError on a non-finite residual like scipy.linalg.norm."""
         active, res = _i(0), _d(0.0)
         rc = self._lib.qf_step_close_iteration(self._h, _dev_ptr(W), _dev_ptr(F) if F is not None else None, float(fscale),
-                                               int(maxit), int(minit), ctypes.byref(active), ctypes.byref(res), _stream_ptr())
+                                               int(maxit), int(minit), ctypes.byref(active), ctypes.byref(res), self._stream())
         if rc == QF_ERR_NONFINITE:
             raise ValueError("array must not contain infs or NaNs")
         _check(rc)
         return bool(active.value), res.value
 
     def step_increment(self, out):
-        _check(self._lib.qf_step_increment(self._h, _dev_ptr(out), _stream_ptr()))
+        _check(self._lib.qf_step_increment(self._h, _dev_ptr(out), self._stream()))
         return out
 
     def step_update(self, W, F, fscale):
-        rc = self._lib.qf_step_update(self._h, _dev_ptr(W), _dev_ptr(F) if F is not None else None, float(fscale), _stream_ptr())
+        rc = self._lib.qf_step_update(self._h, _dev_ptr(W), _dev_ptr(F) if F is not None else None, float(fscale), self._stream())
         if rc == QF_ERR_UNSUPPORTED:
             raise NotImplementedError(self._lib.qf_last_error().decode())
         _check(rc)
 
     def step_stats(self):
         st = qf_stats()
-        _check(self._lib.qf_step_stats(self._h, ctypes.byref(st), _stream_ptr()))
+        _check(self._lib.qf_step_stats(self._h, ctypes.byref(st), self._stream()))
         return dict(tol_used=st.tol_used, last_resnorm=st.last_resnorm, total_iterations=int(st.total_iterations),
                     number_of_maxit=int(st.number_of_maxit), steps_done=int(st.steps_done))
 
     def profile_iteration(self, W, dt, reps=5):
         pt = qf_phase_times()
-        _check(self._lib.qf_profile_iteration(self._h, _dev_ptr(W), float(dt), int(reps), ctypes.byref(pt), _stream_ptr()))
+        _check(self._lib.qf_profile_iteration(self._h, _dev_ptr(W), float(dt), int(reps), ctypes.byref(pt), self._stream()))
         return {k: getattr(pt, k) for k, _ in qf_phase_times._fields_}
 
     # -- multi-GPU -----------------------------------------------------------------------
@@ -376,9 +405,10 @@ _MAX_CACHED_HANDLES = 8      # a handle owns ~8 N^2 complex matrices (0.55 GB at
 def get_handle(N: int, batch: int = 1, device: int | None = None) -> Handle:
     """Module-level LRU cache, mirroring the reference's per-N caches (quflow/laplacian/cpu.py:11-17).
 
-    Callers use the handle for the duration of one call; the least recently used one is destroyed when more than
-    ``_MAX_CACHED_HANDLES`` distinct (N, batch, device) combinations have been seen.  Hold your own ``Handle`` for
-    long-lived use (bench.py, multi-GPU sharding)."""
+    Callers use the handle for the duration of one call (or pin it with ``Handle.use()`` across several); the least
+    recently used idle one is destroyed when more than ``_MAX_CACHED_HANDLES`` distinct (N, batch, device) combinations
+    have been seen.  One handle serves one host thread / stream at a time.  Hold your own ``Handle`` for long-lived use
+    (bench.py, multi-GPU sharding)."""
     if device is None:
         try:
             import torch
@@ -389,8 +419,8 @@ def get_handle(N: int, batch: int = 1, device: int | None = None) -> Handle:
     if key in _handles:
         _handles.move_to_end(key)
         return _handles[key]
-    while len(_handles) >= _MAX_CACHED_HANDLES:
-        _, old = _handles.popitem(last=False)
-        old.close()
+    if len(_handles) >= _MAX_CACHED_HANDLES:
+        for old_key in [k for k, hd in _handles.items() if hd._busy == 0][:len(_handles) - _MAX_CACHED_HANDLES + 1]:
+            _handles.pop(old_key).close()      # least recently used first; handles pinned by Handle.use() are kept
     _handles[key] = Handle(*key)
     return _handles[key]

@@ -50,7 +50,7 @@ extern "C" int qf_create(int N, int batch, int device, qf_handle_t *out)
         return QF_ERR_CUDA;
     }
     if (device < 0 || device >= ndev) { qf_set_error("qf_create: device %d out of range (%d devices)", device, ndev); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(device));
+    QF_ON_DEVICE(device);
     cudaDeviceProp prop;
     QF_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) {
@@ -76,13 +76,19 @@ extern "C" int qf_create(int N, int batch, int device, qf_handle_t *out)
     if (rc == QF_OK) rc = alloc_mat(h, &h->S);
     if (rc == QF_OK) rc = alloc_mat(h, &h->scratch);
     if (rc == QF_OK) rc = qf_gemm_create(h);
-    if (rc != QF_OK) { qf_destroy(h); return rc; }
     const size_t rp = sizeof(double) * (size_t)batch * 2 * h->nslots * N;
-    QF_CUDA(cudaMalloc(&h->rowpart, rp));
-    QF_CUDA(cudaMemset(h->rowpart, 0, rp));
-    QF_CUDA(cudaMalloc(&h->ctrl, sizeof(QfCtrl) * batch));
-    QF_CUDA(cudaMemset(h->ctrl, 0, sizeof(QfCtrl) * batch));
-    QF_CUDA(cudaMallocHost(&h->ctrl_host, sizeof(QfCtrl) * batch));
+    auto cu = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && rc == QF_OK) {
+            qf_set_error("qf_create: %s failed: %s", what, cudaGetErrorString(e));
+            rc = QF_ERR_CUDA;
+        }
+    };
+    if (rc == QF_OK) cu(cudaMalloc(&h->rowpart, rp), "cudaMalloc(rowpart)");
+    if (rc == QF_OK) cu(cudaMemset(h->rowpart, 0, rp), "cudaMemset(rowpart)");
+    if (rc == QF_OK) cu(cudaMalloc(&h->ctrl, sizeof(QfCtrl) * batch), "cudaMalloc(ctrl)");
+    if (rc == QF_OK) cu(cudaMemset(h->ctrl, 0, sizeof(QfCtrl) * batch), "cudaMemset(ctrl)");
+    if (rc == QF_OK) cu(cudaMallocHost(&h->ctrl_host, sizeof(QfCtrl) * batch), "cudaMallocHost(ctrl_host)");
+    if (rc != QF_OK) { qf_destroy(h); return rc; }      // frees whatever was allocated so far
     *out = h;
     return QF_OK;
 }
@@ -90,7 +96,7 @@ extern "C" int qf_create(int N, int batch, int device, qf_handle_t *out)
 extern "C" int qf_destroy(qf_handle_t h)
 {
     if (!h) return QF_OK;
-    cudaSetDevice(h->device);
+    QfDeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     qf_graph_destroy(h);
     qf_gemm_destroy(h);
@@ -111,7 +117,7 @@ extern "C" int qf_solve_poisson(qf_handle_t h, const void *W_dev, void *P_dev, v
 {
     if (!h || !W_dev || !P_dev) { qf_set_error("qf_solve_poisson: null argument"); return QF_ERR_INVALID; }
     if (W_dev == P_dev) { qf_set_error("qf_solve_poisson: W and P may not alias"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     const double2 *W = (const double2 *)W_dev;
     // Wh == W: the solve reads W directly (no W + dW pass), eps = 1, not gated
     return qf_launch_poisson(h, W, nullptr, const_cast<double2 *>(W), (double2 *)P_dev, 1.0, false, (cudaStream_t)stream);
@@ -121,14 +127,14 @@ extern "C" int qf_laplace(qf_handle_t h, const void *P_dev, void *W_dev, void *s
 {
     if (!h || !W_dev || !P_dev) { qf_set_error("qf_laplace: null argument"); return QF_ERR_INVALID; }
     if (W_dev == P_dev) { qf_set_error("qf_laplace: P and W may not alias"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     return qf_launch_laplace(h, (const double2 *)P_dev, (double2 *)W_dev, (cudaStream_t)stream);
 }
 
 extern "C" int qf_norm_inf(qf_handle_t h, const void *W_dev, double *out_host, void *stream)
 {
     if (!h || !W_dev || !out_host) { qf_set_error("qf_norm_inf: null argument"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     QF_CHECK(qf_launch_norm_inf(h, (const double2 *)W_dev, st));
     QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl) * h->batch, cudaMemcpyDeviceToHost, st));
@@ -140,7 +146,7 @@ extern "C" int qf_norm_inf(qf_handle_t h, const void *W_dev, double *out_host, v
 extern "C" int qf_zgemm(qf_handle_t h, const void *A_dev, const void *B_dev, void *C_dev, void *stream)
 {
     if (!h || !A_dev || !B_dev || !C_dev) { qf_set_error("qf_zgemm: null argument"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     return qf_launch_zgemm(h, (const double2 *)A_dev, (const double2 *)B_dev, (double2 *)C_dev, false, false, -1, 1, false,
                            (cudaStream_t)stream);
 }
@@ -158,7 +164,7 @@ extern "C" int qf_isomp_host(qf_handle_t h, void *W_host, double dt, int steps, 
                              unsigned flags, qf_stats *stats, int32_t *iters_per_step)
 {
     if (!h || !W_host) { qf_set_error("qf_isomp_host: null argument"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     QF_CHECK(ensure_io(h, false));
     const size_t bytes = sizeof(double2) * h->mat_elems * h->batch;
     QF_CUDA(cudaMemcpyAsync(h->io, W_host, bytes, cudaMemcpyHostToDevice, 0));
@@ -171,7 +177,7 @@ extern "C" int qf_isomp_host(qf_handle_t h, void *W_host, double dt, int steps, 
 extern "C" int qf_solve_poisson_host(qf_handle_t h, const void *W_host, void *P_host)
 {
     if (!h || !W_host || !P_host) { qf_set_error("qf_solve_poisson_host: null argument"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     QF_CHECK(ensure_io(h, true));
     const size_t bytes = sizeof(double2) * h->mat_elems * h->batch;
     QF_CUDA(cudaMemcpyAsync(h->io, W_host, bytes, cudaMemcpyHostToDevice, 0));
@@ -183,7 +189,7 @@ extern "C" int qf_solve_poisson_host(qf_handle_t h, const void *W_host, void *P_
 extern "C" int qf_laplace_host(qf_handle_t h, const void *P_host, void *W_host)
 {
     if (!h || !W_host || !P_host) { qf_set_error("qf_laplace_host: null argument"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     QF_CHECK(ensure_io(h, true));
     const size_t bytes = sizeof(double2) * h->mat_elems * h->batch;
     QF_CUDA(cudaMemcpyAsync(h->io, P_host, bytes, cudaMemcpyHostToDevice, 0));

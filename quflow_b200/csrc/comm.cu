@@ -37,7 +37,7 @@ extern "C" int qf_comm_init(qf_handle_t h, const void *unique_id, int rank, int 
     if (!h || !unique_id || nranks < 1 || rank < 0 || rank >= nranks) { qf_set_error("qf_comm_init: bad arguments"); return QF_ERR_INVALID; }
     if (h->batch != 1) { qf_set_error("row sharding is for a single large-N simulation (batch == 1); ensembles shard per member"); return QF_ERR_INVALID; }
     if (nranks > 1 && h->N % (2 * nranks) != 0) { qf_set_error("row sharding needs N divisible by 2*nranks (N=%d, nranks=%d)", h->N, nranks); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     if (h->nccl_comm) { ncclCommDestroy((ncclComm_t)h->nccl_comm); h->nccl_comm = nullptr; }
     h->rank = rank;
     h->nranks = nranks;
@@ -108,7 +108,7 @@ static_assert(sizeof(QfP2PBlob) <= QF_P2P_BLOB_BYTES, "blob too large");
 extern "C" int qf_comm_p2p_export(qf_handle_t h, void *blob_out)
 {
     if (!h || !blob_out) { qf_set_error("qf_comm_p2p_export: null"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
     if (!p) {
         p = new QfP2P();
@@ -138,7 +138,7 @@ extern "C" int qf_comm_p2p_import(qf_handle_t h, const void *blobs, int rank, in
     if (nranks > 1 && h->N % (2 * nranks) != 0) { qf_set_error("row sharding needs N divisible by 2*nranks (N=%d, nranks=%d)", h->N, nranks); return QF_ERR_INVALID; }
     QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
     if (!p) { qf_set_error("qf_comm_p2p_import: call qf_comm_p2p_export first"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     p->nranks = nranks;
     p->rank = rank;
     for (int r = 0; r < nranks; ++r) {

@@ -444,7 +444,7 @@ __global__ void k_inner_final(const double *__restrict__ part, int nblocks, doub
 extern "C" int qf_inner(qf_handle_t h, const void *P_dev, const void *W_dev, double *out_host, void *stream)
 {
     if (!h || !P_dev || !W_dev || !out_host) { qf_set_error("qf_inner: null argument"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int B = h->batch;
     if (!h->inner_part) QF_CUDA(cudaMalloc(&h->inner_part, sizeof(double) * (size_t)B * (INNER_BLOCKS + 1)));
@@ -688,7 +688,7 @@ extern "C" int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double
     if (minit < 1) { qf_set_error("minit must be at least 1."); return QF_ERR_INVALID; }       // isospectral.py:400
     if (maxit < minit) { qf_set_error("maxit must be at minit."); return QF_ERR_INVALID; }     // isospectral.py:401
     if (steps < 0) { qf_set_error("steps must be non-negative"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int N = h->N, B = h->batch;
     const size_t n2 = h->mat_elems;
@@ -798,7 +798,7 @@ extern "C" int qf_step_open(qf_handle_t h, const void *W_dev, double dt, double 
 {
     if (!h || !W_dev) { qf_set_error("qf_step_open: null argument"); return QF_ERR_INVALID; }
     if (h->batch != 1 || h->nranks != 1) { qf_set_error("qf_step_open: the host-stepped driver runs one member on one GPU"); return QF_ERR_UNSUPPORTED; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n2 = h->mat_elems;
     const bool compsum = (flags & QF_FLAG_COMPSUM) != 0;
@@ -824,7 +824,7 @@ extern "C" int qf_step_begin(qf_handle_t h, const void *W_dev, void *stream)
 {
     QF_CHECK(step_check(h, "qf_step_begin"));
     if (!W_dev) { qf_set_error("qf_step_begin: null W"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n2 = h->mat_elems;
     k_step_begin<<<1, 1, 0, st>>>(h->ctrl, 1, 0, 0);                        // resnorm = inf (:470)
@@ -848,14 +848,14 @@ extern "C" void *qf_step_buffer(qf_handle_t h, int which)
 extern "C" int qf_step_hamiltonian(qf_handle_t h, void *stream)
 {
     QF_CHECK(step_check(h, "qf_step_hamiltonian"));
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     return qf_launch_poisson(h, h->Wh, nullptr, h->Wh, h->P, h->step_eps, true, (cudaStream_t)stream);   // :489,:492
 }
 
 extern "C" int qf_step_scale_p(qf_handle_t h, int divide, void *stream)
 {
     QF_CHECK(step_check(h, "qf_step_scale_p"));
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     const size_t n2 = h->mat_elems;
     k_scale<<<(unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)h->sm_count * 8), 256, 0, (cudaStream_t)stream>>>(h->P, n2, h->step_eps, divide);
     h->launches++;
@@ -866,7 +866,7 @@ extern "C" int qf_step_scale_p(qf_handle_t h, int divide, void *stream)
 extern "C" int qf_step_products(qf_handle_t h, void *stream)
 {
     QF_CHECK(step_check(h, "qf_step_products"));
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     QF_CHECK(qf_launch_zgemm(h, h->P, h->Wh, h->A, false, true, -1, 1, false, st));   // :496
     QF_CHECK(qf_launch_zgemm(h, h->A, h->P, h->S, true, true, -1, 1, true, st));      // :499
@@ -878,7 +878,7 @@ extern "C" int qf_step_close_iteration(qf_handle_t h, const void *W_dev, const v
 {
     QF_CHECK(step_check(h, "qf_step_close_iteration"));
     if (!W_dev) { qf_set_error("qf_step_close_iteration: null W"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int N = h->N;
     const int nb = (N + TS - 1) / TS;
@@ -908,7 +908,7 @@ extern "C" int qf_step_increment(qf_handle_t h, void *out_dev, void *stream)
 {
     QF_CHECK(step_check(h, "qf_step_increment"));
     if (!out_dev) { qf_set_error("qf_step_increment: null output"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     const int N = h->N;
     const int nb = (N + TS - 1) / TS;
     k_increment<<<dim3(nb, nb, 1), 256, 0, (cudaStream_t)stream>>>(h->A, (double2 *)out_dev, N, N, 1);
@@ -923,7 +923,7 @@ extern "C" int qf_step_update(qf_handle_t h, void *W_dev, const void *F_dev, dou
     if (!W_dev) { qf_set_error("qf_step_update: null W"); return QF_ERR_INVALID; }
     const bool compsum = (h->step_flags & QF_FLAG_COMPSUM) != 0;
     if (compsum && F_dev) { qf_set_error("Compensated sum with forcing is not yet implemented."); return QF_ERR_UNSUPPORTED; }   // :588-589
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int N = h->N;
     const int nb = (N + TS - 1) / TS;
@@ -945,7 +945,7 @@ extern "C" int qf_step_stats(qf_handle_t h, qf_stats *stats, void *stream)
 {
     QF_CHECK(step_check(h, "qf_step_stats"));
     if (!stats) { qf_set_error("qf_step_stats: null output"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl), cudaMemcpyDeviceToHost, st));
     QF_CUDA(cudaStreamSynchronize(st));
@@ -962,7 +962,7 @@ extern "C" int qf_step_stats(qf_handle_t h, qf_stats *stats, void *stream)
 extern "C" int qf_profile_iteration(qf_handle_t h, const void *W_dev, double dt, int reps, qf_phase_times *out, void *stream)
 {
     if (!h || !W_dev || !out || reps < 1) { qf_set_error("qf_profile_iteration: bad arguments"); return QF_ERR_INVALID; }
-    QF_CUDA(cudaSetDevice(h->device));
+    QF_ON_DEVICE(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int N = h->N, B = h->batch;
     const size_t n2 = h->mat_elems;

@@ -17,6 +17,8 @@
 
 #include "qf_common.cuh"
 
+int qf_poisson_prepare(qf_handle_s *h);
+
 // ---------------------------------------------------------------------------------------
 // host: the work plan of k_poisson_band (pure host code, also exported for the CPU tests: qf_poisson_plan)
 // ---------------------------------------------------------------------------------------
@@ -107,7 +109,7 @@ static bool qf_poisson_plan_host(int N, int &L, int &M, int &NT, int &CL, std::v
 
 // params_out[6] = L, M, NT (threads per CTA), CL (CTAs per cluster), PC (positions per CTA), number of units;
 // units_out receives 8 ints per unit (bL, posbase, bS, PS, nlink, rank0, 0, 0) if it has room for them (cap ints).
-// Returns the number of units, 0 if N is served by the fallback kernel, or a negative qf_status.  No CUDA call.
+// Returns the number of units, 0 if N needs more than 8 CTAs per band (unsupported), or a negative qf_status.  No CUDA call.
 extern "C" int qf_poisson_plan(int N, int *params_out, int *units_out, int cap)
 {
     if (N < 2 || !params_out) { qf_set_error("qf_poisson_plan: bad arguments"); return QF_ERR_INVALID; }
@@ -198,7 +200,7 @@ int qf_build_tables(qf_handle_s *h)
         h->p_NTMAX = NTMAX;
         h->p_nunits = (int)nunits;
     }
-    return QF_OK;
+    return qf_poisson_prepare(h);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -758,6 +760,27 @@ __global__ void k_laplace(const double2 *__restrict__ P, double2 *__restrict__ W
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
+static void *poisson_band_fn(const qf_handle_s *h)
+{
+    void *fn = nullptr;
+#define QF_PB(CC) if (h->p_L == 16 && h->p_M == 4 && h->p_CL == CC && h->p_NTMAX == 512) fn = (void *)k_poisson_band<16, 4, CC, 512>;
+    QF_PB(1) QF_PB(2) QF_PB(4) QF_PB(8)
+#undef QF_PB
+    return fn;
+}
+
+// Per-handle (= per-device) kernel set-up: the opt-in to more than 48 KB of dynamic shared memory is a property of the
+// function ON THE CURRENT DEVICE, so it is made once for every handle, right after its tables are built.
+int qf_poisson_prepare(qf_handle_s *h)
+{
+    void *fn = poisson_band_fn(h);
+    if (!fn) { qf_set_error("no k_poisson_band instantiation for L=%d M=%d CL=%d", h->p_L, h->p_M, h->p_CL); return QF_ERR_UNSUPPORTED; }
+    QF_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->p_NTMAX == 512 ? 144 * 1024 : 72 * 1024));
+    const char *env = getenv("QF_POISSON_PF");
+    h->p_pf = env ? atoi(env) : 1;
+    return QF_OK;
+}
+
 int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, double2 *Wh, double2 *P, double eps,
                       bool gated, cudaStream_t st, int members)
 {
@@ -774,23 +797,9 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
         const int L = h->p_L, M = h->p_M, CL = h->p_CL, NT = h->p_NT;
         const int PC = (NT / M) * L;
         const size_t smem = std::max((size_t)NT * L * 8, (size_t)(PC * M + (PC / L) * 4) * sizeof(double2));
-        void *fn = nullptr;
-#define QF_PB(CC) if (L == 16 && M == 4 && CL == CC && h->p_NTMAX == 512) fn = (void *)k_poisson_band<16, 4, CC, 512>;
-        QF_PB(1) QF_PB(2) QF_PB(4) QF_PB(8)
-#undef QF_PB
+        void *fn = poisson_band_fn(h);
         if (!fn) { qf_set_error("no k_poisson_band instantiation for L=%d M=%d CL=%d", L, M, CL); return QF_ERR_UNSUPPORTED; }
-        static void *attr_fn[8] = {nullptr};
-        bool seen = false;
-        for (void *f : attr_fn) seen |= (f == fn);
-        if (!seen) {
-            QF_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->p_NTMAX == 512 ? 144 * 1024 : 72 * 1024));
-            for (void *&f : attr_fn) if (!f) { f = fn; break; }
-        }
-        static int pf = -1;
-        if (pf < 0) {
-            const char *env = getenv("QF_POISSON_PF");
-            pf = env ? atoi(env) : 1;
-        }
+        const int pf = h->p_pf;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)h->p_nunits, (unsigned)nmem);
         cfg.blockDim = dim3((unsigned)NT);

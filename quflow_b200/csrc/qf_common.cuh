@@ -21,6 +21,31 @@ void qf_set_error(const char *fmt, ...);
         }                                                                                         \
     } while (0)
 
+// Entry points run on the handle's device and leave the caller's current device as they found it.
+struct QfDeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit QfDeviceGuard(int dev)
+    {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) cur = -1;
+        if (cur != dev) {
+            ok = (cudaSetDevice(dev) == cudaSuccess);
+            prev = cur;
+        }
+    }
+    ~QfDeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define QF_ON_DEVICE(dev)                                                                         \
+    QfDeviceGuard _qf_guard(dev);                                                                 \
+    if (!_qf_guard.ok) {                                                                          \
+        qf_set_error("cudaSetDevice(%d) failed at %s:%d", (int)(dev), __FILE__, __LINE__);        \
+        return QF_ERR_CUDA;                                                                       \
+    }
+
 #define QF_CHECK(expr)                  \
     do {                                \
         int _s = (expr);                \
@@ -74,6 +99,7 @@ struct qf_handle_s {
     int p_NT = 0;                   // threads per CTA
     int p_NTMAX = 256;              // launch bound of the instantiation in use
     int p_nunits = 0;               // CTAs in the launch
+    int p_pf = 1;                   // L2 prefetch of the following unit (QF_POISSON_PF, read at handle creation)
     // work matrices, batch * N * N complex128 each
     double2 *dW = nullptr, *Wh = nullptr, *P = nullptr, *A = nullptr, *S = nullptr, *scratch = nullptr;
     double2 *A2 = nullptr, *S2 = nullptr;   // odd-iteration copies of A and S (multi-GPU push mode only)

@@ -88,7 +88,7 @@ def member_slice(k: int, rank: int, world: int) -> slice:
     return slice(start, start + base + (1 if rank < rem else 0))
 
 
-def isomp_ensemble_sharded(W_local, dt, steps, dist=None, **kw):
+def isomp_ensemble_sharded(W_local, dt, steps, **kw):
     """Advance this rank's members of an ensemble (``W_local``: (k_local, N, N)); no collective on the data path."""
     from .integrators import isomp_ensemble
     return isomp_ensemble(W_local, dt, steps, **kw)

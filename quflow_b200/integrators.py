@@ -88,61 +88,62 @@ def _isomp_host_stepped(W, dt, steps, hamiltonian, time, forcing, strang_splitti
     if isinstance(tol, str) and not auto:
         raise ValueError("tol must be a float or 'auto'")
     h = get_handle(N, 1, dev.index)
-    tol_used = h.step_open(Wd, dt, -1.0 if auto else float(tol), compsum=bool(compsum), reinitialize=bool(reinitialize))
-    if auto:
-        if verbatim:
-            print("Tolerance set to {}.".format(tol_used))            # :449-450
-        if stats:
-            stats['tol_auto'] = tol_used                               # :451-452
-    Whalf = h.buffer_tensor(QF_BUF_WHALF)
-    Phalf = h.buffer_tensor(QF_BUF_P)
-    inc = h.buffer_tensor(QF_BUF_SCRATCH)
+    with h.use():      # pinned: hooks may create other handles while views of this one's buffers are alive
+        tol_used = h.step_open(Wd, dt, -1.0 if auto else float(tol), compsum=bool(compsum), reinitialize=bool(reinitialize))
+        if auto:
+            if verbatim:
+                print("Tolerance set to {}.".format(tol_used))            # :449-450
+            if stats:
+                stats['tol_auto'] = tol_used                               # :451-452
+        Whalf = h.buffer_tensor(QF_BUF_WHALF)
+        Phalf = h.buffer_tensor(QF_BUF_P)
+        inc = h.buffer_tensor(QF_BUF_SCRATCH)
 
-    def strang(Wcur):
-        Wnew = strang_splitting(dt / 2, to_user(Wcur, writable=True))   # :466-467, :602-603 (the reference rebinds W)
-        if Wnew is not Wcur:
-            Wcur.copy_(from_user(Wnew, "strang_splitting"))
-        return Wcur
+        def strang(Wcur):
+            Wnew = strang_splitting(dt / 2, to_user(Wcur, writable=True))   # :466-467, :602-603 (the reference rebinds W)
+            if Wnew is not Wcur:
+                Wcur.copy_(from_user(Wnew, "strang_splitting"))
+            return Wcur
 
-    seen_maxit = 0
-    for k in range(steps):
-        if strang_splitting:
-            Wd = strang(Wd)
-        h.step_begin(Wd)                                               # :470-472, :481-482
-        FW = None
-        for i in range(maxit):                                         # :475
-            if default_ham:
-                h.step_hamiltonian()                                   # :489, :492
-            else:
-                Pu = hamiltonian(to_user(Whalf)) if autonomous else hamiltonian(to_user(Whalf), time=time + dt / 2)   # :488-491
-                Phalf.copy_(from_user(Pu, "hamiltonian"))
-                h.step_scale_p(divide=False)                           # :492
-            h.step_products()                                          # :496, :499
-            if forcing:                                                # :511-520
-                h.step_scale_p(divide=True)                            # :513
-                Fu = (forcing(to_user(Phalf), to_user(Whalf)) if autonomous_force
-                      else forcing(to_user(Phalf), to_user(Whalf), time=time + dt / 2))
-                FW = from_user(Fu, "forcing")
-            active, _ = h.step_close_iteration(Wd, FW, dt / 2, maxit, minit)   # :503-509, :518-536
-            if not active:
-                break
-        if verbatim:
-            n_maxit = h.step_stats()['number_of_maxit']
-            if n_maxit > seen_maxit:
-                print("Max iterations {} reached at step {}.".format(maxit, k))      # :538-542
-            seen_maxit = n_maxit
-        if callback is not None:                                       # :547-551
-            h.step_increment(inc)
-            callback(to_user(Wd), to_user(inc))
-        if compsum and forcing:
-            raise NotImplementedError("Compensated sum with forcing is not yet implemented.")   # :588-589
-        h.step_update(Wd, FW, dt / 2)                                  # :553-596
-        if time is not None:
-            time += dt                                                 # :598-599
-        if strang_splitting:
-            Wd = strang(Wd)
+        seen_maxit = 0
+        for k in range(steps):
+            if strang_splitting:
+                Wd = strang(Wd)
+            h.step_begin(Wd)                                               # :470-472, :481-482
+            FW = None
+            for i in range(maxit):                                         # :475
+                if default_ham:
+                    h.step_hamiltonian()                                   # :489, :492
+                else:
+                    Pu = hamiltonian(to_user(Whalf)) if autonomous else hamiltonian(to_user(Whalf), time=time + dt / 2)   # :488-491
+                    Phalf.copy_(from_user(Pu, "hamiltonian"))
+                    h.step_scale_p(divide=False)                           # :492
+                h.step_products()                                          # :496, :499
+                if forcing:                                                # :511-520
+                    h.step_scale_p(divide=True)                            # :513
+                    Fu = (forcing(to_user(Phalf), to_user(Whalf)) if autonomous_force
+                          else forcing(to_user(Phalf), to_user(Whalf), time=time + dt / 2))
+                    FW = from_user(Fu, "forcing")
+                active, _ = h.step_close_iteration(Wd, FW, dt / 2, maxit, minit)   # :503-509, :518-536
+                if not active:
+                    break
+            if verbatim:
+                n_maxit = h.step_stats()['number_of_maxit']
+                if n_maxit > seen_maxit:
+                    print("Max iterations {} reached at step {}.".format(maxit, k))      # :538-542
+                seen_maxit = n_maxit
+            if callback is not None:                                       # :547-551
+                h.step_increment(inc)
+                callback(to_user(Wd), to_user(inc))
+            if compsum and forcing:
+                raise NotImplementedError("Compensated sum with forcing is not yet implemented.")   # :588-589
+            h.step_update(Wd, FW, dt / 2)                                  # :553-596
+            if time is not None:
+                time += dt                                                 # :598-599
+            if strang_splitting:
+                Wd = strang(Wd)
 
-    st = h.step_stats()
+        st = h.step_stats()
     if verbatim and steps > 0:
         print("Average number of iterations per step: {:.2f}".format(st['total_iterations'] / steps))   # :607-608
     if stats and steps > 0:                                            # :609-611

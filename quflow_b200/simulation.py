@@ -9,7 +9,9 @@ what the callbacks receive (``cfun(W, delta_time=, delta_steps=, **stats)``, :79
 attributes ``version``, ``created``, ``qutypes``, ``loggers``, ``N``; datasets ``mat`` (T,N,N) chunked (1,N,N) with
 attribute ``qutype``; ``time`` float64 (T,), ``step`` int (T,); ``tol_auto``, ``iterations``, ``number_of_maxit``,
 user fields and logger outputs; sub-group ``args/`` holding the solver arguments, callables pickled — :128-146,
-357-431, 433-478) so files written here open with the reference and vice versa.
+357-431, 433-478).  Files written here follow the reference's layout; files written by the reference can be continued
+here only when their ``qutypes`` are ``{'mat'}`` (anything else is refused on open, see ``__init__``).  The layout has
+been exercised against ``tests/fake_h5py.py`` only: h5py is absent from this image.
 
 What is new: when the integrator is this package's ``isomp`` the state stays on the GPU for the whole run; every
 output interval costs one device→host copy into pinned memory for the callbacks instead of a round trip per chunk.
@@ -73,6 +75,12 @@ class QuSimulation(object):
             with _h5py().File(filename, "r") as f:
                 g = f[self.datapath]
                 self.qutypes = pickle.loads(bytes(g.attrs["qutypes"][0]))
+                unsupported = [q for q in self.qutypes if q != 'mat']
+                if unsupported:
+                    # appending only `mat` would leave the other datasets one row behind per record: refuse
+                    raise NotImplementedError(
+                        f"{filename} stores the representations {sorted(self.qutypes)}; quflow_b200.QuSimulation can only "
+                        "continue files whose qutypes are {'mat'} (fun/shr/shc need the SHT layer of the reference)")
                 if "loggers" in g.attrs:
                     self.loggers = pickle.loads(bytes(g.attrs["loggers"][0]))
         self._refresh_fieldnames()

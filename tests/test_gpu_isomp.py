@@ -79,25 +79,27 @@ def test_isomp_config3_N1024_100_steps_vs_oracle(qf):
     assert np.abs(W + W.conj().T).max() == 0.0
 
 
-def test_isomp_config4_N2048_properties(qf):
-    """BASELINE config 4 size: R(2048, 42).  The oracle needs ~0.7 s per step here, so: 8 steps against the oracle
-    (<= 1e-10, same iteration counts), then size-independent properties over 40 steps — exact skew-Hermitian symmetry,
-    zero trace, Casimirs C_2..C_4 conserved to the fixed-point tolerance (the reference's own drift over 100 steps is
+def test_isomp_config4_N2048_100_steps_vs_oracle(qf):
+    """BASELINE config 4 size, the headline workload of bench.py: R(2048, 42), natural mode.  The north-star bar at the
+    size that is timed: 100 steps against the CPU oracle run live on the same input (about 0.5 s per step on the box's
+    host cores) — relative Frobenius error <= 1e-10 and identical per-step iteration counts — plus the
+    size-independent properties: exact skew-Hermitian symmetry, zero trace, Casimirs C_2..C_4 conserved to the
+    fixed-point tolerance and no worse than the oracle's own drift (the reference's drift over 100 steps is
     1e-12 ... 3e-10)."""
     N = 2048
     W0 = oracle.random_skewherm(N, 42)
     dt = 0.25 * oracle.hbar(N)
-    W, st, iters = run_gpu(qf, W0, dt, 8)
+    W, st, iters = run_gpu(qf, W0, dt, 100)
     rec = {}
-    Wref = oracle.isomp(W0.copy(), dt, 8, record=rec)
+    Wref = oracle.isomp(W0.copy(), dt, 100, record=rec)
     assert list(iters) == rec["iterations"]
     assert relfro(W, Wref) < TOL_100_STEPS
-    W40, st40, it40 = run_gpu(qf, W0, dt, 40)
-    assert np.abs(W40 + W40.conj().T).max() == 0.0
-    assert abs(np.trace(W40)) < 1e-12 * np.linalg.norm(W40)
-    c0, c1 = _casimirs_by_products(W0), _casimirs_by_products(W40)
+    assert np.abs(W + W.conj().T).max() == 0.0
+    assert abs(np.trace(W)) < 1e-12 * np.linalg.norm(W)
+    c0, c1, cr = _casimirs_by_products(W0), _casimirs_by_products(W), _casimirs_by_products(Wref)
     assert np.all(np.abs(c1 - c0) <= 1e-9 * np.abs(c0) + 1e-12)
-    assert 2 <= it40.mean() <= 4 and st40["number_of_maxit"] == 0
+    assert np.all(np.abs(c1 - c0) <= 2 * np.abs(cr - c0) + 1e-12 * np.abs(c0))     # drift no worse than the reference's
+    assert 2 <= iters.mean() <= 4 and st["number_of_maxit"] == 0
 
 
 def test_reference_golden_vector_head_semantics(qf):
@@ -114,10 +116,15 @@ def test_isomp_option_variants(qf, tag, kw):
     g = golden(f"isomp_R_N32_{tag}.npz")
     W, st, iters = run_gpu(qf, oracle.random_skewherm(32, 42), float(g["dt"]), int(g["steps"]), **kw)
     if tag != "tol1e-10":
-        # with tol far below the attainable residual the loop ends on the stagnation rule
-        # (resnorm >= resnorm_old), i.e. on rounding noise: counts may legitimately differ there
         assert list(iters) == list(g["iterations"])
         assert st["number_of_maxit"] / int(g["steps"]) == float(g["number_of_maxit"])
+    else:
+        # with tol far below the attainable residual the loop ends on the stagnation rule (resnorm >= resnorm_old), i.e.
+        # on rounding noise: a step may stop one iteration earlier or later than the reference, never more, and the
+        # totals stay within 10 %
+        ref_it = np.asarray(g["iterations"])
+        assert np.abs(np.asarray(iters) - ref_it).max() <= 1
+        assert abs(int(np.sum(iters)) - int(ref_it.sum())) <= 0.1 * ref_it.sum()
     assert relfro(W, g["Wfinal"]) < TOL_100_STEPS
 
 

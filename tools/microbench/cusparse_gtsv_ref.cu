@@ -17,7 +17,9 @@ int main(int argc, char **argv)
 {
     cusparseHandle_t hs;
     CK(cusparseCreate(&hs));
-    for (int N : {512, 1024, 2048}) {
+    std::vector<int> sizes = {512, 1024, 2048};
+    if (argc > 1) sizes = {atoi(argv[1])};      // bench.py passes the size it is timing
+    for (int N : sizes) {
         const int batch = N / 2 + 1, m = N;
         const size_t tot = (size_t)batch * m;
         std::vector<double> dl(tot), d(tot), du(tot), x(tot);
