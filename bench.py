@@ -367,13 +367,17 @@ def gpu_arm(args):
     # ---- e2e: public API, host buffers, one call per step ------------------------------------------
     Wpin = torch.from_numpy(W0.copy()).pin_memory()
     Wh = Wpin.numpy()
-    # one GPU: the module-level qf.isomp; several GPUs: the same host-buffer call on the row-sharded handle (every rank
-    # copies the replicated state in over its own PCIe link, the step runs sharded, every rank reads the result back)
+    # one GPU: the module-level qf.isomp.  Several GPUs: the host-buffer call on the row-sharded handle with a
+    # row-distributed host state (tile-exchange path): every rank uploads its own two row blocks over its own PCIe link,
+    # the state is completed over NVLink, the step runs sharded, every rank downloads its own rows again.  (Pull / NCCL
+    # paths: every rank copies the whole state in and out.)
+    own_rows = world > 1 and handle.comm_mode() == "tile"
+
     def e2e_step():
         if world == 1:
             qf.isomp(Wh, kw["dt"], steps=1, maxit=kw["maxit"], minit=kw["minit"])
         else:
-            handle.isomp(Wh, kw["dt"], 1, maxit=kw["maxit"], minit=kw["minit"])
+            handle.isomp(Wh, kw["dt"], 1, maxit=kw["maxit"], minit=kw["minit"], host_rows="own" if own_rows else "all")
     for _ in range(min(args.warmup, 2)):
         e2e_step()
     barrier()
@@ -487,14 +491,16 @@ def gpu_arm(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
         "config": workload_config(N, mode, kw, its),
         "parallelism": ("single GPU" if world == 1 else
-                        f"{world} GPUs: GEMMs sharded by row blocks, state replicated, {handle.comm_mode()} "
-                        f"all-gather over NVLink peer memory (DESIGN.md section 4)"),
+                        f"{world} GPUs: one simulation sharded by row blocks, data path '{handle.comm_mode()}' over NVLink "
+                        f"peer memory (DESIGN.md section 4)"),
         "iterations_per_sec": value * its,
         "clocks": clocks,
-        "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": 16 * N * N, "d2h_bytes_per_step": 16 * N * N,
-                "note": "one qf.isomp(W_numpy_pinned, dt, steps=1) call per step (on several GPUs: the same host-buffer call "
-                        "on the row-sharded handle, every rank copying in and out); chunked calls reset the warm start "
-                        "like the reference (isospectral.py:430)"},
+        "e2e": {"value": e2e_val, "unit": "steps/s",
+                "h2d_bytes_per_step": 16 * N * N * (1 if (world == 1 or own_rows) else world),
+                "d2h_bytes_per_step": 16 * N * N * (1 if (world == 1 or own_rows) else world),
+                "note": "one qf.isomp(W_numpy_pinned, dt, steps=1) call per step; on several GPUs the host state is "
+                        "row-distributed (every rank copies its own 1/G of the rows in and out, bytes are the sum over ranks) "
+                        "and completed over NVLink; chunked calls reset the warm start like the reference (isospectral.py:430)"},
         "gpu_launches": launches,
         "roofline": roofline,
         "roofline_poisson": roofline_poisson,

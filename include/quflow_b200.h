@@ -39,7 +39,8 @@ typedef enum {
     QF_ERR_CUDA = -2,       /* CUDA runtime / driver failure */
     QF_ERR_NONFINITE = -3,  /* residual became NaN/Inf: scipy.linalg.norm's ValueError, isospectral.py:534 */
     QF_ERR_NCCL = -4,       /* NCCL failure (multi-GPU path) */
-    QF_ERR_UNSUPPORTED = -5
+    QF_ERR_UNSUPPORTED = -5,
+    QF_ERR_COMM = -6        /* multi-GPU peer exchange: a peer rank did not answer within the time limit */
 } qf_status;
 
 /* Statistics of one qf_isomp call.
@@ -60,6 +61,10 @@ typedef struct {
 #define QF_FLAG_MULTISTATE 4u    /* the `batch` members are ONE multi-state (k, N, N) run of the reference: members
                                     1.. are advected by member 0's stream function (select_first, cpu.py:672-674),
                                     tolerance and residual come from member 0 (isospectral.py:444-446, 528-531) */
+
+#define QF_FLAG_HOST_ROWS_OWN 8u  /* qf_isomp_host on a row-sharded handle (tile-exchange path): the host array of this
+                                    rank is read and written on the rank's OWN two row blocks only (a row-distributed
+                                    host state): 1/nranks of the matrix crosses each GPU's PCIe link per direction */
 
 /* Library / device info. Returns the number of CUDA devices (>=0) or a negative qf_status. */
 int qf_device_count(void);
@@ -160,6 +165,11 @@ int qf_step_increment(qf_handle_t h, void *out_dev, void *stream);   /* out = 2 
 int qf_step_update(qf_handle_t h, void *W_dev, const void *F_dev /* may be NULL */, double fscale, void *stream);
 int qf_step_stats(qf_handle_t h, qf_stats *stats, void *stream);
 
+/* The tail of the fixed-point iteration (dW = S + A - A^H, W~ = W + dW, residual partial sums; isospectral.py:499-536)
+ * can run fused into the epilogue of the second GEMM (1) or as a kernel of its own after it (0, default: measured faster,
+ * DESIGN.md).  Also QF_FUSE_POST=1 in the environment at handle creation. */
+int qf_set_fuse_post(qf_handle_t h, int enable);
+
 /* Introspection used by bench.py: number of kernels this library launched since creation
  * of the handle, and per-phase device time of the last qf_profile_iteration call. */
 int64_t qf_launch_count(qf_handle_t h);
@@ -187,30 +197,41 @@ typedef struct {
 int qf_profile_iteration(qf_handle_t h, const void *W_dev, double dt, int reps, qf_phase_times *out, void *stream);
 
 /* ---- multi-GPU (one process per GPU) -------------------------------------------------
- * Row-block sharding of one large-N simulation: rank r owns rows [r*N/G, (r+1)*N/G) of the
- * GEMM outputs; the state is replicated; one NCCL all-gather per GEMM.
- * The 128-byte unique id is created on rank 0 and distributed by the host side
- * (torch.distributed broadcast). */
+ * New functionality: the reference is single-process.  ONE large-N simulation is sharded by row
+ * blocks of the two GEMMs: the N rows are cut into 2*nranks blocks and rank r owns blocks r and 2*nranks-1-r (which
+ * balances the upper-triangular second GEMM).  Ensembles shard per member on the host side and need none of this.
+ *
+ * Peer-memory data paths (default).  Every rank exports a blob of CUDA IPC handles, the host side all-gathers the blobs
+ * (torch.distributed) and every rank imports all of them; the per-iteration communication then runs as plain kernels over
+ * the NVLink peer mappings, inside the step graph:
+ *   tile exchange (qf_comm_mode 5, default when N is divisible by 128*nranks): the tail of the iteration (dW, W~,
+ *     residual) and the update are sharded by tile pairs too.  Per iteration a rank stores the lower tiles of A its peers
+ *     need straight from the GEMM epilogue into their memory, and its new W~ tiles and residual partial sums into every
+ *     peer's copy; two flag exchanges per iteration are all that is left of a collective.  Only the Poisson solve runs
+ *     replicated.
+ *   pull all-gather (qf_comm_mode 2): A and S are completed on every rank by kernels that pull the peers' rows; the tail
+ *     and the update run replicated.
+ * NCCL path (qf_comm_mode 1): the same two gathers as one in-place ncclAllGather each on the compute stream, eager
+ * launches; the 128-byte unique id is created on rank 0 and distributed by the host side. */
 #define QF_UNIQUE_ID_BYTES 128
 int qf_comm_get_unique_id(void *id_out);
 int qf_comm_init(qf_handle_t h, const void *unique_id, int rank, int nranks);
-/* Peer-memory data path (default): every rank exports a blob of CUDA IPC handles (its A/S buffers and flag array),
- * the host side all-gathers the blobs (torch.distributed) and every rank imports all of them.  The per-iteration
- * all-gathers then run as plain kernels that pull the peers' row blocks over NVLink, inside the step graph. */
 #define QF_P2P_BLOB_BYTES 256
 int qf_comm_p2p_export(qf_handle_t h, void *blob_out /* QF_P2P_BLOB_BYTES */);
 int qf_comm_p2p_import(qf_handle_t h, const void *blobs /* nranks * QF_P2P_BLOB_BYTES */, int rank, int nranks);
-/* After the import the default data path is the FUSED one: the GEMM kernel stores every finished tile of its row
- * blocks into all peers' copies of the output as well (plain stores through the NVLink peer mappings), A and S are
- * double-buffered by iteration parity, and one flag barrier per fixed-point iteration replaces the gathers.
- * qf_comm_set_push(h, 0) selects the separate pull kernels instead, qf_comm_set_push(h, 2) one push-copy kernel after
- * both GEMMs (also: QF_COMM=pull|push|pushcopy in the environment). */
-int qf_comm_set_push(qf_handle_t h, int enable);
-/* Data path in use: 0 none (single GPU / emulated ranks), 1 NCCL all-gather, 2 pull kernels, 3 fused GEMM + push,
- * 4 push-copy kernel after the GEMMs. */
+/* After the import: 1 selects the tile exchange, 0 the pull all-gather (also: QF_COMM=tile|pull in the environment). */
+int qf_comm_set_tile(qf_handle_t h, int enable);
+/* Data path in use: 0 none (single GPU / emulated ranks), 1 NCCL all-gather, 2 pull all-gather, 5 tile exchange. */
 int qf_comm_mode(qf_handle_t h);
-/* Test hook: run the row-sharded data path for `nranks` ranks on ONE GPU (all ranks' tiles, no communication). */
+/* Test hook: run the row-sharded GEMM schedule of `nranks` ranks on ONE GPU (all ranks' tiles, no communication). */
 int qf_set_emulated_ranks(qf_handle_t h, int nranks);
+/* Test hooks for the tile-exchange path on ONE GPU: attach G handles of this process (same device, same N) to each other
+ * through plain device pointers, then advance all of them in lock step — every phase of the iteration is enqueued for
+ * all ranks before the next phase of any rank, so no kernel waits for a kernel queued behind it.  Arguments as qf_isomp,
+ * with one W_dev, one stats entry and `steps` iteration counts per rank. */
+int qf_comm_attach_local(qf_handle_t *handles, int G);
+int qf_isomp_lockstep(qf_handle_t *handles, int G, void **W_devs, double dt, int steps, double tol, int maxit, int minit,
+                      unsigned flags, qf_stats *stats, int32_t *iters_per_step, void *stream);
 
 #ifdef __cplusplus
 }

@@ -21,9 +21,11 @@ QF_ERR_CUDA = -2
 QF_ERR_NONFINITE = -3
 QF_ERR_NCCL = -4
 QF_ERR_UNSUPPORTED = -5
+QF_ERR_COMM = -6
 QF_FLAG_COMPSUM = 1
 QF_FLAG_REINITIALIZE = 2
 QF_FLAG_MULTISTATE = 4
+QF_FLAG_HOST_ROWS_OWN = 8
 QF_UNIQUE_ID_BYTES = 128
 QF_P2P_BLOB_BYTES = 256
 QF_BUF_WHALF, QF_BUF_P, QF_BUF_SCRATCH = 0, 1, 2
@@ -88,7 +90,11 @@ SYMBOLS = {
     "qf_set_emulated_ranks": (_i, [_vp, _i]),
     "qf_comm_p2p_export": (_i, [_vp, _vp]),
     "qf_comm_p2p_import": (_i, [_vp, _vp, _i, _i]),
-    "qf_comm_set_push": (_i, [_vp, _i]),
+    "qf_comm_set_tile": (_i, [_vp, _i]),
+    "qf_comm_attach_local": (_i, [ctypes.POINTER(_vp), _i]),
+    "qf_isomp_lockstep": (_i, [ctypes.POINTER(_vp), _i, ctypes.POINTER(_vp), _d, _i, _d, _i, _i, _u, ctypes.POINTER(qf_stats),
+                               ctypes.POINTER(ctypes.c_int32), _vp]),
+    "qf_set_fuse_post": (_i, [_vp, _i]),
     "qf_comm_mode": (_i, [_vp]),
 }
 
@@ -274,14 +280,24 @@ class Handle:
         return out
 
     def isomp(self, W, dt, steps, tol=-1.0, maxit=10, minit=1, compsum=False, reinitialize=False, want_iters=False,
-              multistate=False):
+              multistate=False, host_rows="all"):
         """Advance W in place.  Returns (list of per-member stats dicts, iters array or None).
+
+        ``host_rows="own"`` (numpy W on a row-sharded handle, tile-exchange path): the host array is a row-distributed
+        state — this rank reads and writes its own two row blocks only (``quflow_b200.distributed.row_blocks``), the
+        other rows of the array are left untouched.
 
         Raises ValueError on a non-finite residual (the reference raises it from scipy.linalg.norm).
         """
         self._shape_ok(W)
         flags = ((QF_FLAG_COMPSUM if compsum else 0) | (QF_FLAG_REINITIALIZE if reinitialize else 0)
                  | (QF_FLAG_MULTISTATE if multistate else 0))
+        if host_rows == "own":
+            if not isinstance(W, np.ndarray):
+                raise TypeError("host_rows='own' applies to numpy (host) arrays")
+            flags |= QF_FLAG_HOST_ROWS_OWN
+        elif host_rows != "all":
+            raise ValueError("host_rows must be 'all' or 'own'")
         stats = (qf_stats * self.batch)()
         iters = np.zeros((self.batch, max(steps, 1)), dtype=np.int32) if want_iters else None
         iters_p = iters.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)) if want_iters else None
@@ -379,15 +395,45 @@ class Handle:
         _check(self._lib.qf_comm_p2p_import(self._h, ctypes.create_string_buffer(raw, len(raw)), int(rank), int(nranks)))
 
     def comm_mode(self) -> str:
-        return {0: "none", 1: "nccl", 2: "pull", 3: "push", 4: "pushcopy"}[int(self._lib.qf_comm_mode(self._h))]
+        return {0: "none", 1: "nccl", 2: "pull", 5: "tile"}[int(self._lib.qf_comm_mode(self._h))]
 
-    def comm_set_push(self, enable):
-        """False/0: pull kernels, True/1: fused GEMM + push, 2: one push-copy kernel after the GEMMs."""
-        _check(self._lib.qf_comm_set_push(self._h, int(enable)))
+    def comm_set_tile(self, enable: bool):
+        """True: tile exchange (sharded tail and update, W~ pushed by the owners); False: pull all-gather of A and S."""
+        _check(self._lib.qf_comm_set_tile(self._h, 1 if enable else 0))
+
+    def set_fuse_post(self, enable: bool):
+        """Run the tail of the iteration fused into the epilogue of the second GEMM (True) or as its own kernel (False)."""
+        _check(self._lib.qf_set_fuse_post(self._h, 1 if enable else 0))
 
     def comm_init(self, unique_id: bytes, rank: int, nranks: int):
         buf = ctypes.create_string_buffer(unique_id, QF_UNIQUE_ID_BYTES)
         _check(self._lib.qf_comm_init(self._h, buf, int(rank), int(nranks)))
+
+
+def attach_local(handles):
+    """Test hook: attach handles of this process (same device, same N) to each other as the ranks of one tile-exchange
+    group; drive them with :func:`isomp_lockstep`."""
+    arr = (_vp * len(handles))(*[h._h for h in handles])
+    _check(library().qf_comm_attach_local(arr, len(handles)))
+
+
+def isomp_lockstep(handles, Ws, dt, steps, tol=-1.0, maxit=10, minit=1, compsum=False, reinitialize=False):
+    """Advance the replicated states ``Ws`` (one torch CUDA tensor per rank) of a local tile-exchange group in lock step
+    on one GPU.  Returns (list of stats dicts, iteration counts (G, steps))."""
+    G = len(handles)
+    flags = (QF_FLAG_COMPSUM if compsum else 0) | (QF_FLAG_REINITIALIZE if reinitialize else 0)
+    hs = (_vp * G)(*[h._h for h in handles])
+    ws = (_vp * G)(*[_dev_ptr(W) for W in Ws])
+    stats = (qf_stats * G)()
+    iters = np.zeros((G, max(steps, 1)), dtype=np.int32)
+    rc = library().qf_isomp_lockstep(hs, G, ws, float(dt), int(steps), float(tol), int(maxit), int(minit), flags, stats,
+                                     iters.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _stream_ptr(handles[0].device))
+    if rc == QF_ERR_NONFINITE:
+        raise ValueError("array must not contain infs or NaNs")
+    _check(rc)
+    out = [dict(tol_used=s.tol_used, last_resnorm=s.last_resnorm, total_iterations=int(s.total_iterations),
+                number_of_maxit=int(s.number_of_maxit), steps_done=int(s.steps_done)) for s in stats]
+    return out, iters[:, :steps]
 
 
 def comm_unique_id() -> bytes:

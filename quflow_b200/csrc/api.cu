@@ -85,6 +85,17 @@ extern "C" int qf_create(int N, int batch, int device, qf_handle_t *out)
     };
     if (rc == QF_OK) cu(cudaMalloc(&h->rowpart, rp), "cudaMalloc(rowpart)");
     if (rc == QF_OK) cu(cudaMemset(h->rowpart, 0, rp), "cudaMemset(rowpart)");
+    h->nsd = (N + 15) / 16;
+    h->nsm = (N + 31) / 32;
+    const size_t rp2 = sizeof(double) * (size_t)batch * N * (h->nsd + h->nsm);
+    if (rc == QF_OK) cu(cudaMalloc(&h->rowpart2, rp2), "cudaMalloc(rowpart2)");
+    if (rc == QF_OK) cu(cudaMemset(h->rowpart2, 0, rp2), "cudaMemset(rowpart2)");
+    {
+        // The fused GEMM-2 tail is parity-green but measured slower than the separate k_post launch at every size
+        // (DESIGN.md section 3.4), so it is opt-in: QF_FUSE_POST=1 or qf_set_fuse_post.
+        const char *env = getenv("QF_FUSE_POST");
+        h->fuse_post = (env && env[0] == '1') ? 1 : 0;
+    }
     if (rc == QF_OK) cu(cudaMalloc(&h->ctrl, sizeof(QfCtrl) * batch), "cudaMalloc(ctrl)");
     if (rc == QF_OK) cu(cudaMemset(h->ctrl, 0, sizeof(QfCtrl) * batch), "cudaMemset(ctrl)");
     if (rc == QF_OK) cu(cudaMallocHost(&h->ctrl_host, sizeof(QfCtrl) * batch), "cudaMallocHost(ctrl_host)");
@@ -103,7 +114,7 @@ extern "C" int qf_destroy(qf_handle_t h)
     qf_comm_destroy(h);
     qf_p2p_destroy(h);
     void *ptrs[] = {h->ptab_w, h->ptab_iu, h->ptab_units, h->dW, h->Wh, h->P, h->A, h->S, h->scratch, h->kahan_c,
-                    h->io, h->io2, h->rowpart, h->inner_part, h->ctrl, h->iters_dev};
+                    h->io, h->io2, h->rowpart, h->rowpart2, h->inner_part, h->ctrl, h->iters_dev};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
@@ -112,6 +123,15 @@ extern "C" int qf_destroy(qf_handle_t h)
 }
 
 extern "C" int64_t qf_launch_count(qf_handle_t h) { return h ? h->launches : 0; }
+
+extern "C" int qf_set_fuse_post(qf_handle_t h, int enable)
+{
+    if (!h) { qf_set_error("qf_set_fuse_post: null handle"); return QF_ERR_INVALID; }
+    if (enable && !qf_gemm_can_fuse_post(h)) { qf_set_error("the fused GEMM-2 tail needs the warp-specialised 3M TMA kernel"); return QF_ERR_UNSUPPORTED; }
+    h->fuse_post = enable ? 1 : 0;
+    qf_graph_destroy(h);        // the step graph bakes the choice in
+    return QF_OK;
+}
 
 extern "C" int qf_solve_poisson(qf_handle_t h, const void *W_dev, void *P_dev, void *stream)
 {
@@ -165,8 +185,31 @@ extern "C" int qf_isomp_host(qf_handle_t h, void *W_host, double dt, int steps, 
 {
     if (!h || !W_host) { qf_set_error("qf_isomp_host: null argument"); return QF_ERR_INVALID; }
     QF_ON_DEVICE(h->device);
-    QF_CHECK(ensure_io(h, false));
     const size_t bytes = sizeof(double2) * h->mat_elems * h->batch;
+    if (flags & QF_FLAG_HOST_ROWS_OWN) {
+        // Row-distributed host state (tile-exchange path): this rank's host array is read and written on its own two
+        // row blocks only.  Upload 1/G of the matrix over this GPU's PCIe link, complete the state on every rank over
+        // NVLink, run, download the own rows again.
+        if (!(h->nranks > 1 && h->comm_mode == 5)) { qf_set_error("QF_FLAG_HOST_ROWS_OWN needs the tile-exchange data path"); return QF_ERR_INVALID; }
+        const int G = h->nranks, hb = qf_block_rows(h->N, G);
+        const size_t blk = sizeof(double2) * (size_t)hb * h->N;
+        const int blocks[2] = {h->rank, 2 * G - 1 - h->rank};
+        // everybody has finished reading the previous call's state before anyone overwrites it
+        QF_CHECK(qf_xchg_signal(h, QF_XF_X, false, 0));
+        QF_CHECK(qf_xchg_wait(h, QF_XF_X, false, 0));
+        for (int q = 0; q < 2; ++q)
+            QF_CUDA(cudaMemcpyAsync((char *)h->Wst + blocks[q] * blk, (const char *)W_host + blocks[q] * blk, blk, cudaMemcpyHostToDevice, 0));
+        QF_CHECK(qf_xchg_push_rows(h, 0));
+        QF_CHECK(qf_xchg_signal(h, QF_XF_X, false, 0));
+        QF_CHECK(qf_xchg_wait(h, QF_XF_X, false, 0));
+        int rc = qf_isomp_impl(h, nullptr, dt, steps, tol, maxit, minit, flags, stats, iters_per_step, 0);
+        if (rc != QF_OK && rc != QF_ERR_NONFINITE) return rc;
+        for (int q = 0; q < 2; ++q)
+            QF_CUDA(cudaMemcpyAsync((char *)W_host + blocks[q] * blk, (const char *)h->Wst + blocks[q] * blk, blk, cudaMemcpyDeviceToHost, 0));
+        QF_CUDA(cudaStreamSynchronize(0));
+        return rc;
+    }
+    QF_CHECK(ensure_io(h, false));
     QF_CUDA(cudaMemcpyAsync(h->io, W_host, bytes, cudaMemcpyHostToDevice, 0));
     int rc = qf_isomp(h, h->io, dt, steps, tol, maxit, minit, flags, stats, iters_per_step, 0);
     if (rc != QF_OK && rc != QF_ERR_NONFINITE) return rc;

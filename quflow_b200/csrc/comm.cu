@@ -1,9 +1,16 @@
-// Multi-GPU plumbing: one process per GPU, NCCL over NVLink/NVSwitch.
+// Multi-GPU plumbing: one process per GPU; new functionality (the reference is single-process).
 //
-// New functionality (the reference is single-process).  The state (W, dW, W~, P~) is replicated;
-// the two GEMMs are sharded by row blocks (qf_prow in qf_common.cuh) and each is completed by ONE in-place
-// ncclAllGather of the rank-permuted output.  Everything downstream (k_post, k_control, k_update) runs replicated
-// on identical bytes, so all ranks take the same convergence decisions without a scalar all-reduce.
+// One large-N simulation is sharded by row blocks of the two GEMMs (rank r owns blocks r and 2G-1-r of the 2G blocks).
+// Three data paths complete the iteration, all selected per handle (comm_mode):
+//   5  tile exchange (default, bottom of this file): the tail of the iteration and the update are sharded by tile pairs
+//      as well; per iteration a rank pushes the few lower tiles of A its peers need and its new W~ tiles over NVLink peer
+//      mappings, inside the step graph; the Poisson solve is the only replicated kernel;
+//   2  pull all-gather: A and S (rank-permuted rows) are completed on every rank by kernels that pull the peers' rows;
+//      tail and update run replicated;
+//   1  NCCL: the same gathers as one in-place ncclAllGather each, eager launches (NCCL cannot run inside the body of a
+//      conditional graph node).
+// On every path all ranks evaluate the stopping rule on identical bytes, so they take the same decisions without a
+// scalar all-reduce.
 #include <stdlib.h>
 #include <string.h>
 
@@ -76,58 +83,159 @@ void qf_comm_destroy(qf_handle_s *) {}
 #endif
 
 // ---------------------------------------------------------------------------------------
-// Peer-memory all-gather over NVLink (default data path for the row-sharded GEMM outputs).
-//
-// NCCL cannot live inside the body of a CUDA conditional (WHILE) node and cannot be gated by a device flag, so the
-// per-iteration gathers are done by a plain kernel that PULLS the peers' row blocks through P2P-mapped memory
-// (cudaIpc handles exchanged once by the host side).  Synchronisation is a monotone sequence number per source
-// rank written into every peer's flag array: a rank signals "my rows of gather #seq are complete" at the start of
-// its gather kernel (its GEMM finished earlier on the same stream) and every CTA waits until all sources reached
-// seq before copying.  Write-after-read safety needs no extra handshake: a rank can only start overwriting its
-// rows of A in iteration i+1 after it passed the S gather of iteration i, which required every peer's "S ready"
-// signal, which each peer raises only after its own A gather of iteration i has finished (stream order); the same
-// chain protects S.
+// Peer memory.  Everything a peer ever touches lives in ONE allocation per rank, the arena
+//     [ W~ | A | Wst | rowpart | rowpart2 | flags ]
+// exported as one CUDA IPC handle (plus the separately allocated S for the pull path).  The host side all-gathers the
+// blobs (torch.distributed) and every rank maps every peer once.
 // ---------------------------------------------------------------------------------------
+struct QfArenaLayout {
+    size_t wh, a, wst, part, part2, flags, total;     // byte offsets
+};
+static QfArenaLayout arena_layout(const qf_handle_s *h)
+{
+    auto up = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+    QfArenaLayout l;
+    const size_t mat = up(sizeof(double2) * h->mat_elems);
+    l.wh = 0;
+    l.a = l.wh + mat;
+    l.wst = l.a + mat;
+    l.part = l.wst + mat;
+    l.part2 = l.part + up(sizeof(double) * 2 * (size_t)h->nslots * h->N);
+    l.flags = l.part2 + up(sizeof(double) * (size_t)h->N * (h->nsd + h->nsm));
+    l.total = l.flags + up(sizeof(unsigned long long) * 4 * QF_MAX_RANKS);
+    return l;
+}
+// flags: [0, 2 MAXR) pull all-gather (kind 0 / 1 signalled through one monotone sequence), [2 MAXR, 4 MAXR) tile exchange
+constexpr int QF_FLAGS_XCHG = 2 * QF_MAX_RANKS;
+
 struct QfP2P {
     int nranks = 0, rank = 0;
-    unsigned long long *flags = nullptr;               // [2 * MAXR] local, written by peers ([MAXR..): push barrier)
-    double2 *AS2 = nullptr;                            // [A2 | S2]: odd-iteration copies for the push mode (one allocation)
-    double2 *peerA[QF_MAX_RANKS] = {}, *peerS[QF_MAX_RANKS] = {}, *peerAS2[QF_MAX_RANKS] = {};
-    unsigned long long *peerFlags[QF_MAX_RANKS] = {};
-    // device copies of the pointer tables
-    double2 **peerA_dev = nullptr, **peerS_dev = nullptr;
-    double2 **pushA_dev = nullptr, **pushS_dev = nullptr;   // [2][MAXR], parity-major
-    unsigned long long **peerFlags_dev = nullptr;
+    bool local = false;                                // peers are handles of this process on the same device (tests)
+    char *peerArena[QF_MAX_RANKS] = {};
+    double2 *peerS[QF_MAX_RANKS] = {};
+    // device copies of the pointer tables, QF_MAX_RANKS entries each
+    double2 **peerA_dev = nullptr, **peerS_dev = nullptr, **peerWh_dev = nullptr, **peerWst_dev = nullptr;
+    double **peerPart_dev = nullptr;
+    unsigned long long **peerFlags_dev = nullptr;      // pull path: base of the flag block
+    unsigned long long **peerXFlags_dev = nullptr;     // tile exchange: base + QF_FLAGS_XCHG
+    QfXchg desc;
 };
 
 struct QfP2PBlob {
-    cudaIpcMemHandle_t A, S, flags, AS2;
+    cudaIpcMemHandle_t arena, S;
 };
 static_assert(sizeof(QfP2PBlob) <= QF_P2P_BLOB_BYTES, "blob too large");
+
+static unsigned long long *arena_flags(qf_handle_s *h) { return reinterpret_cast<unsigned long long *>((char *)h->arena + arena_layout(h).flags); }
+
+// Move the peer-visible buffers of the handle into one arena (idempotent).
+static int ensure_arena(qf_handle_s *h)
+{
+    if (h->arena) return QF_OK;
+    if (h->batch != 1) { qf_set_error("row sharding needs batch == 1"); return QF_ERR_INVALID; }
+    const QfArenaLayout l = arena_layout(h);
+    char *base = nullptr;
+    QF_CUDA(cudaMalloc(&base, l.total));
+    QF_CUDA(cudaMemset(base, 0, l.total));
+    QF_CUDA(cudaDeviceSynchronize());
+    qf_graph_destroy(h);                      // the step graph bakes the buffer addresses in
+    cudaFree(h->Wh);
+    cudaFree(h->A);
+    cudaFree(h->rowpart);
+    cudaFree(h->rowpart2);
+    h->arena = base;
+    h->Wh = reinterpret_cast<double2 *>(base + l.wh);
+    h->A = reinterpret_cast<double2 *>(base + l.a);
+    h->Wst = reinterpret_cast<double2 *>(base + l.wst);
+    h->rowpart = reinterpret_cast<double *>(base + l.part);
+    h->rowpart2 = reinterpret_cast<double *>(base + l.part2);
+    return QF_OK;
+}
 
 extern "C" int qf_comm_p2p_export(qf_handle_t h, void *blob_out)
 {
     if (!h || !blob_out) { qf_set_error("qf_comm_p2p_export: null"); return QF_ERR_INVALID; }
     QF_ON_DEVICE(h->device);
-    QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
-    if (!p) {
-        p = new QfP2P();
-        h->p2p = p;
-        QF_CUDA(cudaMalloc(&p->flags, sizeof(unsigned long long) * 2 * QF_MAX_RANKS));
-        QF_CUDA(cudaMemset(p->flags, 0, sizeof(unsigned long long) * 2 * QF_MAX_RANKS));
-        QF_CUDA(cudaMalloc(&p->AS2, sizeof(double2) * 2 * h->mat_elems));
-        QF_CUDA(cudaMemset(p->AS2, 0, sizeof(double2) * 2 * h->mat_elems));
-        h->A2 = p->AS2;
-        h->S2 = p->AS2 + h->mat_elems;
-    }
+    QF_CHECK(ensure_arena(h));
     QfP2PBlob b;
     memset(&b, 0, sizeof(b));
-    QF_CUDA(cudaIpcGetMemHandle(&b.A, h->A));
+    QF_CUDA(cudaIpcGetMemHandle(&b.arena, h->arena));
     QF_CUDA(cudaIpcGetMemHandle(&b.S, h->S));
-    QF_CUDA(cudaIpcGetMemHandle(&b.flags, p->flags));
-    QF_CUDA(cudaIpcGetMemHandle(&b.AS2, p->AS2));
     memset(blob_out, 0, QF_P2P_BLOB_BYTES);
     memcpy(blob_out, &b, sizeof(b));
+    return QF_OK;
+}
+
+static void p2p_release(qf_handle_s *h)
+{
+    QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
+    if (!p) return;
+    if (!p->local)
+        for (int r = 0; r < p->nranks; ++r) {
+            if (r == p->rank) continue;
+            if (p->peerArena[r]) cudaIpcCloseMemHandle(p->peerArena[r]);
+            if (p->peerS[r]) cudaIpcCloseMemHandle(p->peerS[r]);
+        }
+    void *tabs[] = {p->peerA_dev, p->peerS_dev, p->peerWh_dev, p->peerWst_dev, p->peerPart_dev, p->peerFlags_dev, p->peerXFlags_dev};
+    for (void *t : tabs)
+        if (t) cudaFree(t);
+    delete p;
+    h->p2p = nullptr;
+}
+
+// Build the device tables and the QfXchg descriptor from the mapped peers; picks the data path.
+static int p2p_finish(qf_handle_s *h, QfP2P *p)
+{
+    const int nranks = p->nranks, rank = p->rank;
+    const QfArenaLayout l = arena_layout(h);
+    void *tA[QF_MAX_RANKS] = {}, *tS[QF_MAX_RANKS] = {}, *tWh[QF_MAX_RANKS] = {}, *tWst[QF_MAX_RANKS] = {}, *tPart[QF_MAX_RANKS] = {},
+         *tF[QF_MAX_RANKS] = {}, *tXF[QF_MAX_RANKS] = {};
+    for (int r = 0; r < nranks; ++r) {
+        char *base = p->peerArena[r];
+        tA[r] = base + l.a;
+        tS[r] = p->peerS[r];
+        tWh[r] = base + l.wh;
+        tWst[r] = base + l.wst;
+        tPart[r] = base + l.part;
+        tF[r] = base + l.flags;
+        tXF[r] = base + l.flags + sizeof(unsigned long long) * QF_FLAGS_XCHG;
+    }
+    auto upload = [&](void *const *tab, void **dev) -> int {
+        QF_CUDA(cudaMalloc(dev, sizeof(void *) * QF_MAX_RANKS));
+        QF_CUDA(cudaMemcpy(*dev, tab, sizeof(void *) * QF_MAX_RANKS, cudaMemcpyHostToDevice));
+        return QF_OK;
+    };
+    QF_CHECK(upload(tA, (void **)&p->peerA_dev));
+    QF_CHECK(upload(tS, (void **)&p->peerS_dev));
+    QF_CHECK(upload(tWh, (void **)&p->peerWh_dev));
+    QF_CHECK(upload(tWst, (void **)&p->peerWst_dev));
+    QF_CHECK(upload(tPart, (void **)&p->peerPart_dev));
+    QF_CHECK(upload(tF, (void **)&p->peerFlags_dev));
+    QF_CHECK(upload(tXF, (void **)&p->peerXFlags_dev));
+    p->desc.nranks = nranks;
+    p->desc.rank = rank;
+    p->desc.hb = qf_block_rows(h->N, nranks);
+    p->desc.peerWh = p->peerWh_dev;
+    p->desc.peerA = p->peerA_dev;
+    p->desc.peerWst = p->peerWst_dev;
+    p->desc.peerPart = p->peerPart_dev;
+    p->desc.part2_off = (long long)((l.part2 - l.part) / sizeof(double));
+    p->desc.peerFlags = p->peerXFlags_dev;
+    p->desc.myFlags = arena_flags(h) + QF_FLAGS_XCHG;
+    h->rank = rank;
+    h->nranks = nranks;
+    // Data path: tile exchange whenever the ownership blocks are whole 64-row tiles (N divisible by 128 * nranks) and the
+    // warp-specialised 3M TMA GEMM is in use; otherwise the pull all-gather.  QF_COMM=pull|tile overrides.
+    const char *env = getenv("QF_COMM");
+    const bool can_tile = (h->N % (128 * nranks) == 0) && qf_gemm_can_fuse_post(h);
+    bool tile = can_tile;
+    if (env && strcmp(env, "pull") == 0) tile = false;
+    if (env && strcmp(env, "tile") == 0 && !can_tile) {
+        qf_set_error("QF_COMM=tile needs N divisible by 128*nranks (N=%d, nranks=%d) and the default GEMM kernel", h->N, nranks);
+        return QF_ERR_UNSUPPORTED;
+    }
+    h->comm_mode = (nranks > 1) ? (tile ? 5 : 2) : 0;
+    qf_graph_destroy(h);
     return QF_OK;
 }
 
@@ -136,93 +244,83 @@ extern "C" int qf_comm_p2p_import(qf_handle_t h, const void *blobs, int rank, in
     if (!h || !blobs || nranks < 1 || nranks > QF_MAX_RANKS || rank < 0 || rank >= nranks) { qf_set_error("qf_comm_p2p_import: bad arguments"); return QF_ERR_INVALID; }
     if (h->batch != 1) { qf_set_error("row sharding needs batch == 1"); return QF_ERR_INVALID; }
     if (nranks > 1 && h->N % (2 * nranks) != 0) { qf_set_error("row sharding needs N divisible by 2*nranks (N=%d, nranks=%d)", h->N, nranks); return QF_ERR_INVALID; }
-    QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
-    if (!p) { qf_set_error("qf_comm_p2p_import: call qf_comm_p2p_export first"); return QF_ERR_INVALID; }
+    if (!h->arena) { qf_set_error("qf_comm_p2p_import: call qf_comm_p2p_export first"); return QF_ERR_INVALID; }
     QF_ON_DEVICE(h->device);
+    p2p_release(h);                           // a second import replaces the first: no leaked mappings or tables
+    QfP2P *p = new QfP2P();
+    h->p2p = p;
     p->nranks = nranks;
     p->rank = rank;
     for (int r = 0; r < nranks; ++r) {
         if (r == rank) {
-            p->peerA[r] = h->A;
+            p->peerArena[r] = (char *)h->arena;
             p->peerS[r] = h->S;
-            p->peerFlags[r] = p->flags;
-            p->peerAS2[r] = p->AS2;
             continue;
         }
         QfP2PBlob b;
         memcpy(&b, (const char *)blobs + (size_t)r * QF_P2P_BLOB_BYTES, sizeof(b));
-        QF_CUDA(cudaIpcOpenMemHandle((void **)&p->peerA[r], b.A, cudaIpcMemLazyEnablePeerAccess));
+        QF_CUDA(cudaIpcOpenMemHandle((void **)&p->peerArena[r], b.arena, cudaIpcMemLazyEnablePeerAccess));
         QF_CUDA(cudaIpcOpenMemHandle((void **)&p->peerS[r], b.S, cudaIpcMemLazyEnablePeerAccess));
-        QF_CUDA(cudaIpcOpenMemHandle((void **)&p->peerFlags[r], b.flags, cudaIpcMemLazyEnablePeerAccess));
-        QF_CUDA(cudaIpcOpenMemHandle((void **)&p->peerAS2[r], b.AS2, cudaIpcMemLazyEnablePeerAccess));
     }
-    QF_CUDA(cudaMalloc(&p->peerA_dev, sizeof(void *) * QF_MAX_RANKS));
-    QF_CUDA(cudaMalloc(&p->peerS_dev, sizeof(void *) * QF_MAX_RANKS));
-    QF_CUDA(cudaMalloc(&p->peerFlags_dev, sizeof(void *) * QF_MAX_RANKS));
-    QF_CUDA(cudaMemcpy(p->peerA_dev, p->peerA, sizeof(void *) * QF_MAX_RANKS, cudaMemcpyHostToDevice));
-    QF_CUDA(cudaMemcpy(p->peerS_dev, p->peerS, sizeof(void *) * QF_MAX_RANKS, cudaMemcpyHostToDevice));
-    QF_CUDA(cudaMemcpy(p->peerFlags_dev, p->peerFlags, sizeof(void *) * QF_MAX_RANKS, cudaMemcpyHostToDevice));
-    {
-        double2 *tabA[2 * QF_MAX_RANKS] = {}, *tabS[2 * QF_MAX_RANKS] = {};
-        for (int r = 0; r < nranks; ++r) {
-            tabA[r] = p->peerA[r];
-            tabS[r] = p->peerS[r];
-            tabA[QF_MAX_RANKS + r] = p->peerAS2[r];
-            tabS[QF_MAX_RANKS + r] = p->peerAS2[r] + h->mat_elems;
+    return p2p_finish(h, p);
+}
+
+// Test hook: attach G handles that live in THIS process on ONE device to each other (plain device pointers instead of
+// IPC mappings).  Used with qf_isomp_lockstep to run the tile-exchange path for G ranks on a single GPU.
+extern "C" int qf_comm_attach_local(qf_handle_t *hs, int G)
+{
+    if (!hs || G < 1 || G > QF_MAX_RANKS) { qf_set_error("qf_comm_attach_local: bad arguments"); return QF_ERR_INVALID; }
+    for (int r = 0; r < G; ++r)
+        if (!hs[r] || hs[r]->N != hs[0]->N || hs[r]->device != hs[0]->device || hs[r]->batch != 1) {
+            qf_set_error("qf_comm_attach_local: the handles must share N and the device and have batch == 1");
+            return QF_ERR_INVALID;
         }
-        QF_CUDA(cudaMalloc(&p->pushA_dev, sizeof(tabA)));
-        QF_CUDA(cudaMalloc(&p->pushS_dev, sizeof(tabS)));
-        QF_CUDA(cudaMemcpy(p->pushA_dev, tabA, sizeof(tabA), cudaMemcpyHostToDevice));
-        QF_CUDA(cudaMemcpy(p->pushS_dev, tabS, sizeof(tabS), cudaMemcpyHostToDevice));
+    if (G > 1 && hs[0]->N % (2 * G) != 0) { qf_set_error("row sharding needs N divisible by 2*nranks (N=%d, nranks=%d)", hs[0]->N, G); return QF_ERR_INVALID; }
+    QF_ON_DEVICE(hs[0]->device);
+    for (int r = 0; r < G; ++r) QF_CHECK(ensure_arena(hs[r]));
+    for (int r = 0; r < G; ++r) {
+        p2p_release(hs[r]);
+        QfP2P *p = new QfP2P();
+        hs[r]->p2p = p;
+        p->local = true;
+        p->nranks = G;
+        p->rank = r;
+        for (int q = 0; q < G; ++q) {
+            p->peerArena[q] = (char *)hs[q]->arena;
+            p->peerS[q] = hs[q]->S;
+        }
+        QF_CHECK(p2p_finish(hs[r], p));
     }
-    h->rank = rank;
-    h->nranks = nranks;
-    // Default data path: the GEMM epilogue pushes its tiles to the peers (fused all-gather).  QF_COMM=pull keeps the
-    // separate pull kernels (also used when the warp-specialised 3M TMA GEMM is switched off).
-    const char *env = getenv("QF_COMM");
-    bool pull = env && strcmp(env, "pull") == 0;
-    if (!env || (strcmp(env, "pull") != 0 && strcmp(env, "push") != 0)) {
-        // The push hides behind the GEMM only while finished tiles leave early: with fewer than two data-parallel waves
-        // per rank the stream-K schedule completes every tile at the very end and the pull (overlapped with the second
-        // GEMM) is faster (measured: push +3 % at 2 GPUs, -33 % at 8 GPUs, N = 2048).
-        const long long tiles = ((long long)h->N / nranks / 64) * (h->N / 64);
-        pull = tiles < 2LL * h->sm_count;
-    }
-    h->comm_mode = (nranks > 1) ? (pull ? 2 : 3) : 0;
-    if (nranks > 1 && env && strcmp(env, "pushcopy") == 0) h->comm_mode = 4;
     return QF_OK;
 }
 
 void qf_p2p_destroy(qf_handle_s *h)
 {
-    QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
-    if (!p) return;
-    for (int r = 0; r < p->nranks; ++r) {
-        if (r == p->rank) continue;
-        if (p->peerA[r]) cudaIpcCloseMemHandle(p->peerA[r]);
-        if (p->peerS[r]) cudaIpcCloseMemHandle(p->peerS[r]);
-        if (p->peerFlags[r]) cudaIpcCloseMemHandle(p->peerFlags[r]);
-        if (p->peerAS2[r]) cudaIpcCloseMemHandle(p->peerAS2[r]);
+    p2p_release(h);
+    if (h->arena) {
+        cudaFree(h->arena);
+        h->arena = nullptr;
+        h->Wh = h->A = h->Wst = nullptr;       // they lived inside the arena
+        h->rowpart = h->rowpart2 = nullptr;
     }
-    if (p->pushA_dev) cudaFree(p->pushA_dev);
-    if (p->pushS_dev) cudaFree(p->pushS_dev);
-    if (p->AS2) cudaFree(p->AS2);
-    h->A2 = h->S2 = nullptr;
-    if (p->peerA_dev) cudaFree(p->peerA_dev);
-    if (p->peerS_dev) cudaFree(p->peerS_dev);
-    if (p->peerFlags_dev) cudaFree(p->peerFlags_dev);
-    if (p->flags) cudaFree(p->flags);
-    delete p;
-    h->p2p = nullptr;
 }
 
+// ---------------------------------------------------------------------------------------
+// Pull all-gather (comm_mode 2).  NCCL cannot live inside the body of a CUDA conditional (WHILE) node and cannot be
+// gated by a device flag, so the per-iteration gathers are done by a plain kernel that PULLS the peers' row blocks
+// through the peer mappings.  Synchronisation is a monotone sequence number per source rank written into every peer's
+// flag array: a rank signals "my rows of gather #seq are complete" at the start of its gather kernel (its GEMM finished
+// earlier on the same stream) and every CTA waits until all sources reached seq before copying.  Write-after-read
+// safety needs no extra handshake: a rank can only start overwriting its rows of A in iteration i+1 after it passed the
+// S gather of iteration i, which required every peer's "S ready" signal, which each peer raises only after its own A
+// gather of iteration i has finished (stream order); the same chain protects S.
 // kind 0: gather of A (full rows), kind 1: gather of S (only the columns at or right of the diagonal block are
 // needed by k_post).  seq = 2 * gseq + kind + 1 is monotone over the life of the handle.
 // One warp per pulled row, 8 independent 16-byte loads in flight per lane.
+// ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_p2p_allgather(double2 *const *__restrict__ peers, unsigned long long *const *__restrict__ peer_flags,
-                volatile unsigned long long *my_flags, int rank, int nranks, int N, int hb, int kind,
-                const QfCtrl *__restrict__ ctrl, int gated)
+                volatile unsigned long long *my_flags, int rank, int nranks, int N, int hb, int kind, QfCtrl *ctrl, int gated)
 {
     if (gated && !ctrl[0].active) return;
     const unsigned long long seq = 2ull * ctrl[0].gseq + (unsigned long long)kind + 1ull;
@@ -231,9 +329,13 @@ k_p2p_allgather(double2 *const *__restrict__ peers, unsigned long long *const *_
         *reinterpret_cast<volatile unsigned long long *>(peer_flags[threadIdx.x] + rank) = seq;   // "my rows are ready"
     }
     if (threadIdx.x == 0) {
+        const long long t0 = clock64();
         for (int p = 0; p < nranks; ++p) {
             if (p == rank) continue;
-            while (my_flags[p] < seq) __nanosleep(200);
+            while (my_flags[p] < seq) {
+                __nanosleep(200);
+                if (clock64() - t0 > 4000000000ll) { ctrl[0].nonfinite = 2; break; }      // a peer never answered: give up, report
+            }
         }
         __threadfence_system();
     }
@@ -273,7 +375,7 @@ int qf_comm_p2p_allgather(qf_handle_s *h, int kind, bool gated, cudaStream_t st)
 {
     QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
     const int hb = qf_block_rows(h->N, h->nranks);
-    k_p2p_allgather<<<h->sm_count * 2, 256, 0, st>>>(kind == 0 ? p->peerA_dev : p->peerS_dev, p->peerFlags_dev, p->flags, h->rank,
+    k_p2p_allgather<<<h->sm_count * 2, 256, 0, st>>>(kind == 0 ? p->peerA_dev : p->peerS_dev, p->peerFlags_dev, arena_flags(h), h->rank,
                                                  h->nranks, h->N, hb, kind, h->ctrl, gated ? 1 : 0);
     h->launches++;
     QF_CUDA(cudaGetLastError());
@@ -281,72 +383,116 @@ int qf_comm_p2p_allgather(qf_handle_s *h, int kind, bool gated, cudaStream_t st)
 }
 
 // ---------------------------------------------------------------------------------------
-// Push mode (default): the GEMM kernel stores every finished tile of its row blocks into all peers' copies of the
-// output as well (zgemm.cu, k_zgemm3m_ws epilogue), so the all-gather rides on the GEMM and needs no kernel of its
-// own.  What remains is one barrier per fixed-point iteration, after both GEMMs: "my tiles of iteration #seq have
-// landed everywhere" / "everybody's have landed here".
-// Write-after-read safety: A and S are double-buffered by the parity of the iteration counter.  A rank reaches the
-// GEMMs of iteration i+2 only after the barrier of iteration i+1, which needs every peer's signal i+1, which a peer
-// raises after its GEMMs of i+1, i.e. after its k_post of iteration i has finished reading buffer i mod 2.
+// Tile exchange (comm_mode 5): the kernels that store into peer memory are the GEMM (lower tiles of A, zgemm.cu), the
+// tail of the iteration (k_post or the fused GEMM-2 tail: W~ tiles and residual partials) and k_update (W~ of the next
+// step), all in isomp.cu / zgemm.cu.  What lives here is the synchronisation — a signal and a wait kernel per flag kind,
+// separate launches so that the lock-step emulation on one GPU can enqueue every rank's signal before any rank's wait —
+// and the two state exchanges at the ends of a call.
+//   QF_XF_G1  seq = gseq + 1        raised after a rank's first GEMM; consumed inside the peers' tail kernels
+//   QF_XF_X   seq = xseq + 1        raised after a rank's pushes of an exchange; xseq advances in the wait kernel
+// Write-after-read safety: a rank pushes into a peer's W~ / partials / A only after that peer signalled G1 of the same
+// iteration (tail kernels wait for it) or passed the previous exchange barrier (first GEMM), i.e. after the peer's last
+// reads of the previous contents; DESIGN.md section 4 walks through every buffer.
 // ---------------------------------------------------------------------------------------
-__global__ void k_push_barrier(unsigned long long *const *__restrict__ peer_flags, volatile unsigned long long *my_flags,
-                               int rank, int nranks, const QfCtrl *__restrict__ ctrl, int gated)
+const QfXchg *qf_xchg_desc(qf_handle_s *h)
+{
+    QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
+    return (p && h->comm_mode == 5) ? &p->desc : nullptr;
+}
+
+__global__ void k_xchg_signal(const QfXchg x, int kind, const QfCtrl *__restrict__ ctrl, int gated)
 {
     if (gated && !ctrl[0].active) return;
-    const unsigned long long seq = ctrl[0].gseq + 1ull;
+    const unsigned long long seq = (kind == QF_XF_G1 ? ctrl[0].gseq : ctrl[0].xseq) + 1ull;
     const int t = threadIdx.x;
-    if (t < nranks && t != rank) {
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long *>(peer_flags[t] + QF_MAX_RANKS + rank) = seq;
-        while (my_flags[QF_MAX_RANKS + t] < seq) __nanosleep(100);
-        __threadfence_system();
+    if (t < x.nranks && t != x.rank) {
+        __threadfence_system();          // release: this rank's earlier kernels (and their remote stores) come first
+        *reinterpret_cast<volatile unsigned long long *>(x.peerFlags[t] + kind * QF_MAX_RANKS + x.rank) = seq;
     }
 }
 
-int qf_comm_push_barrier(qf_handle_s *h, bool gated, cudaStream_t st)
+__global__ void k_xchg_wait(const QfXchg x, int kind, QfCtrl *ctrl, int gated)
 {
-    QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
-    k_push_barrier<<<1, 32, 0, st>>>(p->peerFlags_dev, p->flags, h->rank, h->nranks, h->ctrl, gated ? 1 : 0);
+    if (gated && !ctrl[0].active) return;
+    const unsigned long long seq = (kind == QF_XF_G1 ? ctrl[0].gseq : ctrl[0].xseq) + 1ull;
+    if (!xchg_wait_flags(x, kind, seq)) ctrl[0].nonfinite = 2;
+    if (kind == QF_XF_X) ctrl[0].xseq = seq;
+}
+
+int qf_xchg_signal(qf_handle_s *h, int kind, bool gated, cudaStream_t st)
+{
+    const QfXchg *x = qf_xchg_desc(h);
+    if (!x) { qf_set_error("qf_xchg_signal: the handle has no tile-exchange communicator"); return QF_ERR_INVALID; }
+    k_xchg_signal<<<1, 32, 0, st>>>(*x, kind, h->ctrl, gated ? 1 : 0);
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;
 }
 
-// Push-copy mode: the GEMMs write their (double-buffered) outputs locally; afterwards one kernel copies this rank's
-// rows of A and of S into every peer's copy with plain remote stores (NVLink writes run faster than the reads of the
-// pull kernels), followed by the same flag barrier.  One warp per (matrix, row): the row is read once from local
-// memory, 8 x 16 bytes per lane in flight, and stored to all peers.
-__global__ void __launch_bounds__(256)
-k_push_rows(double2 *const *__restrict__ peersA, double2 *const *__restrict__ peersS, int rank, int nranks, int N, int hb,
-            const QfCtrl *__restrict__ ctrl, int gated)
+int qf_xchg_wait(qf_handle_s *h, int kind, bool gated, cudaStream_t st)
 {
-    if (gated && !ctrl[0].active) return;
-    const int par = (int)(ctrl[0].gseq & 1ull);
-    double2 *const *pa = peersA + par * QF_MAX_RANKS;
-    double2 *const *ps = peersS + par * QF_MAX_RANKS;
-    const int lane = threadIdx.x & 31;
-    const int rows_per_rank = 2 * hb;
-    const int total = 2 * rows_per_rank;                   // A rows, then S rows
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
-        const int kind = w / rows_per_rank;
-        const int lr = w - kind * rows_per_rank;           // row inside this rank's permuted region
-        const int prow = rank * rows_per_rank + lr;
-        int c0 = 0;
-        if (kind == 1) {                                   // k_post reads S only at columns >= its row (64-aligned tiles)
-            const int blk = lr < hb ? rank : 2 * nranks - 1 - rank;
-            c0 = ((blk * hb) / 64) * 64;
+    const QfXchg *x = qf_xchg_desc(h);
+    if (!x) { qf_set_error("qf_xchg_wait: the handle has no tile-exchange communicator"); return QF_ERR_INVALID; }
+    k_xchg_wait<<<1, 1, 0, st>>>(*x, kind, h->ctrl, gated ? 1 : 0);
+    h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
+// End of a call: every rank holds the up-to-date state on the tile pairs it owns; store them into every peer's Wst.
+// One CTA per 32 x 32 tile pair (bi <= bj), as in k_update.
+__global__ void __launch_bounds__(256)
+k_xchg_push_state(const QfXchg x, int N)
+{
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bi > bj || qf_owner_of_row(bi * 32, x.hb, x.nranks) != x.rank) return;
+    const double2 *__restrict__ mine = x.peerWst[x.rank];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int half = 0; half < (bi == bj ? 1 : 2); ++half) {
+        const int r0 = (half ? bj : bi) * 32, c0 = (half ? bi : bj) * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = r0 + ty + 8 * q, c = c0 + tx;
+            if (r < N && c < N) {
+                const double2 v = mine[(size_t)r * N + c];
+                for (int p = 0; p < x.nranks; ++p)
+                    if (p != x.rank) x.peerWst[p][(size_t)r * N + c] = v;
+            }
         }
-        double2 *const *tab = kind ? ps : pa;
-        const double2 *__restrict__ src = tab[rank] + (size_t)prow * N;
-        for (int c = c0 + lane; c < N; c += 32 * 8) {
+    }
+    __threadfence_system();
+}
+
+int qf_xchg_push_state(qf_handle_s *h, cudaStream_t st)
+{
+    const QfXchg *x = qf_xchg_desc(h);
+    if (!x) { qf_set_error("qf_xchg_push_state: the handle has no tile-exchange communicator"); return QF_ERR_INVALID; }
+    const int nb = (h->N + 31) / 32;
+    k_xchg_push_state<<<dim3(nb, nb), 256, 0, st>>>(*x, h->N);
+    h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
+// Start of a row-sharded host call: this rank uploaded its two row blocks of the state; store them into every peer's Wst.
+__global__ void __launch_bounds__(256)
+k_xchg_push_rows(const QfXchg x, int N)
+{
+    const double2 *__restrict__ mine = x.peerWst[x.rank];
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < 2 * x.hb; w += warps) {
+        const int blk = w < x.hb ? x.rank : 2 * x.nranks - 1 - x.rank;
+        const int row = blk * x.hb + (w < x.hb ? w : w - x.hb);
+        const double2 *__restrict__ s = mine + (size_t)row * N;
+        for (int c = lane; c < N; c += 32 * 8) {
             double2 v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                if (c + 32 * u < N) v[u] = __ldcg(src + c + 32 * u);
-            for (int p = 0; p < nranks; ++p) {
-                if (p == rank) continue;
-                double2 *__restrict__ d = tab[p] + (size_t)prow * N;
+                if (c + 32 * u < N) v[u] = s[c + 32 * u];
+            for (int p = 0; p < x.nranks; ++p) {
+                if (p == x.rank) continue;
+                double2 *__restrict__ d = x.peerWst[p] + (size_t)row * N;
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
                     if (c + 32 * u < N) d[c + 32 * u] = v[u];
@@ -356,44 +502,37 @@ k_push_rows(double2 *const *__restrict__ peersA, double2 *const *__restrict__ pe
     __threadfence_system();
 }
 
-int qf_comm_push_rows(qf_handle_s *h, bool gated, cudaStream_t st)
+int qf_xchg_push_rows(qf_handle_s *h, cudaStream_t st)
 {
-    QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
-    const int hb = qf_block_rows(h->N, h->nranks);
-    k_push_rows<<<h->sm_count * 2, 256, 0, st>>>(p->pushA_dev, p->pushS_dev, h->rank, h->nranks, h->N, hb, h->ctrl, gated ? 1 : 0);
+    const QfXchg *x = qf_xchg_desc(h);
+    if (!x) { qf_set_error("qf_xchg_push_rows: the handle has no tile-exchange communicator"); return QF_ERR_INVALID; }
+    k_xchg_push_rows<<<h->sm_count * 2, 256, 0, st>>>(*x, h->N);
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;
 }
 
-int qf_comm_push_args(qf_handle_s *h, int kind, QfGemmPush *out)
+// Select the data path after qf_comm_p2p_import / qf_comm_attach_local: 0 pull all-gather, 1 tile exchange.
+extern "C" int qf_comm_set_tile(qf_handle_t h, int enable)
 {
-    QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
-    if (!p || !p->pushA_dev) { qf_set_error("push mode needs qf_comm_p2p_import"); return QF_ERR_INVALID; }
-    out->C1 = kind == 0 ? h->A2 : h->S2;
-    out->A1 = kind == 0 ? nullptr : h->A2;      // the second GEMM multiplies the A of the same iteration
-    out->peers = (h->comm_mode == 4) ? nullptr : (kind == 0 ? p->pushA_dev : p->pushS_dev);   // mode 4 copies after the GEMMs
-    out->nranks = h->nranks;
-    out->rank = h->rank;
-    return QF_OK;
-}
-
-// Switch between the fused push (1, default) and the separate pull kernels (0) after qf_comm_p2p_import.
-extern "C" int qf_comm_set_push(qf_handle_t h, int enable)
-{
-    if (!h || !h->p2p || h->nranks < 2 || h->comm_mode < 2) {
-        qf_set_error("qf_comm_set_push: the handle has no peer-memory communicator");
+    if (!h || !h->p2p || h->nranks < 2 || (h->comm_mode != 2 && h->comm_mode != 5)) {
+        qf_set_error("qf_comm_set_tile: the handle has no peer-memory communicator");
         return QF_ERR_INVALID;
     }
-    h->comm_mode = enable == 2 ? 4 : (enable ? 3 : 2);   // 2: push-copy after the GEMMs
+    if (enable && !(h->N % (128 * h->nranks) == 0 && qf_gemm_can_fuse_post(h))) {
+        qf_set_error("the tile-exchange path needs N divisible by 128*nranks (N=%d, nranks=%d) and the default GEMM kernel", h->N, h->nranks);
+        return QF_ERR_UNSUPPORTED;
+    }
+    h->comm_mode = enable ? 5 : 2;
     qf_graph_destroy(h);   // the step graph bakes the data path in
     return QF_OK;
 }
 
-// 0: single GPU / emulated ranks, 1: NCCL all-gather, 2: pull kernels, 3: fused GEMM + push
+// 0: single GPU / emulated ranks, 1: NCCL all-gather, 2: pull all-gather, 5: tile exchange
 extern "C" int qf_comm_mode(qf_handle_t h) { return h ? h->comm_mode : 0; }
 
-// Single-GPU emulation of G ranks (tests): same tile lists, same permuted layout, no communication.
+// Single-GPU emulation of the row-sharded GEMM schedule of G ranks (tests): same tile lists, same permuted layout, no
+// communication.
 extern "C" int qf_set_emulated_ranks(qf_handle_t h, int nranks)
 {
     if (!h || nranks < 1) { qf_set_error("qf_set_emulated_ranks: bad arguments"); return QF_ERR_INVALID; }
@@ -402,5 +541,6 @@ extern "C" int qf_set_emulated_ranks(qf_handle_t h, int nranks)
     if (nranks > 1 && h->N % (2 * nranks) != 0) { qf_set_error("row sharding needs N divisible by 2*nranks"); return QF_ERR_INVALID; }
     h->rank = 0;
     h->nranks = nranks;
+    qf_graph_destroy(h);
     return QF_OK;
 }

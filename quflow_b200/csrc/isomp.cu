@@ -89,29 +89,38 @@ __global__ void k_zero(double2 *X, size_t n2, const QfCtrl *__restrict__ ctrl)
 // dW_ij = d, dW_ji = -conj(d);  deterministic partial row sums of r for the infinity norm:
 //   direct[i][bj] = sum_{j in tile, j >= i} r_ij      mirr[j][bi] = sum_{i in tile, i < j} r_ij
 // It also writes the next iterate W~ = W + dW (both triangles), so no separate pass is needed before the Poisson solve.
+// Tile-exchange path (xg.nranks > 1): a tile pair is processed by the rank that owns row block bi only — the rows of A and
+// S it needs are its own, the transposed tile of A was pushed to it by the owner of row block bj during the first GEMM
+// (the block's first thread waits for every peer's "GEMM 1 complete" flag) — and the new W~ tiles and the residual
+// partials are stored into every peer's copy as well, through the NVLink peer mappings.
 template <bool FORCING>
 __global__ void __launch_bounds__(256)
 k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *__restrict__ dWg, double *__restrict__ rowpart,
-       int N, int nslots, const QfCtrl *__restrict__ ctrl, int hb, int G, const double2 *__restrict__ Wg, double2 *__restrict__ Whg,
-       const double2 *__restrict__ Fg, double fscale, const double2 *__restrict__ Ag1, const double2 *__restrict__ Sg1)
+       int N, int nslots, QfCtrl *__restrict__ ctrl, int hb, int G, const double2 *__restrict__ Wg, double2 *__restrict__ Whg,
+       const double2 *__restrict__ Fg, double fscale, const QfXchg xg)
 {
     const int b = blockIdx.z;
     if (!ctrl[b].active) return;
     const int bi = blockIdx.y, bj = blockIdx.x;
     if (bi > bj) return;
+    const bool xpush = xg.nranks > 1;
+    if (xpush) {
+        if (qf_owner_of_row(bi * TS, xg.hb, xg.nranks) != xg.rank) return;
+        if (threadIdx.x == 0 && !xchg_wait_flags(xg, QF_XF_G1, ctrl[0].gseq + 1ull)) ctrl[0].nonfinite = 2;
+        __syncthreads();
+    }
     __shared__ double2 T[TS][TS + 1];
     __shared__ double2 D[TS][TS + 1];
     __shared__ double R[TS][TS + 1];
     const size_t off = (size_t)b * N * N;
-    const bool odd = Ag1 && (ctrl[b].gseq & 1ull);     // multi-GPU push mode: A and S alternate between two buffers
-    const double2 *A = (odd ? Ag1 : Ag) + off;
-    const double2 *S = (odd ? Sg1 : Sg) + off;
+    const double2 *A = Ag + off;
+    const double2 *S = Sg + off;
     double2 *dW = dWg + off;
     const double2 *W = Wg + off;
     double2 *Wh = Whg + off;
     const double2 *F = FORCING ? Fg + off : nullptr;
-    double *direct = rowpart + ((size_t)b * 2 + 0) * nslots * N;
-    double *mirr = rowpart + ((size_t)b * 2 + 1) * nslots * N;
+    double *direct = rowpart + (size_t)b * nslots * N;                              // [member][N][nslots]
+    double *mirr = rowpart + ((size_t)gridDim.z + b) * nslots * N;                  // second array, same shape
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 
     // A_ji tile, coalesced along i
@@ -119,7 +128,7 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
     for (int q = 0; q < 4; ++q) {
         const int jj = ty + 8 * q;
         const int j = bj * TS + jj, i = bi * TS + tx;
-        T[jj][tx] = (j < N && i < N) ? A[(size_t)qf_prow(j, hb, G) * N + i] : make_double2(0.0, 0.0);
+        T[jj][tx] = (j < N && i < N) ? __ldcg(A + (size_t)qf_prow(j, hb, G) * N + i) : make_double2(0.0, 0.0);
     }
     __syncthreads();
 #pragma unroll
@@ -140,14 +149,23 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
             const double2 old = dW[ij];
             r = zabs(zsub(old, dn));                                  // :526,:534
             dW[ij] = dn;
-            Wh[ij] = zadd(W[ij], dn);                                 // next iterate W~ = W + dW (:481-482)
+            const double2 wh = zadd(W[ij], dn);                       // next iterate W~ = W + dW (:481-482)
+            Wh[ij] = wh;
+            if (xpush)
+                for (int p = 0; p < xg.nranks; ++p)
+                    if (p != xg.rank) xg.peerWh[p][off + ij] = wh;
         }
         D[ii][tx] = d;                                                // without the forcing term: mirrored below
         R[ii][tx] = r;
         // direct row sum over the 32 columns of this tile (fixed shuffle tree => deterministic)
         double s = r;
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (tx == 0 && i < N) direct[(size_t)i * nslots + bj] = s;
+        if (tx == 0 && i < N) {
+            direct[(size_t)i * nslots + bj] = s;
+            if (xpush)
+                for (int p = 0; p < xg.nranks; ++p)
+                    if (p != xg.rank) xg.peerPart[p][(size_t)(direct - rowpart) + (size_t)i * nslots + bj] = s;
+        }
     }
     __syncthreads();
 #pragma unroll
@@ -166,31 +184,43 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
                 rl = R[tx][jj];
             }
             dW[ji] = dm;
-            Wh[ji] = zadd(W[ji], dm);
+            const double2 wh = zadd(W[ji], dm);
+            Wh[ji] = wh;
+            if (xpush)
+                for (int p = 0; p < xg.nranks; ++p)
+                    if (p != xg.rank) xg.peerWh[p][off + ji] = wh;
         }
         double s = rl;
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (tx == 0 && j < N) mirr[(size_t)j * nslots + bi] = s;
+        if (tx == 0 && j < N) {
+            mirr[(size_t)j * nslots + bi] = s;
+            if (xpush)
+                for (int p = 0; p < xg.nranks; ++p)
+                    if (p != xg.rank) xg.peerPart[p][(size_t)(mirr - rowpart) + (size_t)j * nslots + bi] = s;
+        }
     }
+    if (xpush) __threadfence_system();     // remote stores are performed before the kernel (and the flag that follows it) completes
 }
 
 // ------------------------------------------------------------------------------- control
 // Row sums of the residual (one warp per row, slots contiguous), max over rows through an order-independent
 // atomicMax, and the stopping rule evaluated by the last block to finish (ticket counter).
+// The two partial-sum arrays are [member][N][na] and [member][N][nb] (k_post: na = nb = nslots; fused GEMM-2 tail: nsd, nsm).
 __global__ void __launch_bounds__(256)
-k_control(const double *__restrict__ rowpart, int N, int nslots, QfCtrl *ctrl, int maxit, int minit, int nfollow,
-          cudaGraphConditionalHandle cond, int use_cond)
+k_control(const double *__restrict__ parta, int na, const double *__restrict__ partb, int nb, int N, QfCtrl *ctrl, int maxit,
+          int minit, int nfollow, cudaGraphConditionalHandle cond, int use_cond)
 {
     const int b = blockIdx.y;
     QfCtrl &c = ctrl[b];
     if (!c.active) return;
-    const double *direct = rowpart + ((size_t)b * 2 + 0) * nslots * N;
-    const double *mirr = rowpart + ((size_t)b * 2 + 1) * nslots * N;
+    const double *direct = parta + (size_t)b * na * N;
+    const double *mirr = partb + (size_t)b * nb * N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = blockIdx.x * 8 + warp;
     double s = 0.0;
     if (row < N) {
-        for (int k = lane; k < nslots; k += 32) s += direct[(size_t)row * nslots + k] + mirr[(size_t)row * nslots + k];
+        for (int k = lane; k < na; k += 32) s += direct[(size_t)row * na + k];
+        for (int k = lane; k < nb; k += 32) s += mirr[(size_t)row * nb + k];
     }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     __shared__ int last;
@@ -267,11 +297,13 @@ __device__ __forceinline__ double2 kahan_add(double2 w, double2 inc, double2 &kc
     return tt;                                // :586
 }
 
+// Tile-exchange path (xg.nranks > 1): a tile pair is updated by the rank that owns row block bi only (A, dW and the state
+// are valid there); the first iterate of the next step, W~, is stored into every peer's copy as well.
 template <bool COMPSUM, bool FORCING>
 __global__ void __launch_bounds__(256)
 k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__restrict__ Kg, int N, QfCtrl *ctrl,
          int32_t *iters, int steps_cap, int hb, int G, const double2 *__restrict__ dWg, double2 *__restrict__ Whg, int reinit,
-         const double2 *__restrict__ Fg, double fscale, const double2 *__restrict__ Ag1)
+         const double2 *__restrict__ Fg, double fscale, const QfXchg xg)
 {
     const int b = blockIdx.z;
     QfCtrl &c = ctrl[b];
@@ -282,10 +314,11 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
         c.steps_done += 1;
     }
     if (bi > bj) return;
+    const bool xpush = xg.nranks > 1;
+    if (xpush && qf_owner_of_row(bi * TS, xg.hb, xg.nranks) != xg.rank) return;
     __shared__ double2 T[TS][TS + 1];
     const size_t off = (size_t)b * N * N;
-    const bool odd = Ag1 && ((c.gseq - 1ull) & 1ull);   // the buffer of the last executed iteration (push mode)
-    const double2 *A = (odd ? Ag1 : Ag) + off;
+    const double2 *A = Ag + off;
     double2 *W = Wg + off;
     double2 *K = COMPSUM ? Kg + off : nullptr;
     const double2 *dW = dWg + off;
@@ -296,7 +329,7 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
     for (int q = 0; q < 4; ++q) {
         const int jj = ty + 8 * q;
         const int j = bj * TS + jj, i = bi * TS + tx;
-        T[jj][tx] = (j < N && i < N) ? A[(size_t)qf_prow(j, hb, G) * N + i] : make_double2(0.0, 0.0);
+        T[jj][tx] = (j < N && i < N) ? __ldcg(A + (size_t)qf_prow(j, hb, G) * N + i) : make_double2(0.0, 0.0);
     }
     __syncthreads();
     double2 cv[4];
@@ -319,7 +352,11 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
                 if (FORCING) w = zadd(w, zscale(2.0, zscale(fscale, F[ij])));   // FW *= 2; W += FW (:594-596)
             }
             W[ij] = w;
-            Wh[ij] = reinit ? w : zadd(w, dW[ij]);
+            const double2 wh = reinit ? w : zadd(w, dW[ij]);
+            Wh[ij] = wh;
+            if (xpush)
+                for (int p = 0; p < xg.nranks; ++p)
+                    if (p != xg.rank) xg.peerWh[p][off + ij] = wh;
         }
         cv[q] = cm;
     }
@@ -345,9 +382,14 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
                 if (FORCING) w = zadd(w, zscale(2.0, zscale(fscale, F[ji])));
             }
             W[ji] = w;
-            Wh[ji] = reinit ? w : zadd(w, dW[ji]);
+            const double2 wh = reinit ? w : zadd(w, dW[ji]);
+            Wh[ji] = wh;
+            if (xpush)
+                for (int p = 0; p < xg.nranks; ++p)
+                    if (p != xg.rank) xg.peerWh[p][off + ji] = wh;
         }
     }
+    if (xpush) __threadfence_system();
 }
 
 // out = 2 (A - A^H): the increment handed to `callback(W, dW)` just before the update (isospectral.py:547-551)
@@ -473,65 +515,129 @@ int qf_launch_norm_inf(qf_handle_s *h, const double2 *W, cudaStream_t st)
 
 static inline double qf_hbar(int N) { return 2.0 / sqrt((double)N * (double)N - 1.0); }   // quflow/geometry.py:7-9
 
+// One fixed-point iteration, in three phases.  A single rank runs them back to back; the lock-step emulation of the
+// tile-exchange path on one GPU (qf_isomp_lockstep, tests) runs phase A for every rank, then B, then C, so that no kernel
+// ever waits for a kernel that is queued behind it.
+//   A  P~ = eps Delta^-1 W~;  A = P~ W~ (own row blocks)  [tile exchange: lower tiles -> the owner of their column block; signal]
+//   B  S = A P~ with the fused tail: dW, W~, residual partials   [tile exchange: W~ tiles + partials -> every peer; signal]
+//      (legacy all-gather paths and QF_FUSE_POST=0: plain second GEMM, gathers, k_post)
+//   C  [tile exchange: wait for every peer's signal]  stopping rule (k_control)
+enum { QF_PH_A = 1, QF_PH_B = 2, QF_PH_C = 4, QF_PH_ALL = 7 };
+
 int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit, int minit, cudaStream_t st,
-                         cudaEvent_t *ev /* 5 events or null */)
+                         cudaEvent_t *ev /* 5 events or null */, int phases = QF_PH_ALL)
 {
     const int N = h->N;
     const int G = h->nranks;
-    const bool real_comm = (G > 1 && h->comm_mode != 0);
-    const int my = real_comm ? h->rank : -1;          // -1: compute every rank's blocks here (single GPU / emulation)
-    const int hb = qf_block_rows(N, G);
-    if (ev) QF_CUDA(cudaEventRecord(ev[0], st));
-    // W~ = W + dW was written by the previous k_post / k_update (or copied at call start): solve straight from it
+    const bool xmode = (G > 1 && h->comm_mode == 5);                    // tile exchange
+    const bool legacy_comm = (G > 1 && (h->comm_mode == 1 || h->comm_mode == 2));
+    const int my = (xmode || legacy_comm) ? h->rank : -1;             // -1: compute every rank's blocks here (single GPU / emulation)
+    const bool permuted = G > 1 && !xmode;                            // legacy paths store A and S with rank-permuted rows
+    const int hb = permuted ? qf_block_rows(N, G) : N;                // qf_prow arguments of k_post (identity unless permuted)
+    const int Gp = permuted ? G : 1;
+    const bool fused = h->fuse_post && (G == 1 || xmode) && qf_gemm_can_fuse_post(h);
+    const QfXchg *xg = xmode ? qf_xchg_desc(h) : nullptr;
     const bool multistate = h->multistate && h->batch > 1;
-    QF_CHECK(qf_launch_poisson(h, h->Wh, nullptr, h->Wh, h->P, eps, true, st, multistate ? 1 : h->batch));
-    if (multistate) {
-        const size_t n2 = h->mat_elems;
-        k_bcast_p<<<(unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)h->sm_count * 8), 256, 0, st>>>(h->P, n2, h->batch, h->ctrl);
-        h->launches++;
+    if (phases & QF_PH_A) {
+        if (ev) QF_CUDA(cudaEventRecord(ev[0], st));
+        // W~ = W + dW was written by the previous iteration / update (or copied at call start): solve straight from it
+        QF_CHECK(qf_launch_poisson(h, h->Wh, nullptr, h->Wh, h->P, eps, true, st, multistate ? 1 : h->batch));
+        if (multistate) {
+            const size_t n2 = h->mat_elems;
+            k_bcast_p<<<(unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)h->sm_count * 8), 256, 0, st>>>(h->P, n2, h->batch, h->ctrl);
+            h->launches++;
+        }
+        if (ev) QF_CUDA(cudaEventRecord(ev[1], st));
+        QF_CHECK(qf_launch_zgemm(h, h->P, h->Wh, h->A, false, true, my, G, false, st, !permuted, xg));   // rows of A = P~ W~
+        if (xmode) QF_CHECK(qf_xchg_signal(h, QF_XF_G1, true, st));
+        // (Running the A gather on a forked branch next to the second GEMM was measured twice: no gain — the cooperative
+        // GEMM launch waits for the gather's CTAs — so the gathers stay in stream order.)
+        if (legacy_comm) QF_CHECK(h->comm_mode == 2 ? qf_comm_p2p_allgather(h, 0, true, st) : qf_comm_allgather_rows(h, h->A, st));
+        if (ev) QF_CUDA(cudaEventRecord(ev[2], st));
     }
-    if (ev) QF_CUDA(cudaEventRecord(ev[1], st));
-    const bool push = real_comm && (h->comm_mode == 3 || h->comm_mode == 4);   // double-buffered A/S + flag barrier
-    QfGemmPush pa, ps;
-    if (push) {
-        QF_CHECK(qf_comm_push_args(h, 0, &pa));
-        QF_CHECK(qf_comm_push_args(h, 1, &ps));
+    const dim3 gc((N + 7) / 8, multistate ? 1 : h->batch);
+    const int nfollow = multistate ? h->batch - 1 : 0;
+    double *part_direct = h->rowpart2, *part_mirror = h->rowpart2 + (size_t)h->batch * N * h->nsd;
+    if (fused) {
+        if (phases & QF_PH_B) {
+            // GEMM 2 with the fused tail: dW = S + (A - A^H), W~ = W + dW and the residual partials come straight from the
+            // accumulators of the upper tiles of S = A P~ (QfEpiPost); only the stopping rule is left as a launch of its own
+            QfEpiPost epi;
+            epi.A = h->A;
+            epi.dW = h->dW;
+            epi.W = W;
+            epi.Wh = h->Wh;
+            epi.part_direct = part_direct;
+            epi.part_mirror = part_mirror;
+            epi.nsd = h->nsd;
+            epi.nsm = h->nsm;
+            QF_CHECK(qf_launch_zgemm_post(h, h->A, h->P, epi, true, my, G, st, xg));
+            if (ev) QF_CUDA(cudaEventRecord(ev[3], st));
+            if (xmode) QF_CHECK(qf_xchg_signal(h, QF_XF_X, true, st));
+        }
+        if (phases & QF_PH_C) {
+            if (xmode) QF_CHECK(qf_xchg_wait(h, QF_XF_X, true, st));      // every peer's W~ tiles and partials have landed
+            k_control<<<gc, 256, 0, st>>>(part_direct, h->nsd, part_mirror, h->nsm, N, h->ctrl, maxit, minit, nfollow, h->cap_cond,
+                                          h->cap_use_cond);
+            h->launches += 1;
+            if (ev) QF_CUDA(cudaEventRecord(ev[4], st));
+        }
+        QF_CUDA(cudaGetLastError());
+        return QF_OK;
     }
-    QF_CHECK(qf_launch_zgemm(h, h->P, h->Wh, h->A, false, true, my, G, false, st, push ? &pa : nullptr));   // rows of A = P~ W~
-    // (Running the A gather on a forked branch next to the second GEMM was measured twice: no gain — the cooperative
-    // GEMM launch waits for the gather's CTAs — so the gathers stay in stream order.)
-    if (real_comm && !push) QF_CHECK(h->comm_mode == 2 ? qf_comm_p2p_allgather(h, 0, true, st) : qf_comm_allgather_rows(h, h->A, st));
-    if (ev) QF_CUDA(cudaEventRecord(ev[2], st));
-    QF_CHECK(qf_launch_zgemm(h, h->A, h->P, h->S, true, true, my, G, true, st, push ? &ps : nullptr));      // rows of S = A P~ (A rows are local)
-    if (real_comm && !push) QF_CHECK(h->comm_mode == 2 ? qf_comm_p2p_allgather(h, 1, true, st) : qf_comm_allgather_rows(h, h->S, st));
-    if (push && h->comm_mode == 4) QF_CHECK(qf_comm_push_rows(h, true, st));   // copy my rows of A and S into the peers' buffers
-    if (push) QF_CHECK(qf_comm_push_barrier(h, true, st));   // pushed tiles / rows: wait until everybody's have landed
-    if (ev) QF_CUDA(cudaEventRecord(ev[3], st));
     const int nb = (N + TS - 1) / TS;
-    dim3 g(nb, nb, h->batch);
-    k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, G, W, h->Wh, nullptr, 0.0,
-                                     push ? h->A2 : nullptr, push ? h->S2 : nullptr);
-    k_control<<<dim3((N + 7) / 8, multistate ? 1 : h->batch), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit,
-                                                                        multistate ? h->batch - 1 : 0, h->cap_cond, h->cap_use_cond);
-    h->launches += 2;
-    if (ev) QF_CUDA(cudaEventRecord(ev[4], st));
+    const dim3 g(nb, nb, h->batch);
+    const QfXchg solo;
+    if (phases & QF_PH_B) {
+        QF_CHECK(qf_launch_zgemm(h, h->A, h->P, h->S, true, true, my, G, permuted, st, !permuted, nullptr));   // rows of S = A P~ (A rows are local)
+        if (legacy_comm) QF_CHECK(h->comm_mode == 2 ? qf_comm_p2p_allgather(h, 1, true, st) : qf_comm_allgather_rows(h, h->S, st));
+        if (ev) QF_CUDA(cudaEventRecord(ev[3], st));
+        if (xmode) {
+            // the owners of the tile pairs form dW, W~ and the residual partials and push W~ / the partials to every peer
+            k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, Gp, W, h->Wh, nullptr, 0.0, *xg);
+            h->launches++;
+            QF_CHECK(qf_xchg_signal(h, QF_XF_X, true, st));
+        }
+    }
+    if (phases & QF_PH_C) {
+        if (xmode)
+            QF_CHECK(qf_xchg_wait(h, QF_XF_X, true, st));
+        else {
+            k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, Gp, W, h->Wh, nullptr, 0.0, solo);
+            h->launches++;
+        }
+        k_control<<<gc, 256, 0, st>>>(h->rowpart, h->nslots, h->rowpart + (size_t)h->batch * h->nslots * N, h->nslots, N, h->ctrl, maxit,
+                                      minit, nfollow, h->cap_cond, h->cap_use_cond);
+        h->launches++;
+        if (ev) QF_CUDA(cudaEventRecord(ev[4], st));
+    }
     QF_CUDA(cudaGetLastError());
     return QF_OK;
 }
 
-int qf_enqueue_update(qf_handle_s *h, double2 *W, bool compsum, bool reinit, cudaStream_t st)
+// End of a step: W += 2 (A - A^H).  Tile exchange: every rank updates the tile pairs it owns and pushes the next step's
+// first iterate W~ to its peers (phase 1), then waits until everybody's tiles have landed (phase 2).
+int qf_enqueue_update(qf_handle_s *h, double2 *W, bool compsum, bool reinit, cudaStream_t st, int phases = 3)
 {
     const int N = h->N;
     const int nb = (N + TS - 1) / TS;
-    const int hb = qf_block_rows(N, h->nranks);
+    const bool xmode = (h->nranks > 1 && h->comm_mode == 5);
+    const bool permuted = h->nranks > 1 && !xmode;
+    const int hb = permuted ? qf_block_rows(N, h->nranks) : N;
+    const int Gp = permuted ? h->nranks : 1;
     dim3 g(nb, nb, h->batch);
-    const double2 *A1 = (h->nranks > 1 && h->comm_mode >= 3) ? h->A2 : nullptr;
-    if (compsum)
-        k_update<true, false><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks, h->dW, h->Wh, reinit ? 1 : 0, nullptr, 0.0, A1);
-    else
-        k_update<false, false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, h->iters_dev, h->steps_cap, hb, h->nranks, h->dW, h->Wh, reinit ? 1 : 0, nullptr, 0.0, A1);
-    h->launches++;
-    QF_CUDA(cudaGetLastError());
+    const QfXchg solo;
+    const QfXchg xg = xmode ? *qf_xchg_desc(h) : solo;
+    if (phases & 1) {
+        if (compsum)
+            k_update<true, false><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, h->iters_dev, h->steps_cap, hb, Gp, h->dW, h->Wh, reinit ? 1 : 0, nullptr, 0.0, xg);
+        else
+            k_update<false, false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, h->iters_dev, h->steps_cap, hb, Gp, h->dW, h->Wh, reinit ? 1 : 0, nullptr, 0.0, xg);
+        h->launches++;
+        QF_CUDA(cudaGetLastError());
+        if (xmode) QF_CHECK(qf_xchg_signal(h, QF_XF_X, false, st));
+    }
+    if ((phases & 2) && xmode) QF_CHECK(qf_xchg_wait(h, QF_XF_X, false, st));
     return QF_OK;
 }
 
@@ -599,7 +705,7 @@ static int build_step_graph(qf_handle_s *h, double2 *W, double eps, int maxit, i
     h->step_graph = nullptr;
     if (!h->cap_stream) QF_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
 
-    const int N = h->N, B = h->batch;
+    const int B = h->batch;
     const size_t n2 = h->mat_elems;
     QfStepGraph *g = new QfStepGraph();
     g->W = W; g->eps = eps; g->maxit = maxit; g->minit = minit; g->compsum = compsum; g->reinit = reinit;
@@ -616,7 +722,7 @@ static int build_step_graph(qf_handle_s *h, double2 *W, double eps, int maxit, i
     QF_G(cudaGraphCreate(&g->graph, 0));
     QF_G(cudaGraphConditionalHandleCreate(&g->cond, g->graph, 1, cudaGraphCondAssignDefault));
 
-    cudaGraphNode_t n_begin, n_zero, n_while, n_update, last;
+    cudaGraphNode_t n_begin, n_zero, n_while, last;
     QfCtrl *ctrl = h->ctrl;
     int use_cond = 1;
     QF_G(add_kernel_node(&n_begin, g->graph, nullptr, 0, (void *)k_step_begin, dim3(1), dim3(1), ctrl, B, g->cond, use_cond));
@@ -660,20 +766,17 @@ static int build_step_graph(qf_handle_s *h, double2 *W, double eps, int maxit, i
     if (rc != QF_OK) { free_step_graph(g); return rc; }
     QF_G(ce);
 
-    const int nb = (N + TS - 1) / TS;
-    const dim3 gu(nb, nb, B);
-    const double2 *Ap = h->A;
-    double2 *Kp = h->kahan_c;
-    int32_t *iters = h->iters_dev;
-    int steps_cap = h->steps_cap, hb = qf_block_rows(N, h->nranks), G = h->nranks, Nv = N;
-    void *upd = compsum ? (void *)k_update<true, false> : (void *)k_update<false, false>;
-    const double2 *dWp = h->dW;
-    double2 *Whp = h->Wh;
-    int reinit_i = reinit ? 1 : 0;
-    const double2 *Fnull = nullptr;
-    double fzero = 0.0;
-    const double2 *A1p = (h->nranks > 1 && h->comm_mode >= 3) ? h->A2 : nullptr;
-    QF_G(add_kernel_node(&n_update, g->graph, &n_while, 1, upd, gu, dim3(256), Ap, W, Kp, Nv, ctrl, iters, steps_cap, hb, G, dWp, Whp, reinit_i, Fnull, fzero, A1p));
+    // end of the step, again by stream capture: k_update (+ the exchange of the next W~ on the tile-exchange path)
+    {
+        const long long l1 = h->launches;
+        QF_G(cudaStreamBeginCaptureToGraph(h->cap_stream, g->graph, &n_while, nullptr, 1, cudaStreamCaptureModeRelaxed));
+        rc = qf_enqueue_update(h, W, compsum, reinit, h->cap_stream);
+        ce = cudaStreamEndCapture(h->cap_stream, &captured);
+        g->kernels_per_step += (int)(h->launches - l1) - 1;     // the plain k_update is already counted
+        h->launches = l1;
+        if (rc != QF_OK) { free_step_graph(g); return rc; }
+        QF_G(ce);
+    }
     QF_G(cudaGraphInstantiate(&g->exec, g->graph, 0));
 #undef QF_G
     h->step_graph = g;
@@ -681,54 +784,130 @@ static int build_step_graph(qf_handle_s *h, double2 *W, double eps, int maxit, i
     return QF_OK;
 }
 
-extern "C" int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double tol, int maxit, int minit, unsigned flags,
-                        qf_stats *stats, int32_t *iters_per_step, void *stream)
+// ------------------------------------------------------------------------------- one qf_isomp call, in pieces
+// (shared by qf_isomp, the host-buffer entry point and the lock-step emulation of several ranks on one GPU)
+struct IsompCall {
+    double2 *W = nullptr;       // the buffer the kernels advance: the caller's W_dev, or the handle's Wst (tile exchange)
+    double eps = 0.0;
+    int maxit = 0, minit = 0, steps = 0;
+    bool compsum = false, reinit = false, xmode = false;
+};
+
+// Call start (isospectral.py:426-459): work buffers, tolerance from ||W||_inf, control block.  W_dev == nullptr (tile
+// exchange only): the state was already staged in Wst by the caller (row-sharded host upload).
+static int isomp_call_begin(qf_handle_s *h, void *W_dev, double dt, int steps, double tol, int maxit, int minit, unsigned flags,
+                            cudaStream_t st, IsompCall *c)
 {
-    if (!h || !W_dev) { qf_set_error("qf_isomp: null handle or pointer"); return QF_ERR_INVALID; }
     if (minit < 1) { qf_set_error("minit must be at least 1."); return QF_ERR_INVALID; }       // isospectral.py:400
     if (maxit < minit) { qf_set_error("maxit must be at minit."); return QF_ERR_INVALID; }     // isospectral.py:401
     if (steps < 0) { qf_set_error("steps must be non-negative"); return QF_ERR_INVALID; }
-    QF_ON_DEVICE(h->device);
-    cudaStream_t st = (cudaStream_t)stream;
     const int N = h->N, B = h->batch;
     const size_t n2 = h->mat_elems;
-    double2 *W = (double2 *)W_dev;
-    const bool compsum = (flags & QF_FLAG_COMPSUM) != 0;
-    const bool reinit = (flags & QF_FLAG_REINITIALIZE) != 0;
+    c->xmode = h->nranks > 1 && h->comm_mode == 5;
+    if (!W_dev && !c->xmode) { qf_set_error("qf_isomp: null handle or pointer"); return QF_ERR_INVALID; }
+    c->compsum = (flags & QF_FLAG_COMPSUM) != 0;
+    c->reinit = (flags & QF_FLAG_REINITIALIZE) != 0;
+    c->maxit = maxit;
+    c->minit = minit;
+    c->steps = steps;
     const bool multistate = (flags & QF_FLAG_MULTISTATE) != 0 && B > 1;
     if (multistate && h->nranks > 1) { qf_set_error("multi-state runs are single-GPU"); return QF_ERR_UNSUPPORTED; }
     if ((int)multistate != h->multistate) {
         h->multistate = multistate ? 1 : 0;
         qf_graph_destroy(h);        // the step graph bakes the member coupling in
     }
-
     if (steps > h->steps_cap) {
         if (h->iters_dev) QF_CUDA(cudaFree(h->iters_dev));
         h->steps_cap = std::max(steps, 1024);
         QF_CUDA(cudaMalloc(&h->iters_dev, sizeof(int32_t) * (size_t)B * h->steps_cap));
     }
-    if (compsum && !h->kahan_c) QF_CUDA(cudaMalloc(&h->kahan_c, sizeof(double2) * n2 * B));
+    if (c->compsum && !h->kahan_c) QF_CUDA(cudaMalloc(&h->kahan_c, sizeof(double2) * n2 * B));
 
     const double hb = qf_hbar(N);
-    const double eps = dt / (2.0 * hb);                                     // isospectral.py:436-437
+    c->eps = dt / (2.0 * hb);                                               // isospectral.py:436-437
     double mach_eps = 2.220446049250313e-16;                                // np.finfo(complex128).eps
-    if (!compsum) mach_eps = sqrt(mach_eps);                                // :441-443
+    if (!c->compsum) mach_eps = sqrt(mach_eps);                             // :441-443
     const double tol_factor = mach_eps * dt / hb;                           // :448
 
+    c->W = (double2 *)W_dev;
+    if (c->xmode) {
+        // tile exchange: the state lives in the handle's peer-visible buffer for the duration of the call
+        if (W_dev) QF_CUDA(cudaMemcpyAsync(h->Wst, W_dev, sizeof(double2) * n2, cudaMemcpyDeviceToDevice, st));
+        c->W = h->Wst;
+    }
     QF_CUDA(cudaMemsetAsync(h->dW, 0, sizeof(double2) * n2 * B, st));       // :430
-    QF_CUDA(cudaMemcpyAsync(h->Wh, W, sizeof(double2) * n2 * B, cudaMemcpyDeviceToDevice, st));   // W~ = W + 0
-    if (compsum) QF_CUDA(cudaMemsetAsync(h->kahan_c, 0, sizeof(double2) * n2 * B, st));   // :457
-    QF_CHECK(qf_launch_norm_inf(h, W, st));
+    QF_CUDA(cudaMemcpyAsync(h->Wh, c->W, sizeof(double2) * n2 * B, cudaMemcpyDeviceToDevice, st));   // W~ = W + 0
+    if (c->compsum) QF_CUDA(cudaMemsetAsync(h->kahan_c, 0, sizeof(double2) * n2 * B, st));   // :457
+    QF_CHECK(qf_launch_norm_inf(h, c->W, st));
     k_call_begin<<<B, 1, 0, st>>>(h->ctrl, tol, tol_factor, multistate ? 1 : 0);
     h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
 
+// Call end, tile exchange only: every rank holds the tile pairs it owns; complete the state everywhere (phase 1: push +
+// signal, phase 2: wait) and hand it back to the caller's buffer.
+static int isomp_call_gather(qf_handle_s *h, const IsompCall &c, void *W_dev, cudaStream_t st, int phases)
+{
+    if (!c.xmode) return QF_OK;
+    if (phases & 1) {
+        QF_CHECK(qf_xchg_push_state(h, st));
+        QF_CHECK(qf_xchg_signal(h, QF_XF_X, false, st));
+    }
+    if (phases & 2) {
+        QF_CHECK(qf_xchg_wait(h, QF_XF_X, false, st));
+        if (W_dev) QF_CUDA(cudaMemcpyAsync(W_dev, h->Wst, sizeof(double2) * h->mat_elems, cudaMemcpyDeviceToDevice, st));
+    }
+    return QF_OK;
+}
+
+// Statistics of the call (isospectral.py:607-611); synchronises the stream.
+static int isomp_call_collect(qf_handle_s *h, int steps, qf_stats *stats, int32_t *iters_per_step, cudaStream_t st)
+{
+    const int B = h->batch;
+    QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl) * B, cudaMemcpyDeviceToHost, st));
+    if (iters_per_step && steps > 0) {
+        QF_CUDA(cudaMemcpy2DAsync(iters_per_step, sizeof(int32_t) * steps, h->iters_dev, sizeof(int32_t) * h->steps_cap,
+                                  sizeof(int32_t) * steps, B, cudaMemcpyDeviceToHost, st));
+    }
+    QF_CUDA(cudaStreamSynchronize(st));
+    int rc = QF_OK;
+    for (int b = 0; b < B; ++b) {
+        const QfCtrl &c = h->ctrl_host[b];
+        if (stats) {
+            stats[b].tol_used = c.tol;
+            stats[b].last_resnorm = c.resnorm;
+            stats[b].total_iterations = c.total_it;
+            stats[b].number_of_maxit = c.n_maxit;
+            stats[b].nonfinite = c.nonfinite;
+            stats[b].steps_done = c.steps_done;
+        }
+        if (c.nonfinite == 2) {
+            qf_set_error("a peer rank did not answer within the time limit of the tile exchange (member %d, step %d)", b, c.steps_done);
+            rc = QF_ERR_COMM;
+        } else if (c.nonfinite && rc == QF_OK) {
+            qf_set_error("array must not contain infs or NaNs (member %d, step %d)", b, c.steps_done);
+            rc = QF_ERR_NONFINITE;
+        }
+    }
+    return rc;
+}
+
+// W_dev may be NULL on the tile-exchange path only (state already staged in the handle, qf_isomp_host).
+int qf_isomp_impl(qf_handle_s *h, void *W_dev, double dt, int steps, double tol, int maxit, int minit, unsigned flags,
+                  qf_stats *stats, int32_t *iters_per_step, cudaStream_t st)
+{
+    IsompCall c;
+    QF_CHECK(isomp_call_begin(h, W_dev, dt, steps, tol, maxit, minit, flags, st, &c));
+    const int B = h->batch;
+    const size_t n2 = h->mat_elems;
     const dim3 gz((unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)h->sm_count * 8), B);
     QfStepGraph *sg = nullptr;
     if (h->use_graph && steps > 0) {
         // prepare everything that allocates (tile lists) before capturing
         const bool real_comm = (h->nranks > 1 && h->comm_mode != 0);
         QF_CHECK(qf_gemm_prepare(h, real_comm ? h->rank : -1, h->nranks));
-        int rc = build_step_graph(h, W, eps, maxit, minit, compsum, reinit, &sg);
+        int rc = build_step_graph(h, c.W, c.eps, maxit, minit, c.compsum, c.reinit, &sg);
         if (rc != QF_OK) {
             if (!h->graph_warned) fprintf(stderr, "quflow_b200: step graph unavailable (%s); using eager launches\n", qf_last_error());
             h->graph_warned = 1;
@@ -743,41 +922,73 @@ extern "C" int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double
         for (int k = 0; k < steps; ++k) {
             k_step_begin<<<1, 1, 0, st>>>(h->ctrl, B, 0, 0);
             h->launches++;
-            if (reinit) {
+            if (c.reinit) {
                 k_zero<<<gz, 256, 0, st>>>(h->dW, n2, h->ctrl);
                 h->launches++;
             }
-            for (int i = 0; i < maxit; ++i) QF_CHECK(qf_enqueue_iteration(h, W, eps, maxit, minit, st, nullptr));
-            QF_CHECK(qf_enqueue_update(h, W, compsum, reinit, st));
+            for (int i = 0; i < maxit; ++i) QF_CHECK(qf_enqueue_iteration(h, c.W, c.eps, maxit, minit, st, nullptr));
+            QF_CHECK(qf_enqueue_update(h, c.W, c.compsum, c.reinit, st));
         }
     }
-    QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl) * B, cudaMemcpyDeviceToHost, st));
-    if (iters_per_step && steps > 0) {
-        QF_CUDA(cudaMemcpy2DAsync(iters_per_step, sizeof(int32_t) * steps, h->iters_dev, sizeof(int32_t) * h->steps_cap,
-                                  sizeof(int32_t) * steps, B, cudaMemcpyDeviceToHost, st));
-    }
-    QF_CUDA(cudaStreamSynchronize(st));
+    QF_CHECK(isomp_call_gather(h, c, W_dev, st, 3));
+    const int rc = isomp_call_collect(h, steps, stats, iters_per_step, st);
     if (sg) {
         long long max_it = 0;
         for (int b = 0; b < B; ++b) max_it = std::max(max_it, (long long)h->ctrl_host[b].total_it);
         // kernels actually executed by the graphs: per step begin/update (+zero), per executed loop pass the body
-        h->launches += (long long)steps * sg->kernels_per_step + (B == 1 ? max_it : max_it) * sg->kernels_per_iter;
+        h->launches += (long long)steps * sg->kernels_per_step + max_it * sg->kernels_per_iter;
     }
+    return rc;
+}
+
+extern "C" int qf_isomp(qf_handle_t h, void *W_dev, double dt, int steps, double tol, int maxit, int minit, unsigned flags,
+                        qf_stats *stats, int32_t *iters_per_step, void *stream)
+{
+    if (!h || !W_dev) { qf_set_error("qf_isomp: null handle or pointer"); return QF_ERR_INVALID; }
+    QF_ON_DEVICE(h->device);
+    return qf_isomp_impl(h, W_dev, dt, steps, tol, maxit, minit, flags, stats, iters_per_step, (cudaStream_t)stream);
+}
+
+// Test driver: G handles on ONE device attached to each other by qf_comm_attach_local run the tile-exchange path in lock
+// step — every phase is enqueued for all ranks before the next phase of any rank, on one stream, with eager launches — so
+// the ownership, push and flag logic of the multi-GPU path can be checked on a single GPU without kernels that wait for
+// kernels queued behind them (B200_PROFILING.md).  Same arguments as qf_isomp, one W_dev / stats entry per rank.
+extern "C" int qf_isomp_lockstep(qf_handle_t *hs, int G, void **W_devs, double dt, int steps, double tol, int maxit, int minit,
+                                 unsigned flags, qf_stats *stats, int32_t *iters_per_step, void *stream)
+{
+    if (!hs || !W_devs || G < 1 || G > QF_MAX_RANKS) { qf_set_error("qf_isomp_lockstep: bad arguments"); return QF_ERR_INVALID; }
+    for (int r = 0; r < G; ++r)
+        if (!hs[r] || !W_devs[r] || hs[r]->device != hs[0]->device || hs[r]->N != hs[0]->N || hs[r]->batch != 1 ||
+            (G > 1 && (hs[r]->comm_mode != 5 || hs[r]->nranks != G || hs[r]->rank != r))) {
+            qf_set_error("qf_isomp_lockstep: handle %d is not rank %d of a local tile-exchange group of %d", r, r, G);
+            return QF_ERR_INVALID;
+        }
+    QF_ON_DEVICE(hs[0]->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    IsompCall c[QF_MAX_RANKS];
+    const size_t n2 = hs[0]->mat_elems;
+    const dim3 gz((unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)hs[0]->sm_count * 8), 1);
+    for (int r = 0; r < G; ++r) {
+        QF_CHECK(isomp_call_begin(hs[r], W_devs[r], dt, steps, tol, maxit, minit, flags, st, &c[r]));
+        QF_CHECK(qf_gemm_prepare(hs[r], G > 1 ? r : -1, G));
+    }
+    for (int k = 0; k < steps; ++k) {
+        for (int r = 0; r < G; ++r) {
+            k_step_begin<<<1, 1, 0, st>>>(hs[r]->ctrl, 1, 0, 0);
+            if (c[r].reinit) k_zero<<<gz, 256, 0, st>>>(hs[r]->dW, n2, hs[r]->ctrl);
+        }
+        for (int i = 0; i < maxit; ++i)
+            for (int ph : {QF_PH_A, QF_PH_B, QF_PH_C})
+                for (int r = 0; r < G; ++r) QF_CHECK(qf_enqueue_iteration(hs[r], c[r].W, c[r].eps, maxit, minit, st, nullptr, ph));
+        for (int ph : {1, 2})
+            for (int r = 0; r < G; ++r) QF_CHECK(qf_enqueue_update(hs[r], c[r].W, c[r].compsum, c[r].reinit, st, ph));
+    }
+    for (int ph : {1, 2})
+        for (int r = 0; r < G; ++r) QF_CHECK(isomp_call_gather(hs[r], c[r], W_devs[r], st, ph));
     int rc = QF_OK;
-    for (int b = 0; b < B; ++b) {
-        const QfCtrl &c = h->ctrl_host[b];
-        if (stats) {
-            stats[b].tol_used = c.tol;
-            stats[b].last_resnorm = c.resnorm;
-            stats[b].total_iterations = c.total_it;
-            stats[b].number_of_maxit = c.n_maxit;
-            stats[b].nonfinite = c.nonfinite;
-            stats[b].steps_done = c.steps_done;
-        }
-        if (c.nonfinite) {
-            qf_set_error("array must not contain infs or NaNs (member %d, step %d)", b, c.steps_done);
-            rc = QF_ERR_NONFINITE;
-        }
+    for (int r = 0; r < G; ++r) {
+        const int rr = isomp_call_collect(hs[r], steps, stats ? stats + r : nullptr, iters_per_step ? iters_per_step + (size_t)r * steps : nullptr, st);
+        if (rr != QF_OK) rc = rr;
     }
     return rc;
 }
@@ -885,11 +1096,12 @@ extern "C" int qf_step_close_iteration(qf_handle_t h, const void *W_dev, const v
     dim3 g(nb, nb, 1);
     if (F_dev)
         k_post<true><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, N, 1, (const double2 *)W_dev, h->Wh,
-                                        (const double2 *)F_dev, fscale, nullptr, nullptr);
+                                        (const double2 *)F_dev, fscale, QfXchg());
     else
         k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, N, 1, (const double2 *)W_dev, h->Wh, nullptr, 0.0,
-                                         nullptr, nullptr);
-    k_control<<<dim3((N + 7) / 8, 1), 256, 0, st>>>(h->rowpart, N, h->nslots, h->ctrl, maxit, minit, 0, 0, 0);
+                                         QfXchg());
+    k_control<<<dim3((N + 7) / 8, 1), 256, 0, st>>>(h->rowpart, h->nslots, h->rowpart + (size_t)h->nslots * N, h->nslots, N, h->ctrl,
+                                                    maxit, minit, 0, 0, 0);
     h->launches += 2;
     QF_CUDA(cudaGetLastError());
     QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl), cudaMemcpyDeviceToHost, st));
@@ -931,11 +1143,11 @@ extern "C" int qf_step_update(qf_handle_t h, void *W_dev, const void *F_dev, dou
     const int reinit = (h->step_flags & QF_FLAG_REINITIALIZE) ? 1 : 0;
     double2 *W = (double2 *)W_dev;
     if (compsum)
-        k_update<true, false><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, nullptr, 0.0, nullptr);
+        k_update<true, false><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, nullptr, 0.0, QfXchg());
     else if (F_dev)
-        k_update<false, true><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, (const double2 *)F_dev, fscale, nullptr);
+        k_update<false, true><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, (const double2 *)F_dev, fscale, QfXchg());
     else
-        k_update<false, false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, nullptr, 0.0, nullptr);
+        k_update<false, false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, nullptr, 0.0, QfXchg());
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;

@@ -63,11 +63,12 @@ struct QfCtrl {
     long long total_it;
     long long n_maxit;
     unsigned long long gseq;          // executed iterations over the life of the handle (never reset)
+    unsigned long long xseq;          // exchange barriers passed over the life of the handle (tile-exchange path; never reset)
     unsigned long long resmax_bits;   // running max of residual row sums (bit pattern of a non-negative double)
     unsigned int ticket;              // blocks of k_control that have finished
     int active;           // 1 while the fixed-point loop of the current step runs
     int it;               // iterations executed in the current step
-    int nonfinite;        // sticky: residual was NaN/Inf -> everything becomes a no-op
+    int nonfinite;        // sticky: 1 = residual was NaN/Inf, 2 = a peer did not answer in time -> everything becomes a no-op
     int steps_done;
 };
 
@@ -102,12 +103,17 @@ struct qf_handle_s {
     int p_pf = 1;                   // L2 prefetch of the following unit (QF_POISSON_PF, read at handle creation)
     // work matrices, batch * N * N complex128 each
     double2 *dW = nullptr, *Wh = nullptr, *P = nullptr, *A = nullptr, *S = nullptr, *scratch = nullptr;
-    double2 *A2 = nullptr, *S2 = nullptr;   // odd-iteration copies of A and S (multi-GPU push mode only)
+    double2 *Wst = nullptr;       // tile-exchange path: the state W during a call (IPC-visible; W_dev is copied in and out)
+    void *arena = nullptr;        // tile-exchange path: ONE allocation [W~ | A | Wst | rowpart2 | flags] exported to the peers
     double2 *kahan_c = nullptr;   // compensation term (compsum), lazily allocated
     double2 *io = nullptr;        // staging for the *_host entry points, lazily allocated
     double2 *io2 = nullptr;
     // residual partial row sums: [batch][2][nslots][N]
     double *rowpart = nullptr;
+    // the same for the fused GEMM-2 epilogue: direct [batch][N][nsd] then mirrored [batch][N][nsm] (QfEpiPost)
+    double *rowpart2 = nullptr;
+    int nsd = 0, nsm = 0;
+    int fuse_post = 1;            // QF_FUSE_POST=0: separate k_post launch after a plain second GEMM
     double *inner_part = nullptr; // qf_inner partial sums, lazily allocated
     int nslots = 0;
     QfCtrl *ctrl = nullptr;       // [batch] device
@@ -118,9 +124,9 @@ struct qf_handle_s {
     // multi-GPU
     void *nccl_comm = nullptr;
     void *p2p = nullptr;          // QfP2P (comm.cu)
-    int comm_mode = 0;            // 0: none / emulated, 1: NCCL all-gather (eager only), 2: peer-memory pull kernel,
-                                  // 3: GEMM epilogue pushes its tiles to the peers (fused all-gather), double-buffered A/S
-                                  // 4: one push-copy kernel after both GEMMs, double-buffered A/S
+    int comm_mode = 0;            // 0: none / emulated, 1: NCCL all-gather of A and S (eager only), 2: peer-memory pull
+                                  // kernels for A and S, 5: tile exchange (default: sharded fused tail, W~ pushed by owners)
+    void *xchg = nullptr;         // QfXchgHost (comm.cu)
     int rank = 0, nranks = 1;     // nranks > 1 with nccl_comm == nullptr: all ranks emulated on this GPU (tests)
     QfGemmPlan *gemm = nullptr;
     // CUDA-graph execution of a step (isomp.cu)
@@ -151,19 +157,81 @@ int qf_launch_whalf(qf_handle_s *h, const double2 *W, const double2 *dW, double2
 // zgemm.cu
 int qf_gemm_create(qf_handle_s *h);
 void qf_gemm_destroy(qf_handle_s *h);
+// ---------------------------------------------------------------------------------------
+// Tile-exchange data path of the row-sharded multi-GPU run (comm_mode 5, comm.cu).
+// The N rows are cut into 2G blocks of hb rows; rank r owns blocks r and 2G-1-r (balances the upper-triangular second
+// GEMM).  A tile pair {(I,J), (J,I)}, I <= J, belongs to the owner of row block I.  Device-visible description, passed
+// by value to the kernels that store into peer memory; every table has QF_MAX_RANKS entries, the own rank included.
+// ---------------------------------------------------------------------------------------
+#define QF_XF_G1 0      // flag kind: "my GEMM-1 tiles of iteration seq have landed at their consumers"
+#define QF_XF_X 1       // flag kind: "everything I pushed for exchange #seq has landed" (W~ tiles, residual partials, state)
+struct QfXchg {
+    int nranks = 1, rank = 0, hb = 0;
+    double2 *const *peerWh = nullptr;                 // W~ (replicated: every owner pushes its tiles to everybody)
+    double2 *const *peerA = nullptr;                  // A = P~ W~ (own rows + the transposed tiles the fused tail needs)
+    double2 *const *peerWst = nullptr;                // state W (sharded by tile pairs during a call, completed at its end)
+    double *const *peerPart = nullptr;                // residual partial sums of every rank: [rowpart (k_post) | rowpart2 (fused tail)]
+    long long part2_off = 0;                          // offset (doubles) of rowpart2 inside that allocation
+    unsigned long long *const *peerFlags = nullptr;   // [2][QF_MAX_RANKS] per rank, written by the peers
+    unsigned long long *myFlags = nullptr;
+};
+__host__ __device__ __forceinline__ int qf_owner_of_row(int row, int hb, int G)
+{
+    const int blk = row / hb;
+    return blk < G ? blk : 2 * G - 1 - blk;
+}
+
+#ifdef __CUDACC__
+// Spin (one thread) until every peer's flag of `kind` in this rank's flag array has reached seq.  Bounded: a peer that
+// never answers (a failed rank, mismatched launch sequences) must not hang the GPU inside a kernel; after about two
+// seconds the wait gives up and returns false, and the caller marks the run as failed (QfCtrl.nonfinite = 2).
+__device__ __forceinline__ bool xchg_wait_flags(const QfXchg &x, int kind, unsigned long long seq)
+{
+    const volatile unsigned long long *f = x.myFlags + kind * QF_MAX_RANKS;
+    const long long t0 = clock64();
+    bool ok = true;
+    for (int p = 0; p < x.nranks && ok; ++p) {
+        if (p == x.rank) continue;
+        while (f[p] < seq) {
+            __nanosleep(100);
+            if (clock64() - t0 > 4000000000ll) { ok = false; break; }
+        }
+    }
+    __threadfence_system();      // acquire: what the peers stored before raising their flags is visible from here on
+    return ok;
+}
+#endif
+
 // C = A * B.  upper_only: compute only the 64-wide column blocks that intersect the upper triangle
 // (used for S = A P~ which is skew-Hermitian).  rank/nranks: row-block sharding (rank < 0: all blocks).
-// a_permuted: the A operand is itself stored in the rank-permuted row layout (an earlier GEMM's output).
-// push (multi-GPU "push" mode, comm.cu): the output is double-buffered by the parity of the iteration counter
-// (C / push->C1; the A operand likewise: A / push->A1) and every finished tile is also stored into the peers' copies.
-struct QfGemmPush {
-    double2 *C1;                 // output buffer of odd iterations
-    const double2 *A1;           // A operand of odd iterations (nullptr: not double-buffered)
-    double2 *const *peers;       // device table [2][QF_MAX_RANKS] of the peers' output buffers, parity-major
-    int nranks, rank;
-};
+// a_permuted: the A operand is itself stored in the rank-permuted row layout (an earlier GEMM's output; legacy
+// all-gather data paths, comm_mode 1 and 2).  natural: the output keeps its natural row positions (tile-exchange path);
+// with xg (nranks > 1) every finished tile strictly below the diagonal is also stored into the A buffer of the rank
+// that owns the tile's column block: that rank needs it, transposed, in the fused tail of its second GEMM.
 int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 *C, bool upper_only, bool gated,
-                    int rank, int nranks, bool a_permuted, cudaStream_t st, const QfGemmPush *push = nullptr);
+                    int rank, int nranks, bool a_permuted, cudaStream_t st, bool natural = false, const QfXchg *xg = nullptr);
+
+// Fused tail of the fixed-point iteration (isospectral.py:499-536), executed in the epilogue of the second GEMM by the
+// CTA that finishes an upper tile (I <= J) of S = A P~, straight from the accumulators (S never goes to memory):
+//     c = A_ij - conj(A_ji)           conj_subtract_, isospectral.py:66-81
+//     d = S_ij + c                    the new iterate dW_ij (:499,:509);  dW_ji = -conj(d)
+//     res_ij = |dW_old_ij - d|        residual (:526,:534): partial row sums for the infinity norm
+//     W~_ij = W_ij + d,  W~_ji = W_ji - conj(d)     the next midpoint state (:481-482)
+// Residual partial sums are written to fixed slots, one per (row, 16-column group) for the direct elements and one per
+// (column, 32-row group) for the mirrored ones, so the row sums k_control forms do not depend on scheduling.
+struct QfEpiPost {
+    const double2 *A;        // A = P~ W~ of this iteration, natural row layout
+    double2 *dW;             // in: previous iterate; out: new iterate (both triangles)
+    const double2 *W;        // state at the start of the step
+    double2 *Wh;             // out: W + dW (both triangles)
+    double *part_direct;     // [batch][N][nsd]
+    double *part_mirror;     // [batch][N][nsm]
+    int nsd, nsm;
+};
+// S = A P~ restricted to the upper tiles with the fused tail above; A is in natural row layout.
+bool qf_gemm_can_fuse_post(qf_handle_s *h);
+int qf_launch_zgemm_post(qf_handle_s *h, const double2 *A, const double2 *B, const QfEpiPost &epi, bool gated,
+                         int rank, int nranks, cudaStream_t st, const QfXchg *xg = nullptr);
 
 // ---------------------------------------------------------------------------------------
 // Row-block sharding across G ranks (multi-GPU).
@@ -183,10 +251,16 @@ __host__ __device__ __forceinline__ int qf_prow(int i, int hb, int G)
 }
 int qf_comm_allgather_rows(qf_handle_s *h, double2 *M, cudaStream_t st);   // comm.cu
 int qf_comm_p2p_allgather(qf_handle_s *h, int kind, bool gated, cudaStream_t st);   // comm.cu
-int qf_comm_push_rows(qf_handle_s *h, bool gated, cudaStream_t st);                 // comm.cu: mode 4, copy my rows of A and S to the peers
-int qf_comm_push_barrier(qf_handle_s *h, bool gated, cudaStream_t st);              // comm.cu: all peers' pushed tiles have landed
-int qf_comm_push_args(qf_handle_s *h, int kind, QfGemmPush *out);                    // comm.cu: kind 0 = A, 1 = S
 void qf_p2p_destroy(qf_handle_s *h);
+// tile-exchange path (comm.cu)
+const QfXchg *qf_xchg_desc(qf_handle_s *h);                                          // nullptr unless comm_mode == 5
+int qf_xchg_signal(qf_handle_s *h, int kind, bool gated, cudaStream_t st);           // raise my flag of `kind` at every peer
+int qf_xchg_wait(qf_handle_s *h, int kind, bool gated, cudaStream_t st);             // until every peer raised its flag here
+int qf_xchg_push_state(qf_handle_s *h, cudaStream_t st);                             // my tile pairs of Wst -> every peer
+int qf_xchg_push_rows(qf_handle_s *h, cudaStream_t st);                              // my row blocks of Wst -> every peer
+// isomp.cu: qf_isomp with W_dev == NULL allowed on the tile-exchange path (state already staged in h->Wst)
+int qf_isomp_impl(qf_handle_s *h, void *W_dev, double dt, int steps, double tol, int maxit, int minit, unsigned flags,
+                  qf_stats *stats, int32_t *iters_per_step, cudaStream_t st);
 int qf_gemm_prepare(qf_handle_s *h, int rank, int nranks);                  // zgemm.cu: build tile lists (allocates)
 void qf_graph_destroy(qf_handle_s *h);                                      // isomp.cu
 

@@ -485,6 +485,121 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
     }
 }
 
+// ---- fused tail of the fixed-point iteration (QfEpiPost, qf_common.cuh) --------------------------------------------
+// Fragment layout of the 3M warp tile: sub-tile (i, j) holds row  r = row0 + wm*32 + i*8 + g  and the two adjacent columns
+// c = col0 + wn*16 + j*8 + 2t + e.  Direct accesses: the four lanes of a quad cover 128 contiguous bytes of row r.
+// Transposed accesses (A_ji, W_ji, dW_ji, W~_ji): the eight lanes with equal t cover 128 contiguous bytes of row c.
+// Only elements on or above the diagonal (r <= c) are processed; their mirrors are written from the same registers.
+// Tile-exchange path (xg.nranks > 1): the rank that owns the tile pair also stores W~_ij, W~_ji and the residual partials
+// into every peer's copy (plain stores through the NVLink peer mappings), so that after the exchange barrier every rank
+// holds the complete W~ and can evaluate the stopping rule on identical numbers.
+__device__ __forceinline__ void epi_post_tile(const double (&acc)[MI][Cfg<true>::NJ][Cfg<true>::NACC][2], const SkTile &ti, int N,
+                                              int wm, int wn, int g, int t, const QfEpiPost &E, const QfXchg &xg)
+{
+    constexpr int NJ = Cfg<true>::NJ;
+    const size_t moff = (size_t)ti.member * N * N;
+    const double2 *__restrict__ A = E.A + moff;
+    const double2 *__restrict__ W = E.W + moff;
+    double2 *__restrict__ dW = E.dW + moff;
+    double2 *__restrict__ Wh = E.Wh + moff;
+    double *__restrict__ pd = E.part_direct + (size_t)ti.member * N * E.nsd;
+    double *__restrict__ pm = E.part_mirror + (size_t)ti.member * N * E.nsm;
+    const int cbase = ti.col0 + wn * (8 * NJ) + 2 * t;
+    double colsum[NJ][2];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) colsum[j][0] = colsum[j][1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int r = ti.a_row0 + wm * 32 + i * 8 + g;
+        const bool rok = r < ti.row_end;
+        double rowsum = 0.0;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            double2 ad[2], at[2], dwo[2], wd[2], wt[2];
+            bool ok[2];
+            // the ten loads of this sub-tile are issued before the first use
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = cbase + j * 8 + e;
+                ok[e] = rok && c < N && r <= c;
+                if (ok[e]) {
+                    const size_t rc = (size_t)r * N + c, cr = (size_t)c * N + r;
+                    ad[e] = A[rc];
+                    at[e] = __ldcg(A + cr);      // may have been stored by a peer (tile-exchange path): not through L1
+                    dwo[e] = dW[rc];
+                    wd[e] = W[rc];
+                    wt[e] = W[cr];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = cbase + j * 8 + e;
+                if (ok[e]) {
+                    double2 sv = make_double2(acc[i][j][0][e] - acc[i][j][1][e], (acc[i][j][2][e] - acc[i][j][0][e]) - acc[i][j][1][e]);
+                    if (r == c) sv.x = 0.0;                                        // P W P is skew-Hermitian
+                    const double2 cm = zsub(ad[e], zconj(at[e]));                  // isospectral.py:66-81
+                    const double2 d = zadd(sv, cm);                                // :499, :509
+                    const double res = zabs(zsub(dwo[e], d));                      // :526, :534
+                    const size_t rc = (size_t)r * N + c;
+                    dW[rc] = d;
+                    const double2 whd = zadd(wd[e], d);                            // :481-482
+                    Wh[rc] = whd;
+                    rowsum += res;
+                    if (xg.nranks > 1) {
+                        for (int p = 0; p < xg.nranks; ++p)
+                            if (p != xg.rank) xg.peerWh[p][moff + rc] = whd;
+                    }
+                    if (r < c) {
+                        const size_t cr = (size_t)c * N + r;
+                        const double2 dm = make_double2(-d.x, d.y);                // dW_ji = -conj(dW_ij)
+                        dW[cr] = dm;
+                        const double2 whm = zadd(wt[e], dm);
+                        Wh[cr] = whm;
+                        colsum[j][e] += res;                                       // the mirrored element has the same residual
+                        if (xg.nranks > 1) {
+                            for (int p = 0; p < xg.nranks; ++p)
+                                if (p != xg.rank) xg.peerWh[p][moff + cr] = whm;
+                        }
+                    }
+                }
+            }
+        }
+        // row r, columns of this warp: fixed shuffle tree over the quad
+        rowsum += __shfl_xor_sync(0xffffffffu, rowsum, 1);
+        rowsum += __shfl_xor_sync(0xffffffffu, rowsum, 2);
+        if (t == 0 && rok) {
+            const size_t at_ = (size_t)r * E.nsd + ((ti.col0 >> 4) + wn);
+            pd[at_] = rowsum;
+            if (xg.nranks > 1) {
+                const size_t off = (size_t)xg.part2_off + (size_t)(pd - E.part_direct) + at_;
+                for (int p = 0; p < xg.nranks; ++p)
+                    if (p != xg.rank) xg.peerPart[p][off] = rowsum;
+            }
+        }
+    }
+    // column c (= row c of the mirrored half), the 32 rows of this warp: fixed tree over g
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double v = colsum[j][e];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            const int c = cbase + j * 8 + e;
+            if (g == 0 && c < N) {
+                const size_t at_ = (size_t)c * E.nsm + ((ti.a_row0 >> 5) + wm);
+                pm[at_] = v;
+                if (xg.nranks > 1) {
+                    // the peers' partial arrays have the layout of this rank's: [direct | mirrored] in one allocation
+                    const size_t off = (size_t)xg.part2_off + (size_t)(pm - E.part_direct) + at_;
+                    for (int p = 0; p < xg.nranks; ++p)
+                        if (p != xg.rank) xg.peerPart[p][off] = v;
+                }
+            }
+        }
+}
+
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ---- warp-specialised stream-K kernel (3M arithmetic, TMA) ------------------------------------------------------
@@ -495,18 +610,13 @@ __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 
 // at the (named) barrier around the fix-up.
 constexpr int WS_THREADS = GEMM_THREADS + 32;
 
+template <bool POST>
 __global__ void __launch_bounds__(WS_THREADS, 1)
-k_zgemm3m_ws(double2 *__restrict__ C0, double2 *__restrict__ C1, int N, const SkTile *__restrict__ tiles, int ntiles,
-             double2 *__restrict__ ws, int *__restrict__ flags, const QfCtrl *__restrict__ ctrl, int gated, int dbuf,
-             double2 *const *__restrict__ peers, int nranks, int my_rank, const __grid_constant__ CUtensorMap tmA0,
-             const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB)
+k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, int ntiles, double2 *__restrict__ ws,
+             int *__restrict__ flags, const QfCtrl *__restrict__ ctrl, int gated, const __grid_constant__ CUtensorMap tmA,
+             const __grid_constant__ CUtensorMap tmB, const QfEpiPost epi, const QfXchg xg)
 {
-    // Double-buffered output (multi-GPU push mode): the fixed-point iteration number selects the buffer pair, so a
-    // peer may still read the previous iteration's matrices while this one is being produced.
-    const int par = dbuf ? (int)(ctrl[0].gseq & 1ull) : 0;
-    double2 *__restrict__ Cg = par ? C1 : C0;
-    const CUtensorMap *tmAp = par ? &tmA1 : &tmA0;
-    double2 *const *peers_par = peers ? peers + par * QF_MAX_RANKS : nullptr;
+    const CUtensorMap *tmAp = &tmA;
     constexpr bool M3 = true;
     constexpr int STAGES = Cfg<M3>::STAGES, NJ = Cfg<M3>::NJ, NACC = Cfg<M3>::NACC, WN = Cfg<M3>::WN;
     constexpr int BM = Cfg<M3>::BM, BN = Cfg<M3>::BN, BK = Cfg<M3>::BK;
@@ -535,6 +645,7 @@ k_zgemm3m_ws(double2 *__restrict__ C0, double2 *__restrict__ C1, int N, const Sk
     int tile, ka, kb, tail_local;
     uint32_t gk = 0;
 
+    bool g1_seen = false;
     if (warp == GEMM_THREADS / 32) {
         // ===== producer =====
         if (lane == 0) {
@@ -626,18 +737,30 @@ k_zgemm3m_ws(double2 *__restrict__ C0, double2 *__restrict__ C1, int N, const Sk
                     ++peer;
                 }
             }
-            gemm_store_tile<M3>(acc, Cg + moff, N, ti.c_row0, ti.c_row0 + (ti.row_end - ti.a_row0), ti.col0, wm, wn, g, t);
-            // fused all-gather: the finished tile also goes to the same place in every peer's copy of C, as plain
-            // stores through NVLink peer mappings; they drain while the next tile is being multiplied
-            if (peers_par) {
-                for (int pr = 0; pr < nranks; ++pr) {
-                    if (pr == my_rank) continue;
-                    gemm_store_tile<M3>(acc, peers_par[pr] + moff, N, ti.c_row0, ti.c_row0 + (ti.row_end - ti.a_row0), ti.col0, wm, wn, g, t);
+            if (POST) {
+                // GEMM 2 of the fixed-point iteration: dW, W~ and the residual partials straight from the accumulators
+                if (xg.nranks > 1 && !g1_seen) {
+                    // the transposed A tiles this rank needs were pushed by their owners during THEIR first GEMM: wait (once
+                    // per CTA) until every peer has signalled that its GEMM 1 of this iteration is complete
+                    if (tid == 0) xchg_wait_flags(xg, QF_XF_G1, ctrl[0].gseq + 1ull);
+                    consumer_bar_sync();
+                    g1_seen = true;
                 }
+                epi_post_tile(acc, ti, N, wm, wn, g, t, epi, xg);
+                continue;
+            }
+            gemm_store_tile<M3>(acc, Cg + moff, N, ti.c_row0, ti.c_row0 + (ti.row_end - ti.a_row0), ti.col0, wm, wn, g, t);
+            // tile-exchange path, GEMM 1: a tile strictly below the diagonal is needed (transposed) by the rank that owns
+            // its column block; it goes there as plain stores through the NVLink peer mapping while the next tile is
+            // being multiplied
+            if (xg.nranks > 1 && ti.col0 + BN <= ti.a_row0) {
+                const int oc = qf_owner_of_row(ti.col0, xg.hb, xg.nranks);
+                if (oc != xg.rank)
+                    gemm_store_tile<M3>(acc, xg.peerA[oc] + moff, N, ti.c_row0, ti.c_row0 + (ti.row_end - ti.a_row0), ti.col0, wm, wn, g, t);
             }
         }
     }
-    if (peers_par) __threadfence_system();   // remote tiles are performed before the kernel (and the flag that follows it) completes
+    if (xg.nranks > 1) __threadfence_system();   // remote stores are performed before the kernel (and the flag that follows it) completes
 }
 
 }   // namespace
@@ -669,7 +792,7 @@ struct QfGemmPlan {
     double2 *ws = nullptr;      // [max_ctas][32][256] partial tiles
     int *flags = nullptr;       // [max_ctas]
     // cached tile lists keyed by (upper_only, rank, nranks, a_permuted); rank < 0 = all ranks (single-GPU emulation)
-    struct List { int upper, rank, nranks, aperm, ntiles; SkTile *dev; };
+    struct List { int upper, rank, nranks, aperm, natural, ntiles; SkTile *dev; };
     std::vector<List> lists;
     int BM() const { return m3 ? Cfg<true>::BM : Cfg<false>::BM; }
     int BN() const { return m3 ? Cfg<true>::BN : Cfg<false>::BN; }
@@ -693,7 +816,8 @@ int qf_gemm_create(qf_handle_s *h)
     QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<false>::SMEM));
     QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM));
     QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM));
-    QF_CUDA(cudaFuncSetAttribute(k_zgemm3m_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm3m_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm3m_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM));
     {
         const char *w = getenv("QF_GEMM_WS");
         p->warp_spec = !(w && w[0] == '0');
@@ -756,11 +880,16 @@ static int make_tmap(qf_handle_s *h, const double2 *base, int box_rows, CUtensor
     return QF_OK;
 }
 
-static int get_tile_list(qf_handle_s *h, bool upper_only, int rank, int nranks, bool a_permuted, const SkTile **dev, int *ntiles)
+// natural: output rows keep their natural positions (single GPU: always true in effect; tile-exchange path); otherwise the
+// output uses the rank-permuted row layout of the legacy all-gather paths (qf_prow).
+static int get_tile_list(qf_handle_s *h, bool upper_only, int rank, int nranks, bool a_permuted, bool natural, const SkTile **dev,
+                         int *ntiles)
 {
     QfGemmPlan *p = h->gemm;
+    if (nranks == 1) { natural = true; a_permuted = false; }      // one rank: the permutation is the identity
     for (auto &l : p->lists)
-        if (l.upper == (int)upper_only && l.rank == rank && l.nranks == nranks && l.aperm == (int)a_permuted) {
+        if (l.upper == (int)upper_only && l.rank == rank && l.nranks == nranks && l.aperm == (int)a_permuted &&
+            l.natural == (int)natural) {
             *dev = l.dev;
             *ntiles = l.ntiles;
             return QF_OK;
@@ -784,12 +913,12 @@ static int get_tile_list(qf_handle_s *h, bool upper_only, int rank, int nranks, 
                     for (int r0 = rb; r0 < re; r0 += BMv)
                         for (int c0 = cg; c0 < std::min(N, cg + CG); c0 += BNv) {
                             if (upper_only && (c0 + BNv - 1 < r0)) continue;
-                            tl.push_back(SkTile{b, r0, qf_prow(r0, hb, nranks), c0, std::min(re, r0 + BMv),
+                            tl.push_back(SkTile{b, r0, natural ? r0 : qf_prow(r0, hb, nranks), c0, std::min(re, r0 + BMv),
                                                 a_permuted ? qf_prow(r0, hb, nranks) : r0, 0, 0});
                         }
             }
         }
-    QfGemmPlan::List l{(int)upper_only, rank, nranks, (int)a_permuted, (int)tl.size(), nullptr};
+    QfGemmPlan::List l{(int)upper_only, rank, nranks, (int)a_permuted, (int)natural, (int)tl.size(), nullptr};
     QF_CUDA(cudaMalloc(&l.dev, sizeof(SkTile) * std::max<size_t>(tl.size(), 1)));
     QF_CUDA(cudaMemcpy(l.dev, tl.data(), sizeof(SkTile) * tl.size(), cudaMemcpyHostToDevice));
     p->lists.push_back(l);
@@ -802,8 +931,14 @@ int qf_gemm_prepare(qf_handle_s *h, int rank, int nranks)
 {
     const SkTile *t;
     int n;
-    QF_CHECK(get_tile_list(h, false, rank, nranks, false, &t, &n));
-    QF_CHECK(get_tile_list(h, true, rank, nranks, true, &t, &n));
+    if (h->comm_mode == 5 || nranks == 1) {
+        QF_CHECK(get_tile_list(h, false, rank, nranks, false, true, &t, &n));
+        QF_CHECK(get_tile_list(h, true, rank, nranks, false, true, &t, &n));    // fused GEMM-2 tail
+    }
+    if (h->comm_mode != 5) {
+        QF_CHECK(get_tile_list(h, false, rank, nranks, false, false, &t, &n));
+        QF_CHECK(get_tile_list(h, true, rank, nranks, true, false, &t, &n));
+    }
     return QF_OK;
 }
 
@@ -838,13 +973,13 @@ static cudaError_t launch_sk(qf_handle_s *h, bool tma, int G, const double2 *A, 
 
 // rank/nranks select the row blocks (see qf_prow); rank < 0 computes every rank's blocks (emulation on one GPU).
 int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 *C, bool upper_only, bool gated,
-                    int rank, int nranks, bool a_permuted, cudaStream_t st, const QfGemmPush *push)
+                    int rank, int nranks, bool a_permuted, cudaStream_t st, bool natural, const QfXchg *xg)
 {
     const int N = h->N;
     QfGemmPlan *p = h->gemm;
     const SkTile *tiles;
     int ntiles;
-    QF_CHECK(get_tile_list(h, upper_only, rank, nranks, a_permuted, &tiles, &ntiles));
+    QF_CHECK(get_tile_list(h, upper_only, rank, nranks, a_permuted, natural, &tiles, &ntiles));
     if (ntiles == 0) return QF_OK;
     const int BK = p->BK();
     const int KT = (N + BK - 1) / BK;
@@ -856,15 +991,12 @@ int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 
     CUtensorMap tmA, tmB;
     memset(&tmA, 0, sizeof(tmA));
     memset(&tmB, 0, sizeof(tmB));
-    CUtensorMap tmA1;
-    memset(&tmA1, 0, sizeof(tmA1));
     if (tma) {
         QF_CHECK(make_tmap(h, A, p->BM(), &tmA));
         QF_CHECK(make_tmap(h, B, BK, &tmB));   // B boxes: BK rows x 8 complex
-        QF_CHECK(make_tmap(h, (push && push->A1) ? push->A1 : A, p->BM(), &tmA1));
     }
-    if (push && !(p->m3 && tma && p->warp_spec)) {
-        qf_set_error("the fused GEMM + peer push needs the warp-specialised 3M TMA kernel (QF_GEMM_3M/QF_GEMM_WS/QF_GEMM_LOAD defaults)");
+    if (xg && !(p->m3 && tma && p->warp_spec)) {
+        qf_set_error("the tile-exchange data path needs the warp-specialised 3M TMA kernel (QF_GEMM_3M/QF_GEMM_WS/QF_GEMM_LOAD defaults)");
         return QF_ERR_UNSUPPORTED;
     }
     if (p->m3 && tma && p->warp_spec) {
@@ -878,14 +1010,59 @@ int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 
         attr[0].val.cooperative = 1;
         cfg.attrs = attr;
         cfg.numAttrs = p->cooperative ? 1 : 0;
-        double2 *C1 = push ? push->C1 : C;
-        double2 *const *peers = push ? push->peers : nullptr;
-        QF_CUDA(cudaLaunchKernelEx(&cfg, k_zgemm3m_ws, C, C1, N, tiles, ntiles, p->ws, p->flags, (const QfCtrl *)h->ctrl,
-                                   gated ? 1 : 0, push ? 1 : 0, peers, push ? push->nranks : 1, push ? push->rank : 0, tmA, tmA1, tmB));
+        const QfEpiPost none = {};
+        const QfXchg solo;
+        QF_CUDA(cudaLaunchKernelEx(&cfg, k_zgemm3m_ws<false>, C, N, tiles, ntiles, p->ws, p->flags, (const QfCtrl *)h->ctrl,
+                                   gated ? 1 : 0, tmA, tmB, none, xg ? *xg : solo));
     } else {
         QF_CUDA(p->m3 ? launch_sk<true>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st)
                       : launch_sk<false>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st));
     }
+    h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
+// Second GEMM of the fixed-point iteration with the fused tail (QfEpiPost): upper tiles of S = A P~ only, nothing is
+// written for S itself.  Needs the warp-specialised 3M TMA kernel; the caller falls back to qf_launch_zgemm + k_post
+// (QF_FUSE_POST=0) otherwise.
+bool qf_gemm_can_fuse_post(qf_handle_s *h)
+{
+    QfGemmPlan *p = h->gemm;
+    return p && p->m3 && p->tma && p->warp_spec && h->N >= 8;
+}
+
+int qf_launch_zgemm_post(qf_handle_s *h, const double2 *A, const double2 *B, const QfEpiPost &epi, bool gated, int rank,
+                         int nranks, cudaStream_t st, const QfXchg *xg)
+{
+    const int N = h->N;
+    QfGemmPlan *p = h->gemm;
+    if (!qf_gemm_can_fuse_post(h)) { qf_set_error("the fused GEMM-2 tail needs the warp-specialised 3M TMA kernel"); return QF_ERR_UNSUPPORTED; }
+    const SkTile *tiles;
+    int ntiles;
+    QF_CHECK(get_tile_list(h, true, rank, nranks, false, true, &tiles, &ntiles));
+    if (ntiles == 0) return QF_OK;
+    const int BK = p->BK();
+    const int KT = (N + BK - 1) / BK;
+    const long long T = (long long)ntiles * KT;
+    const int G = (int)std::min<long long>(p->max_ctas, std::max<long long>(1, T / (128 / BK)));
+    CUtensorMap tmA, tmB;
+    QF_CHECK(make_tmap(h, A, p->BM(), &tmA));
+    QF_CHECK(make_tmap(h, B, BK, &tmB));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G);
+    cfg.blockDim = dim3(WS_THREADS);
+    cfg.dynamicSmemBytes = Geo<true>::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p->cooperative ? 1 : 0;
+    double2 *nullC = nullptr;
+    const QfXchg solo;
+    QF_CUDA(cudaLaunchKernelEx(&cfg, k_zgemm3m_ws<true>, nullC, N, tiles, ntiles, p->ws, p->flags, (const QfCtrl *)h->ctrl,
+                               gated ? 1 : 0, tmA, tmB, epi, xg ? *xg : solo));
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;

@@ -2,10 +2,10 @@
 
 New functionality relative to the reference (which is single-process):
 
-* ``attach_row_sharding(handle, dist)`` — shard ONE large-N simulation by row blocks of the two GEMMs across the
-  ranks of the default process group.  The NCCL communicator lives inside libquflow_b200.so (so the all-gathers are
-  enqueued on the same stream as the kernels, with no Python in the loop); torch.distributed only carries the
-  128-byte ncclUniqueId from rank 0 to the other ranks.
+* ``attach_row_sharding(handle, dist)`` — shard ONE large-N simulation by row blocks across the ranks of the default
+  process group.  All per-iteration communication runs inside libquflow_b200.so, on the compute stream, with no Python
+  in the loop (peer-memory kernels, or NCCL); torch.distributed only carries the set-up blobs (CUDA IPC handles or the
+  128-byte ncclUniqueId).
 * ``member_slice(k, rank, world)`` / ``isomp_ensemble_sharded`` — shard an ensemble per member: no data-path
   collective at all, one gather of the results at the end.
 """
@@ -50,17 +50,16 @@ def broadcast_unique_id(dist, make_id=None) -> bytes:
 
 
 def attach_row_sharding(handle, dist, mode=None):
-    """Make ``handle`` (batch == 1) run its GEMMs row-sharded over the default process group.
+    """Make ``handle`` (batch == 1) run one simulation row-sharded over the default process group.
 
-    mode "p2p" (default): "push" when every rank's first GEMM has at least two data-parallel waves of tiles,
-    else "pull" (decided in csrc/comm.cu).
-    mode "push": the GEMM kernel itself stores every finished tile into all peers'
-    copies of its output over NVLink peer mappings (fused GEMM + all-gather), A and S are double-buffered by iteration
-    parity and one flag barrier per fixed-point iteration is all that is left of the collective.  torch.distributed
-    only all-gathers one 256-byte blob of CUDA IPC handles per rank at set-up.
-    mode "pull": one pull kernel after each GEMM, inside the step graph.
+    mode "p2p" (default): peer-memory data path chosen by the library — "tile" whenever N is divisible by 128*world,
+    else "pull" (csrc/comm.cu).  torch.distributed only all-gathers one 256-byte blob of CUDA IPC handles per rank at
+    set-up; everything per iteration runs inside the step graph as kernels over the NVLink peer mappings.
+    mode "tile": tile exchange — GEMMs, the tail of the iteration and the update are all sharded; per iteration a rank
+    pushes the lower tiles of A its peers need (from the GEMM epilogue) and its new W~ tiles; Poisson runs replicated.
+    mode "pull": the GEMM outputs A and S are completed on every rank by pull kernels; tail and update run replicated.
     mode "nccl": one in-place ncclAllGather per GEMM, issued by the library on the compute stream (eager launches;
-    NCCL cannot run inside the conditional graph body).  Select with QF_COMM=push|pull|nccl.
+    NCCL cannot run inside the conditional graph body).  Select with QF_COMM=tile|pull|nccl.
     """
     import os
     world, rank = dist.get_world_size(), dist.get_rank()
@@ -74,9 +73,9 @@ def attach_row_sharding(handle, dist, mode=None):
     else:
         blobs = [None] * world
         dist.all_gather_object(blobs, handle.p2p_export())
-        handle.p2p_import(blobs, rank, world)       # picks push or pull by the tile count per rank (csrc/comm.cu)
-        if mode in ("push", "pull", "pushcopy"):
-            handle.comm_set_push({"pull": 0, "push": 1, "pushcopy": 2}[mode])
+        handle.p2p_import(blobs, rank, world)       # picks tile or pull (csrc/comm.cu)
+        if mode in ("tile", "pull"):
+            handle.comm_set_tile(mode == "tile")
         dist.barrier()              # every rank has mapped every peer before anybody starts signalling
     return handle
 

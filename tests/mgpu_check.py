@@ -1,5 +1,12 @@
 """Multi-GPU parity check, launched by torchrun (one rank per GPU):
-row-sharded isomp over NCCL must reproduce the single-GPU result and the CPU oracle."""
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 tests/mgpu_check.py [--big]
+
+The row-sharded run must reproduce the single-GPU run (<= 1e-13, identical per-step iteration counts), every rank must
+hold bit-identical states, and the CPU oracle must agree (<= 1e-12 at N = 256 ... 1024; with --big also R(2048, 42), the
+configuration bench.py times, 10 steps).  Covers the three data paths (tile exchange, pull all-gather, NCCL), both forms
+of the tail of the iteration (separate kernel / fused into the GEMM-2 epilogue) on the tile path, the row-distributed
+host-buffer call, and the per-member ensemble sharding."""
 import os
 import sys
 
@@ -13,16 +20,21 @@ sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
 import quflow_b200 as qf  # noqa: E402
 from quflow_b200._cuda import Handle  # noqa: E402
-from quflow_b200.distributed import attach_row_sharding, member_slice  # noqa: E402
+from quflow_b200.distributed import attach_row_sharding, member_slice, row_blocks  # noqa: E402
 
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    big = "--big" in sys.argv
     ok = True
-    for N, steps, mode in ((256, 10, "push"), (256, 10, "pull"), (256, 10, "pushcopy"), (256, 10, "nccl"), (1024, 12, "push"),
-                           (1024, 6, "pull"), (1024, 12, "pushcopy")):
+    nsmall = 128 * world                     # smallest size the tile exchange accepts
+    cases = [(nsmall, 10, "tile", False), (nsmall, 10, "tile", True), (nsmall, 10, "pull", False), (nsmall, 8, "nccl", False),
+             (1024, 12, "tile", False), (1024, 6, "pull", False)]
+    if big:
+        cases += [(2048, 10, "tile", False), (2048, 4, "tile", True)]
+    for N, steps, mode, fuse in cases:
         W0 = oracle.random_skewherm(N, 42)
         dt = 0.25 * qf.hbar(N)
         solo = Handle(N, 1, local)
@@ -30,22 +42,37 @@ def main():
         rs, its_s = solo.isomp(Ws, dt, steps, want_iters=True)
         shard = Handle(N, 1, local)
         attach_row_sharding(shard, dist, mode=mode)
+        if fuse:
+            shard.set_fuse_post(True)
         Wd = torch.from_numpy(W0).cuda()
         rd, its_d = shard.isomp(Wd, dt, steps, want_iters=True)
         Wm = Wd.cpu().numpy()
         err = np.linalg.norm(Wm - Ws) / np.linalg.norm(Ws)
         same_its = list(its_s[0]) == list(its_d[0])
-        # all ranks must hold bit-identical states (replicated control flow)
+        # all ranks must hold bit-identical states (every element is computed once and copied, or computed replicated)
         gathered = [None] * world
         dist.all_gather_object(gathered, Wm.tobytes())
         identical = all(g == gathered[0] for g in gathered)
-        msg = f"rank {rank}: N={N} mode={mode} sharded-vs-solo rel.err={err:.2e} iterations equal={same_its} ranks identical={identical}"
-        if N <= 256:
+        msg = (f"rank {rank}: N={N} mode={shard.comm_mode()} fused_tail={fuse} sharded-vs-solo rel.err={err:.2e} "
+               f"iterations equal={same_its} ranks identical={identical}")
+        if N <= 1024 or rank == 0:
             rec = {}
             Wref = oracle.isomp(W0.copy(), dt, steps, record=rec)
             eo = np.linalg.norm(Wm - Wref) / np.linalg.norm(Wref)
             msg += f" vs-oracle={eo:.2e}"
             ok = ok and eo < 1e-12 and list(its_d[0]) == rec["iterations"]
+        if mode == "tile" and not fuse:
+            # row-distributed host buffers: every rank passes its own array and reads / writes its own row blocks only
+            Wh = W0.copy()
+            mine = np.zeros(N, dtype=bool)
+            for a, b in row_blocks(N, world)[rank]:
+                mine[a:b] = True
+            Wh[~mine] = np.nan                      # rows of other ranks must never be read ...
+            shard.isomp(Wh, dt, steps, host_rows="own")
+            eh = np.linalg.norm(Wh[mine] - Wm[mine]) / np.linalg.norm(Wm[mine])
+            untouched = bool(np.isnan(Wh[~mine]).all())           # ... nor written
+            msg += f" host-rows-own err={eh:.2e} other rows untouched={untouched}"
+            ok = ok and eh == 0.0 and untouched
         print(msg, flush=True)
         ok = ok and err < 1e-13 and same_its and identical
         dist.barrier()

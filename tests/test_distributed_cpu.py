@@ -63,8 +63,8 @@ class _FakeHandle:
     def p2p_import(self, blobs, rank, world):
         self.calls.append(("import", [b[0] for b in blobs], rank, world))
 
-    def comm_set_push(self, enable):
-        self.calls.append(("push", bool(enable)))          # 0 pull, 1 fused push, 2 push-copy
+    def comm_set_tile(self, enable):
+        self.calls.append(("tile", bool(enable)))          # True: tile exchange, False: pull all-gather
 
     def comm_init(self, uid, rank, world):
         self.calls.append(("nccl", len(uid), rank, world))
@@ -87,11 +87,11 @@ def _worker(rank, world, port, out):
         # row sharding set-up: every rank imports every rank's IPC blob in rank order; the data path follows `mode`
         h = _FakeHandle(1024, rank)
         qd.attach_row_sharding(h, dist, mode="p2p")
-        ok = ok and h.calls == [("import", list(range(world)), rank, world)]          # default: the library picks push/pull
-        for mode, want in (("push", True), ("pull", False), ("pushcopy", True)):
+        ok = ok and h.calls == [("import", list(range(world)), rank, world)]          # default: the library picks tile/pull
+        for mode, want in (("tile", True), ("pull", False)):
             h = _FakeHandle(1024, rank)
             qd.attach_row_sharding(h, dist, mode=mode)
-            ok = ok and h.calls == [("import", list(range(world)), rank, world), ("push", want)]
+            ok = ok and h.calls == [("import", list(range(world)), rank, world), ("tile", want)]
         try:
             qd.attach_row_sharding(_FakeHandle(1002, rank), dist)                    # N not divisible by 2 * world
             ok = False

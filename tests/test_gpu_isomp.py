@@ -337,6 +337,76 @@ def test_row_sharded_data_path_emulated_on_one_gpu(qf, N, G):
     h1.close(); hG.close()
 
 
+@pytest.mark.parametrize("N,G,fuse", [(256, 2, False), (256, 2, True), (512, 4, False), (1024, 8, False), (1024, 8, True)])
+def test_tile_exchange_ranks_in_lockstep_on_one_gpu(qf, N, G, fuse):
+    """The tile-exchange multi-GPU path (comm_mode 5) for G ranks on ONE GPU: G handles attached to each other through
+    plain device pointers are advanced in lock step (every phase enqueued for all ranks before the next phase of any
+    rank).  Exercises tile-pair ownership, the lower-tile push of the first GEMM, the sharded tail (separate kernel or
+    fused into the GEMM-2 epilogue) with its W~ / residual-partial pushes, the flag protocol, the sharded update and the
+    state gather at the end of the call.  Bar: every rank bit-identical to every other rank, <= 1e-13 from the single-GPU
+    run (the stream-K split of a tile, hence its summation order, depends on the rank's tile list), identical per-step
+    iteration counts, oracle parity."""
+    import torch
+    from quflow_b200._cuda import Handle
+    from quflow_b200._cuda.binding import attach_local, isomp_lockstep
+    W0 = oracle.random_skewherm(N, 31)
+    dt = 0.25 * qf.hbar(N)
+    steps = 12
+    solo = Handle(N)
+    if fuse:
+        solo.set_fuse_post(True)
+    Ws = W0.copy()
+    _, its_solo = solo.isomp(Ws, dt, steps, want_iters=True)
+    hs = [Handle(N) for _ in range(G)]
+    attach_local(hs)
+    assert all(h.comm_mode() == "tile" for h in hs)
+    for h in hs:
+        h.set_fuse_post(fuse)
+    Wd = [torch.from_numpy(W0).cuda() for _ in range(G)]
+    stats, iters = isomp_lockstep(hs, Wd, dt, steps)
+    out = [w.cpu().numpy() for w in Wd]
+    for r in range(G):
+        assert list(iters[r]) == list(its_solo[0])
+        assert np.array_equal(out[r], out[0])               # ranks bit-identical
+    assert relfro(out[0], Ws) < 1e-13                       # the single-GPU run
+    assert np.abs(out[0] + out[0].conj().T).max() == 0.0
+    rec = {}
+    Wref = oracle.isomp(W0.copy(), dt, steps, record=rec)
+    assert list(iters[0]) == rec["iterations"]
+    assert relfro(out[0], Wref) < 1e-12
+    # a second call on the same handles (flags and sequence numbers carry over), with the compensated update
+    Wd2 = [torch.from_numpy(W0).cuda() for _ in range(G)]
+    isomp_lockstep(hs, Wd2, dt, 5, compsum=True)
+    Wc = W0.copy()
+    solo.isomp(Wc, dt, 5, compsum=True)
+    assert relfro(Wd2[G - 1].cpu().numpy(), Wc) < 1e-13
+    assert np.array_equal(Wd2[G - 1].cpu().numpy(), Wd2[0].cpu().numpy())
+    solo.close()
+    for h in hs:
+        h.close()
+
+
+@pytest.mark.parametrize("N", [32, 100, 257, 512])
+def test_fused_gemm2_tail_matches_separate_kernel(qf, N):
+    """The tail of the iteration fused into the GEMM-2 epilogue (qf_set_fuse_post) against the separate k_post launch and
+    the oracle: same iteration counts, <= 1e-12 (the residual partial sums are added in a different order)."""
+    from quflow_b200._cuda import Handle
+    W0 = oracle.random_skewherm(N, 5)
+    dt = 0.25 * qf.hbar(N)
+    ha, hb = Handle(N), Handle(N)
+    hb.set_fuse_post(True)
+    Wa, Wb = W0.copy(), W0.copy()
+    _, ia = ha.isomp(Wa, dt, 20, want_iters=True)
+    _, ib = hb.isomp(Wb, dt, 20, want_iters=True)
+    assert list(ia[0]) == list(ib[0])
+    assert relfro(Wb, Wa) < 1e-13
+    assert np.abs(Wb + Wb.conj().T).max() == 0.0
+    rec = {}
+    Wref = oracle.isomp(W0.copy(), dt, 20, record=rec)
+    assert list(ib[0]) == rec["iterations"] and relfro(Wb, Wref) < 1e-12
+    ha.close(); hb.close()
+
+
 def test_multi_gpu_row_sharding_nccl(qf):
     """Real NCCL path: torchrun with 2 ranks (skipped on a single-GPU box)."""
     import subprocess
