@@ -334,7 +334,7 @@ k_p2p_allgather(double2 *const *__restrict__ peers, unsigned long long *const *_
             if (p == rank) continue;
             while (my_flags[p] < seq) {
                 __nanosleep(200);
-                if (clock64() - t0 > 4000000000ll) { ctrl[0].nonfinite = 2; break; }      // a peer never answered: give up, report
+                if (clock64() - t0 > 20000000000ll) { ctrl[0].nonfinite = 2; break; }     // a peer never answered: give up, report
             }
         }
         __threadfence_system();
@@ -415,7 +415,7 @@ __global__ void k_xchg_wait(const QfXchg x, int kind, QfCtrl *ctrl, int gated)
 {
     if (gated && !ctrl[0].active) return;
     const unsigned long long seq = (kind == QF_XF_G1 ? ctrl[0].gseq : ctrl[0].xseq) + 1ull;
-    if (!xchg_wait_flags(x, kind, seq)) ctrl[0].nonfinite = 2;
+    if (ctrl[0].nonfinite != 2 && !xchg_wait_flags(x, kind, seq)) ctrl[0].nonfinite = 2;
     if (kind == QF_XF_X) ctrl[0].xseq = seq;
 }
 

@@ -106,7 +106,7 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
     const bool xpush = xg.nranks > 1;
     if (xpush) {
         if (qf_owner_of_row(bi * TS, xg.hb, xg.nranks) != xg.rank) return;
-        if (threadIdx.x == 0 && !xchg_wait_flags(xg, QF_XF_G1, ctrl[0].gseq + 1ull)) ctrl[0].nonfinite = 2;
+        if (threadIdx.x == 0 && ctrl[0].nonfinite != 2 && !xchg_wait_flags(xg, QF_XF_G1, ctrl[0].gseq + 1ull)) ctrl[0].nonfinite = 2;
         __syncthreads();
     }
     __shared__ double2 T[TS][TS + 1];

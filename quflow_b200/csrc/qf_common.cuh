@@ -183,8 +183,9 @@ __host__ __device__ __forceinline__ int qf_owner_of_row(int row, int hb, int G)
 
 #ifdef __CUDACC__
 // Spin (one thread) until every peer's flag of `kind` in this rank's flag array has reached seq.  Bounded: a peer that
-// never answers (a failed rank, mismatched launch sequences) must not hang the GPU inside a kernel; after about two
-// seconds the wait gives up and returns false, and the caller marks the run as failed (QfCtrl.nonfinite = 2).
+// never answers (a failed rank, mismatched launch sequences) must not hang the GPU inside a kernel; after about ten
+// seconds the wait gives up and returns false, and the caller marks the run as failed (QfCtrl.nonfinite = 2); once
+// a run is marked failed the later waits return at once.
 __device__ __forceinline__ bool xchg_wait_flags(const QfXchg &x, int kind, unsigned long long seq)
 {
     const volatile unsigned long long *f = x.myFlags + kind * QF_MAX_RANKS;
@@ -194,7 +195,7 @@ __device__ __forceinline__ bool xchg_wait_flags(const QfXchg &x, int kind, unsig
         if (p == x.rank) continue;
         while (f[p] < seq) {
             __nanosleep(100);
-            if (clock64() - t0 > 4000000000ll) { ok = false; break; }
+            if (clock64() - t0 > 20000000000ll) { ok = false; break; }
         }
     }
     __threadfence_system();      // acquire: what the peers stored before raising their flags is visible from here on

@@ -742,7 +742,7 @@ k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, 
                 if (xg.nranks > 1 && !g1_seen) {
                     // the transposed A tiles this rank needs were pushed by their owners during THEIR first GEMM: wait (once
                     // per CTA) until every peer has signalled that its GEMM 1 of this iteration is complete
-                    if (tid == 0) xchg_wait_flags(xg, QF_XF_G1, ctrl[0].gseq + 1ull);
+                    if (tid == 0 && ctrl[0].nonfinite != 2) xchg_wait_flags(xg, QF_XF_G1, ctrl[0].gseq + 1ull);
                     consumer_bar_sync();
                     g1_seen = true;
                 }
