@@ -590,7 +590,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=2048)
+    ap.add_argument("--n", "--size", dest="n", type=int, default=2048,
+                    help="matrix size N (use --size under torch.distributed.run, whose own parser claims --n*)")
     ap.add_argument("--mode", default="natural", choices=["natural", "profile"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="single", choices=["single", "ensemble"],

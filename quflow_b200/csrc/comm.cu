@@ -222,6 +222,12 @@ static int p2p_finish(qf_handle_s *h, QfP2P *p)
     p->desc.part2_off = (long long)((l.part2 - l.part) / sizeof(double));
     p->desc.peerFlags = p->peerXFlags_dev;
     p->desc.myFlags = arena_flags(h) + QF_FLAGS_XCHG;
+    {
+        // ranks may legitimately be seconds apart (host work between calls): the bound only has to end a real hang
+        const char *t = getenv("QF_COMM_TIMEOUT_S");
+        const double secs = t ? atof(t) : 30.0;
+        p->desc.timeout_cycles = (long long)((secs > 0.0 ? secs : 30.0) * 2.0e9);
+    }
     h->rank = rank;
     h->nranks = nranks;
     // Data path: tile exchange whenever the ownership blocks are whole 64-row tiles (N divisible by 128 * nranks) and the
@@ -320,7 +326,8 @@ void qf_p2p_destroy(qf_handle_s *h)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_p2p_allgather(double2 *const *__restrict__ peers, unsigned long long *const *__restrict__ peer_flags,
-                volatile unsigned long long *my_flags, int rank, int nranks, int N, int hb, int kind, QfCtrl *ctrl, int gated)
+                volatile unsigned long long *my_flags, int rank, int nranks, int N, int hb, int kind, QfCtrl *ctrl, int gated,
+                long long timeout_cycles)
 {
     if (gated && !ctrl[0].active) return;
     const unsigned long long seq = 2ull * ctrl[0].gseq + (unsigned long long)kind + 1ull;
@@ -334,7 +341,7 @@ k_p2p_allgather(double2 *const *__restrict__ peers, unsigned long long *const *_
             if (p == rank) continue;
             while (my_flags[p] < seq) {
                 __nanosleep(200);
-                if (clock64() - t0 > 20000000000ll) { ctrl[0].nonfinite = 2; break; }     // a peer never answered: give up, report
+                if (clock64() - t0 > timeout_cycles) { ctrl[0].nonfinite = 2; break; }     // a peer never answered: give up, report
             }
         }
         __threadfence_system();
@@ -376,7 +383,7 @@ int qf_comm_p2p_allgather(qf_handle_s *h, int kind, bool gated, cudaStream_t st)
     QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
     const int hb = qf_block_rows(h->N, h->nranks);
     k_p2p_allgather<<<h->sm_count * 2, 256, 0, st>>>(kind == 0 ? p->peerA_dev : p->peerS_dev, p->peerFlags_dev, arena_flags(h), h->rank,
-                                                 h->nranks, h->N, hb, kind, h->ctrl, gated ? 1 : 0);
+                                                 h->nranks, h->N, hb, kind, h->ctrl, gated ? 1 : 0, p->desc.timeout_cycles);
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;

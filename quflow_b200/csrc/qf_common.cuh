@@ -174,6 +174,7 @@ struct QfXchg {
     long long part2_off = 0;                          // offset (doubles) of rowpart2 inside that allocation
     unsigned long long *const *peerFlags = nullptr;   // [2][QF_MAX_RANKS] per rank, written by the peers
     unsigned long long *myFlags = nullptr;
+    long long timeout_cycles = 60000000000ll;         // give up on a silent peer after this many SM cycles (QF_COMM_TIMEOUT_S)
 };
 __host__ __device__ __forceinline__ int qf_owner_of_row(int row, int hb, int G)
 {
@@ -183,9 +184,9 @@ __host__ __device__ __forceinline__ int qf_owner_of_row(int row, int hb, int G)
 
 #ifdef __CUDACC__
 // Spin (one thread) until every peer's flag of `kind` in this rank's flag array has reached seq.  Bounded: a peer that
-// never answers (a failed rank, mismatched launch sequences) must not hang the GPU inside a kernel; after about ten
-// seconds the wait gives up and returns false, and the caller marks the run as failed (QfCtrl.nonfinite = 2); once
-// a run is marked failed the later waits return at once.
+// never answers (a failed rank, mismatched launch sequences) must not hang the GPU inside a kernel; after
+// x.timeout_cycles (30 s by default, QF_COMM_TIMEOUT_S) the wait gives up and returns false, and the caller marks the
+// run as failed (QfCtrl.nonfinite = 2); once a run is marked failed the later waits return at once.
 __device__ __forceinline__ bool xchg_wait_flags(const QfXchg &x, int kind, unsigned long long seq)
 {
     const volatile unsigned long long *f = x.myFlags + kind * QF_MAX_RANKS;
@@ -195,7 +196,7 @@ __device__ __forceinline__ bool xchg_wait_flags(const QfXchg &x, int kind, unsig
         if (p == x.rank) continue;
         while (f[p] < seq) {
             __nanosleep(100);
-            if (clock64() - t0 > 20000000000ll) { ok = false; break; }
+            if (clock64() - t0 > x.timeout_cycles) { ok = false; break; }
         }
     }
     __threadfence_system();      // acquire: what the peers stored before raising their flags is visible from here on

@@ -13,8 +13,10 @@ user fields and logger outputs; sub-group ``args/`` holding the solver arguments
 here only when their ``qutypes`` are ``{'mat'}`` (anything else is refused on open, see ``__init__``).  The layout has
 been exercised against ``tests/fake_h5py.py`` only: h5py is absent from this image.
 
-What is new: when the integrator is this package's ``isomp`` the state stays on the GPU for the whole run; every
-output interval costs one device→host copy into pinned memory for the callbacks instead of a round trip per chunk.
+What is new: when the integrator is this package's ``isomp`` (or a ``distributed.ShardedIsomp`` over several GPUs) the
+state stays on the GPU for the whole run; every output interval costs one asynchronous device→host copy into a pinned
+double buffer, and the callbacks (HDF5 append, loggers) run on a worker thread while the next chunk of steps is already
+computing (``_OutputPipeline``).
 
 Only the ``mat`` representation is written (``fun``/``shr``/``shc`` need the spherical-harmonic transforms, which are
 outside the hot path).  h5py is imported lazily: it is not part of this image, and nothing on the compute path needs it.
@@ -295,41 +297,115 @@ def solve(W,
             pbar = None
 
     # device-resident fast path: keep the state on the GPU across output intervals
-    host_out = None
-    Wdev = W
     # (hooks that run host code must see arrays of the caller's kind, so they keep the numpy calling convention)
     from .integrators import _is_default_hamiltonian
     host_hooks = (ikw.get('forcing') is not None or ikw.get('strang_splitting') is not None or ikw.get('callback') is not None
                   or not _is_default_hamiltonian(ikw.get('hamiltonian')))
-    on_device = integrator is isomp and not _is_torch(W) and not host_hooks
+    device_integrator = integrator is isomp or getattr(integrator, "device_resident", False)
+    on_device = (device_integrator and not host_hooks and isinstance(W, np.ndarray) and W.dtype == np.complex128
+                 and W.flags.c_contiguous and W.ndim == 2)
+    Wdev = W
+    writer = None
     if on_device:
         import torch
-        if not (isinstance(W, np.ndarray) and W.dtype == np.complex128 and W.flags.c_contiguous and W.ndim == 2):
-            on_device = False
-        else:
-            Wdev = torch.from_numpy(W).to("cuda", non_blocking=False)
-            host_out = torch.empty(W.shape, dtype=torch.complex128).pin_memory()
-
-    for k in range(0, steps, steps_out):                                  # :782
-        n = min(steps_out, steps - k)
-        Wdev = integrator(Wdev, dt, steps=n, **ikw)                       # :788
-        delta_time = n * dt
-        ikw['time'] += delta_time
-        if pbar is not None:
-            pbar.update(n)
+        dev = getattr(integrator, "device", None) or torch.device("cuda", torch.cuda.current_device())
+        Wdev = torch.from_numpy(W).to(dev, non_blocking=False)
         if callback is not None:
-            if on_device:
-                host_out.copy_(Wdev)                                      # one D2H per output record
-                Wcb = host_out.numpy()
-            else:
-                Wcb = Wdev
-            if 'stats' in ikw:
-                callback_kwargs.update(ikw['stats'])                      # :796-797
-            for cfun in callback:
-                cfun(Wcb, delta_time=delta_time, delta_steps=n, **callback_kwargs)
+            writer = _OutputPipeline(W.shape, dev, callback)
+
+    try:
+        for k in range(0, steps, steps_out):                              # :782
+            n = min(steps_out, steps - k)
+            Wdev = integrator(Wdev, dt, steps=n, **ikw)                   # :788
+            delta_time = n * dt
+            ikw['time'] += delta_time
+            if pbar is not None:
+                pbar.update(n)
+            if callback is not None:
+                if 'stats' in ikw:
+                    callback_kwargs.update(ikw['stats'])                  # :796-797
+                if writer is not None:
+                    # snapshot on a side stream into pinned memory; the callbacks (HDF5 append, loggers) run on a worker
+                    # thread while the next chunk of steps is already computing
+                    writer.submit(Wdev, dict(delta_time=delta_time, delta_steps=n, **callback_kwargs))
+                else:
+                    for cfun in callback:
+                        cfun(Wdev, delta_time=delta_time, delta_steps=n, **callback_kwargs)
+    finally:
+        if writer is not None:
+            writer.close()                                                # drains the queue, re-raises a callback's exception
     if pbar is not None:
         pbar.close()
     if on_device:
         W[...] = Wdev.cpu().numpy()                                       # the caller's array ends up advanced, as with the reference
         return W
     return Wdev
+
+
+class _OutputPipeline:
+    """Overlaps the output of `solve` with the computation ("overlap D2H of W with the next chunk").
+
+    `submit(Wdev, kwargs)` enqueues an asynchronous device-to-host copy of the state into one of two pinned buffers on a
+    side stream (ordered after the compute stream by an event) and hands the record to a worker thread, which waits for
+    the copy and then calls the callbacks in submission order with a numpy view of the buffer — exactly what the
+    reference's callbacks receive (`cfun(W, delta_time=, delta_steps=, **stats)`, simulation.py:794-798).  The main thread
+    returns at once and starts the next chunk; it blocks only if both buffers are still in use."""
+
+    def __init__(self, shape, device, callbacks, depth=2):
+        import queue
+        import threading
+        import torch
+        self._torch = torch
+        self.device = device
+        self.callbacks = callbacks
+        self.stream = torch.cuda.Stream(device=device)
+        self.buffers = [torch.empty(shape, dtype=torch.complex128).pin_memory() for _ in range(depth)]
+        self.free = queue.Queue()
+        for i in range(depth):
+            self.free.put(i)
+        self.work = queue.Queue()
+        self.error = None
+        self.thread = threading.Thread(target=self._run, name="quflow_b200-output", daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        while True:
+            item = self.work.get()
+            if item is None:
+                return
+            i, done, kwargs = item
+            try:
+                if self.error is None:
+                    done.synchronize()
+                    Wcb = self.buffers[i].numpy()
+                    for cfun in self.callbacks:
+                        cfun(Wcb, **kwargs)
+            except BaseException as e:      # surfaced by close() on the caller's thread
+                self.error = e
+            finally:
+                self.free.put(i)
+
+    def submit(self, Wdev, kwargs):
+        torch = self._torch
+        if self.error is not None:
+            self.close()
+        i = self.free.get()                 # blocks only when every buffer is still being written out
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            self.buffers[i].copy_(Wdev, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        # the next chunk must not overwrite W before the snapshot has been read: order the compute stream after the copy
+        torch.cuda.current_stream(self.device).wait_event(done)
+        self.work.put((i, done, dict(kwargs)))
+
+    def close(self):
+        if self.thread is not None:
+            self.work.put(None)
+            self.thread.join()
+            self.thread = None
+        if self.error is not None:
+            err, self.error = self.error, None
+            raise err

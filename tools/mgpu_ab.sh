@@ -13,7 +13,7 @@ grep "MGPU_\|rank 0" gpurun_out/${TAG}_g${G}_parity.log | tail -12
 grep -q MGPU_OK gpurun_out/${TAG}_g${G}_parity.log || tail -30 gpurun_out/${TAG}_g${G}_parity.log
 for mode in tile pull; do
     out=gpurun_out/${TAG}_g${G}_${mode}.json
-    QF_COMM=$mode timeout 600 $RUN --master-port 29512 bench.py --gpus $G --n $N --steps $STEPS --warmup 3 --no-cpu-baseline 2>gpurun_out/${TAG}_g${G}_${mode}.err | tail -1 > $out
+    QF_COMM=$mode timeout 600 $RUN --master-port 29512 bench.py --gpus $G --size $N --steps $STEPS --warmup 3 --no-cpu-baseline 2>gpurun_out/${TAG}_g${G}_${mode}.err | tail -1 > $out
     python - "$out" "$mode" <<'PY'
 import json, sys
 try:
