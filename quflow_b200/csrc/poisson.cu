@@ -33,6 +33,11 @@ static bool qf_poisson_plan_host(int N, int &L, int &M, int &NT, int &CL, std::v
     // Measured at N = 2048: 16 positions per thread, 4 diagonals per band and CTAs of up to 512
     // threads are the fastest combination (8 positions: +13 us; 8 diagonals: +7 us; 256-thread cluster pairs: +3 us).
     L = 16;
+    {
+        // QF_POISSON_L=8: eight positions per thread (half the sequential chain, twice the threads per diagonal)
+        const char *env = getenv("QF_POISSON_L");
+        if (env && atoi(env) == 8) L = 8;
+    }
     M = 4;
     const int NTMAX = 512;
     const int chunks = (N + L - 1) / L;
@@ -763,8 +768,9 @@ __global__ void k_laplace(const double2 *__restrict__ P, double2 *__restrict__ W
 static void *poisson_band_fn(const qf_handle_s *h)
 {
     void *fn = nullptr;
-#define QF_PB(CC) if (h->p_L == 16 && h->p_M == 4 && h->p_CL == CC && h->p_NTMAX == 512) fn = (void *)k_poisson_band<16, 4, CC, 512>;
-    QF_PB(1) QF_PB(2) QF_PB(4) QF_PB(8)
+#define QF_PB(LL, CC) if (h->p_L == LL && h->p_M == 4 && h->p_CL == CC && h->p_NTMAX == 512) fn = (void *)k_poisson_band<LL, 4, CC, 512>;
+    QF_PB(16, 1) QF_PB(16, 2) QF_PB(16, 4) QF_PB(16, 8)
+    QF_PB(8, 1) QF_PB(8, 2) QF_PB(8, 4) QF_PB(8, 8)
 #undef QF_PB
     return fn;
 }

@@ -91,3 +91,69 @@ def isomp_ensemble_sharded(W_local, dt, steps, **kw):
     """Advance this rank's members of an ensemble (``W_local``: (k_local, N, N)); no collective on the data path."""
     from .integrators import isomp_ensemble
     return isomp_ensemble(W_local, dt, steps, **kw)
+
+
+class ShardedIsomp:
+    """``isomp`` over the ranks of a torch.distributed process group (one process per GPU) — the multi-GPU counterpart of
+    the reference's pluggable integrator object (``IsompCUDA``, quflow/experimental/isospectral_cuda.py:120-358, passed
+    as ``integrator=`` to ``qf.solve``, quflow/simulation.py:554-566).
+
+    Every rank calls it with the same arguments and the same (replicated) state; the state that comes back is complete
+    and bit-identical on every rank.  ``quflow_b200.solve(W, ..., integrator=ShardedIsomp(dist))`` keeps the state on the
+    GPUs between output intervals; give the output callback (``QuSimulation``) to rank 0 only.
+
+    The parameter list mirrors ``isomp_fixedpoint`` (isospectral.py:338-353) so that ``solve`` finds ``stats`` by
+    introspection (simulation.py:729); hooks that run host code inside the step are single-GPU only.
+    """
+    device_resident = True      # solve(): keep the state on the device between output intervals
+
+    def __init__(self, dist, device=None, mode=None):
+        import torch
+        self.dist = dist
+        self.mode = mode
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._handles = {}
+
+    def handle(self, N):
+        if N not in self._handles:
+            h = binding.Handle(N, 1, self.device.index)
+            attach_row_sharding(h, self.dist, mode=self.mode)
+            self._handles[N] = h
+        return self._handles[N]
+
+    def __call__(self, W, dt, steps=100, hamiltonian=None, time=None, forcing=None, strang_splitting=None, stats=None,
+                 callback=None, tol='auto', maxit=10, minit=1, verbatim=False, compsum=False, reinitialize=False):
+        from .integrators import _is_default_hamiltonian
+        from .laplacian import _is_torch
+        assert minit >= 1, "minit must be at least 1."          # isospectral.py:400
+        assert maxit >= minit, "maxit must be at minit."         # isospectral.py:401
+        if forcing is not None or strang_splitting is not None or callback is not None or not _is_default_hamiltonian(hamiltonian):
+            raise NotImplementedError("ShardedIsomp runs the default Hamiltonian without hooks; hooks are single-GPU (quflow_b200.isomp)")
+        if W.ndim != 2:
+            raise NotImplementedError("ShardedIsomp advances one (N, N) state; ensembles shard per member (member_slice)")
+        auto = (isinstance(tol, str) and tol == 'auto') or (not isinstance(tol, str) and tol < 0)
+        if _is_torch(W):
+            Wc = W if W.is_contiguous() else W.contiguous()
+        else:
+            Wc = np.ascontiguousarray(W, dtype=np.complex128)
+        res, _ = self.handle(Wc.shape[-1]).isomp(Wc, dt, steps, tol=-1.0 if auto else float(tol), maxit=maxit, minit=minit,
+                                                  compsum=bool(compsum), reinitialize=bool(reinitialize))
+        if Wc is not W:
+            if _is_torch(W):
+                W.copy_(Wc)
+            else:
+                W[...] = Wc
+        st = res[0]
+        if auto and stats:
+            stats['tol_auto'] = st['tol_used']                   # :451-452
+        if verbatim and steps > 0 and self.dist.get_rank() == 0:
+            print("Average number of iterations per step: {:.2f}".format(st['total_iterations'] / steps))
+        if stats and steps > 0:                                   # :609-611
+            stats["iterations"] = st['total_iterations'] / steps
+            stats["number_of_maxit"] = st['number_of_maxit'] / steps
+        return W
+
+    def close(self):
+        for h in self._handles.values():
+            h.close()
+        self._handles = {}
