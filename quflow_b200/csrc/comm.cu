@@ -223,6 +223,12 @@ static int p2p_finish(qf_handle_s *h, QfP2P *p)
     p->desc.peerFlags = p->peerXFlags_dev;
     p->desc.myFlags = arena_flags(h) + QF_FLAGS_XCHG;
     {
+        // Upper-only W~ exchange + local mirror: pays off once the volume saved (half of 16 N^2 (G-1)/G bytes per rank)
+        // outweighs the replicated mirror pass, i.e. from four ranks on.  QF_XCHG_UPPER=0|1 overrides.
+        const char *u = getenv("QF_XCHG_UPPER");
+        p->desc.upper_only = u ? (u[0] == '1') : (nranks >= 4);
+    }
+    {
         // ranks may legitimately be seconds apart (host work between calls): the bound only has to end a real hang
         const char *t = getenv("QF_COMM_TIMEOUT_S");
         const double secs = t ? atof(t) : 30.0;
@@ -442,6 +448,151 @@ int qf_xchg_wait(qf_handle_s *h, int kind, bool gated, cudaStream_t st)
     if (!x) { qf_set_error("qf_xchg_wait: the handle has no tile-exchange communicator"); return QF_ERR_INVALID; }
     k_xchg_wait<<<1, 1, 0, st>>>(*x, kind, h->ctrl, gated ? 1 : 0);
     h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
+// W~ exchange.  After the tail of an iteration (or the update) every rank holds the new W~ on the tile pairs it owns:
+// the upper parts of its two row blocks, rows [b hb, (b+1) hb) x columns [b hb, N), and their mirrors, rows
+// [(b+1) hb, N) x columns [b hb, (b+1) hb).  One copy kernel on all SMs stores them into every peer's W~: a warp moves a
+// piece of 256 elements of one row, loaded once (eight 16-byte loads per lane in flight) and stored to each peer.
+// When W is bit-for-bit skew-Hermitian (QfCtrl.skew_exact, checked at call start) W~ is too — the tail and the update
+// write exact mirrors — so only the upper parts travel and every rank rebuilds the lower triangle locally
+// (k_xchg_mirror_wh): half the NVLink volume.
+__global__ void __launch_bounds__(256)
+k_xchg_push_wh(const QfXchg x, int N, const QfCtrl *__restrict__ ctrl, int gated)
+{
+    if (gated && !ctrl[0].active) return;
+    const bool upper_only = x.upper_only && ctrl[0].skew_exact;
+    const double2 *__restrict__ mine = x.peerWh[x.rank];
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int hb = x.hb;
+    for (int q = 0; q < 2; ++q) {
+        const int b = q ? 2 * x.nranks - 1 - x.rank : x.rank;
+        const int r0 = b * hb;
+        // upper part: hb rows, pieces of 256 columns from column r0 on
+        const int upieces = (N - r0 + 255) >> 8;
+        // mirrored part: N - r0 - hb rows of hb columns, pieces of 256 columns
+        const int mrows = upper_only ? 0 : N - r0 - hb, mpieces = (hb + 255) >> 8;
+        const int total = hb * upieces + mrows * mpieces;
+        for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
+            int row, c0, cend;
+            if (w < hb * upieces) {
+                row = r0 + w / upieces;
+                c0 = r0 + ((w % upieces) << 8);
+                cend = N;
+            } else {
+                const int v = w - hb * upieces;
+                row = r0 + hb + v / mpieces;
+                c0 = r0 + ((v % mpieces) << 8);
+                cend = r0 + hb;
+            }
+            const double2 *__restrict__ s = mine + (size_t)row * N;
+            double2 v8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c0 + lane + 32 * u;
+                if (c < cend) v8[u] = s[c];
+            }
+            for (int p = 0; p < x.nranks; ++p) {
+                if (p == x.rank) continue;
+                double2 *__restrict__ d = x.peerWh[p] + (size_t)row * N;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = c0 + lane + 32 * u;
+                    if (c < cend) d[c] = v8[u];
+                }
+            }
+        }
+    }
+    __threadfence_system();      // remote stores are performed before the kernel (and the flag that follows it) completes
+}
+
+int qf_xchg_push_wh(qf_handle_s *h, bool gated, cudaStream_t st)
+{
+    const QfXchg *x = qf_xchg_desc(h);
+    if (!x) { qf_set_error("qf_xchg_push_wh: the handle has no tile-exchange communicator"); return QF_ERR_INVALID; }
+    k_xchg_push_wh<<<h->sm_count * 4, 256, 0, st>>>(*x, h->N, h->ctrl, gated ? 1 : 0);
+    h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
+// Lower triangle of W~ from the upper one, W~_ji = -conj(W~_ij), 32 x 32 tiles transposed through shared memory; a no-op
+// unless the upper-only exchange is active (see k_xchg_push_wh).
+__global__ void __launch_bounds__(256)
+k_xchg_mirror_wh(const QfXchg x, double2 *__restrict__ Wh, int N, const QfCtrl *__restrict__ ctrl, int gated)
+{
+    if (gated && !ctrl[0].active) return;
+    if (!(x.upper_only && ctrl[0].skew_exact)) return;
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bi > bj) return;
+    __shared__ double2 T[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = bi * 32 + ty + 8 * q, j = bj * 32 + tx;
+        if (i < N && j < N) T[ty + 8 * q][tx] = __ldcg(Wh + (size_t)i * N + j);     // stored by a peer: not through L1
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int j = bj * 32 + ty + 8 * q, i = bi * 32 + tx;
+        if (j < N && i < N && i < j) {
+            const double2 v = T[tx][ty + 8 * q];
+            Wh[(size_t)j * N + i] = make_double2(-v.x, v.y);
+        }
+    }
+}
+
+int qf_xchg_mirror_wh(qf_handle_s *h, bool gated, cudaStream_t st)
+{
+    const QfXchg *x = qf_xchg_desc(h);
+    if (!x) { qf_set_error("qf_xchg_mirror_wh: the handle has no tile-exchange communicator"); return QF_ERR_INVALID; }
+    if (!x->upper_only) return QF_OK;
+    const int nb = (h->N + 31) / 32;
+    k_xchg_mirror_wh<<<dim3(nb, nb), 256, 0, st>>>(*x, h->Wh, h->N, h->ctrl, gated ? 1 : 0);
+    h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
+// ctrl[0].skew_exact = 1 iff W_ji == -conj(W_ij) bit for bit for all i < j (the diagonal is free: the tail and the update
+// only ever add purely imaginary numbers to it and mirror nothing onto it).
+__global__ void k_xchg_skew_reset(QfCtrl *ctrl) { ctrl[0].skew_exact = 1; }
+__global__ void __launch_bounds__(256)
+k_xchg_skew_check(const double2 *__restrict__ W, int N, QfCtrl *ctrl)
+{
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bi > bj) return;
+    __shared__ double2 T[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int j = bj * 32 + ty + 8 * q, i = bi * 32 + tx;
+        if (j < N && i < N) T[ty + 8 * q][tx] = W[(size_t)j * N + i];
+    }
+    __syncthreads();
+    int bad = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = bi * 32 + ty + 8 * q, j = bj * 32 + tx;
+        if (i < N && j < N && i < j) {
+            const double2 u = W[(size_t)i * N + j], l = T[tx][ty + 8 * q];
+            // bit-for-bit: -0.0 and 0.0 count as equal (they add identically), NaNs never match
+            if (!(l.x == -u.x && l.y == u.y)) bad = 1;
+        }
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) ctrl[0].skew_exact = 0;
+}
+
+int qf_xchg_skew_check(qf_handle_s *h, const double2 *W, cudaStream_t st)
+{
+    const int nb = (h->N + 31) / 32;
+    k_xchg_skew_reset<<<1, 1, 0, st>>>(h->ctrl);
+    k_xchg_skew_check<<<dim3(nb, nb), 256, 0, st>>>(W, h->N, h->ctrl);
+    h->launches += 2;
     QF_CUDA(cudaGetLastError());
     return QF_OK;
 }

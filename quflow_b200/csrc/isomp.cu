@@ -91,8 +91,9 @@ __global__ void k_zero(double2 *X, size_t n2, const QfCtrl *__restrict__ ctrl)
 // It also writes the next iterate W~ = W + dW (both triangles), so no separate pass is needed before the Poisson solve.
 // Tile-exchange path (xg.nranks > 1): a tile pair is processed by the rank that owns row block bi only — the rows of A and
 // S it needs are its own, the transposed tile of A was pushed to it by the owner of row block bj during the first GEMM
-// (the block's first thread waits for every peer's "GEMM 1 complete" flag) — and the new W~ tiles and the residual
-// partials are stored into every peer's copy as well, through the NVLink peer mappings.
+// (the block's first thread waits for every peer's "GEMM 1 complete" flag) — and the residual partials are stored into
+// every peer's copy as well, through the NVLink peer mappings; the new W~ tiles follow in a copy kernel of their own
+// (comm.cu: k_xchg_push_wh).
 template <bool FORCING>
 __global__ void __launch_bounds__(256)
 k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *__restrict__ dWg, double *__restrict__ rowpart,
@@ -149,11 +150,7 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
             const double2 old = dW[ij];
             r = zabs(zsub(old, dn));                                  // :526,:534
             dW[ij] = dn;
-            const double2 wh = zadd(W[ij], dn);                       // next iterate W~ = W + dW (:481-482)
-            Wh[ij] = wh;
-            if (xpush)
-                for (int p = 0; p < xg.nranks; ++p)
-                    if (p != xg.rank) xg.peerWh[p][off + ij] = wh;
+            Wh[ij] = zadd(W[ij], dn);                                 // next iterate W~ = W + dW (:481-482)
         }
         D[ii][tx] = d;                                                // without the forcing term: mirrored below
         R[ii][tx] = r;
@@ -184,11 +181,7 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
                 rl = R[tx][jj];
             }
             dW[ji] = dm;
-            const double2 wh = zadd(W[ji], dm);
-            Wh[ji] = wh;
-            if (xpush)
-                for (int p = 0; p < xg.nranks; ++p)
-                    if (p != xg.rank) xg.peerWh[p][off + ji] = wh;
+            Wh[ji] = zadd(W[ji], dm);
         }
         double s = rl;
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -298,7 +291,7 @@ __device__ __forceinline__ double2 kahan_add(double2 w, double2 inc, double2 &kc
 }
 
 // Tile-exchange path (xg.nranks > 1): a tile pair is updated by the rank that owns row block bi only (A, dW and the state
-// are valid there); the first iterate of the next step, W~, is stored into every peer's copy as well.
+// are valid there); the first iterate of the next step, W~, goes to the peers in a copy kernel of its own (k_xchg_push_wh).
 template <bool COMPSUM, bool FORCING>
 __global__ void __launch_bounds__(256)
 k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__restrict__ Kg, int N, QfCtrl *ctrl,
@@ -352,11 +345,7 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
                 if (FORCING) w = zadd(w, zscale(2.0, zscale(fscale, F[ij])));   // FW *= 2; W += FW (:594-596)
             }
             W[ij] = w;
-            const double2 wh = reinit ? w : zadd(w, dW[ij]);
-            Wh[ij] = wh;
-            if (xpush)
-                for (int p = 0; p < xg.nranks; ++p)
-                    if (p != xg.rank) xg.peerWh[p][off + ij] = wh;
+            Wh[ij] = reinit ? w : zadd(w, dW[ij]);
         }
         cv[q] = cm;
     }
@@ -382,14 +371,9 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
                 if (FORCING) w = zadd(w, zscale(2.0, zscale(fscale, F[ji])));
             }
             W[ji] = w;
-            const double2 wh = reinit ? w : zadd(w, dW[ji]);
-            Wh[ji] = wh;
-            if (xpush)
-                for (int p = 0; p < xg.nranks; ++p)
-                    if (p != xg.rank) xg.peerWh[p][off + ji] = wh;
+            Wh[ji] = reinit ? w : zadd(w, dW[ji]);
         }
     }
-    if (xpush) __threadfence_system();
 }
 
 // out = 2 (A - A^H): the increment handed to `callback(W, dW)` just before the update (isospectral.py:547-551)
@@ -573,10 +557,16 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
             epi.nsm = h->nsm;
             QF_CHECK(qf_launch_zgemm_post(h, h->A, h->P, epi, true, my, G, st, xg));
             if (ev) QF_CUDA(cudaEventRecord(ev[3], st));
-            if (xmode) QF_CHECK(qf_xchg_signal(h, QF_XF_X, true, st));
+            if (xmode) {
+                QF_CHECK(qf_xchg_push_wh(h, true, st));
+                QF_CHECK(qf_xchg_signal(h, QF_XF_X, true, st));
+            }
         }
         if (phases & QF_PH_C) {
-            if (xmode) QF_CHECK(qf_xchg_wait(h, QF_XF_X, true, st));      // every peer's W~ tiles and partials have landed
+            if (xmode) {
+                QF_CHECK(qf_xchg_wait(h, QF_XF_X, true, st));             // every peer's W~ tiles and partials have landed
+                QF_CHECK(qf_xchg_mirror_wh(h, true, st));
+            }
             k_control<<<gc, 256, 0, st>>>(part_direct, h->nsd, part_mirror, h->nsm, N, h->ctrl, maxit, minit, nfollow, h->cap_cond,
                                           h->cap_use_cond);
             h->launches += 1;
@@ -596,13 +586,15 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
             // the owners of the tile pairs form dW, W~ and the residual partials and push W~ / the partials to every peer
             k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, Gp, W, h->Wh, nullptr, 0.0, *xg);
             h->launches++;
+            QF_CHECK(qf_xchg_push_wh(h, true, st));
             QF_CHECK(qf_xchg_signal(h, QF_XF_X, true, st));
         }
     }
     if (phases & QF_PH_C) {
-        if (xmode)
+        if (xmode) {
             QF_CHECK(qf_xchg_wait(h, QF_XF_X, true, st));
-        else {
+            QF_CHECK(qf_xchg_mirror_wh(h, true, st));
+        } else {
             k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, Gp, W, h->Wh, nullptr, 0.0, solo);
             h->launches++;
         }
@@ -635,9 +627,15 @@ int qf_enqueue_update(qf_handle_s *h, double2 *W, bool compsum, bool reinit, cud
             k_update<false, false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, h->iters_dev, h->steps_cap, hb, Gp, h->dW, h->Wh, reinit ? 1 : 0, nullptr, 0.0, xg);
         h->launches++;
         QF_CUDA(cudaGetLastError());
-        if (xmode) QF_CHECK(qf_xchg_signal(h, QF_XF_X, false, st));
+        if (xmode) {
+            QF_CHECK(qf_xchg_push_wh(h, false, st));
+            QF_CHECK(qf_xchg_signal(h, QF_XF_X, false, st));
+        }
     }
-    if ((phases & 2) && xmode) QF_CHECK(qf_xchg_wait(h, QF_XF_X, false, st));
+    if ((phases & 2) && xmode) {
+        QF_CHECK(qf_xchg_wait(h, QF_XF_X, false, st));
+        QF_CHECK(qf_xchg_mirror_wh(h, false, st));
+    }
     return QF_OK;
 }
 
@@ -842,6 +840,7 @@ static int isomp_call_begin(qf_handle_s *h, void *W_dev, double dt, int steps, d
     k_call_begin<<<B, 1, 0, st>>>(h->ctrl, tol, tol_factor, multistate ? 1 : 0);
     h->launches++;
     QF_CUDA(cudaGetLastError());
+    if (c->xmode) QF_CHECK(qf_xchg_skew_check(h, c->W, st));
     return QF_OK;
 }
 

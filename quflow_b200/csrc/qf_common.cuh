@@ -69,6 +69,8 @@ struct QfCtrl {
     int active;           // 1 while the fixed-point loop of the current step runs
     int it;               // iterations executed in the current step
     int nonfinite;        // sticky: 1 = residual was NaN/Inf, 2 = a peer did not answer in time -> everything becomes a no-op
+    int skew_exact;       // tile exchange: W is bit-for-bit skew-Hermitian (checked at call start), so the lower triangle of
+                          // W~ can be rebuilt locally from the upper one and only upper tiles cross NVLink
     int steps_done;
 };
 
@@ -175,6 +177,7 @@ struct QfXchg {
     unsigned long long *const *peerFlags = nullptr;   // [2][QF_MAX_RANKS] per rank, written by the peers
     unsigned long long *myFlags = nullptr;
     long long timeout_cycles = 60000000000ll;         // give up on a silent peer after this many SM cycles (QF_COMM_TIMEOUT_S)
+    int upper_only = 0;                               // W~ exchange: send upper tiles only when W is exactly skew-Hermitian
 };
 __host__ __device__ __forceinline__ int qf_owner_of_row(int row, int hb, int G)
 {
@@ -258,6 +261,9 @@ void qf_p2p_destroy(qf_handle_s *h);
 const QfXchg *qf_xchg_desc(qf_handle_s *h);                                          // nullptr unless comm_mode == 5
 int qf_xchg_signal(qf_handle_s *h, int kind, bool gated, cudaStream_t st);           // raise my flag of `kind` at every peer
 int qf_xchg_wait(qf_handle_s *h, int kind, bool gated, cudaStream_t st);             // until every peer raised its flag here
+int qf_xchg_push_wh(qf_handle_s *h, bool gated, cudaStream_t st);                    // my tiles of W~ -> every peer
+int qf_xchg_mirror_wh(qf_handle_s *h, bool gated, cudaStream_t st);                  // lower triangle of W~ from the upper one
+int qf_xchg_skew_check(qf_handle_s *h, const double2 *W, cudaStream_t st);           // -> ctrl[0].skew_exact
 int qf_xchg_push_state(qf_handle_s *h, cudaStream_t st);                             // my tile pairs of Wst -> every peer
 int qf_xchg_push_rows(qf_handle_s *h, cudaStream_t st);                              // my row blocks of Wst -> every peer
 // isomp.cu: qf_isomp with W_dev == NULL allowed on the tile-exchange path (state already staged in h->Wst)

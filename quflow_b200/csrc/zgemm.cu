@@ -490,9 +490,9 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
 // c = col0 + wn*16 + j*8 + 2t + e.  Direct accesses: the four lanes of a quad cover 128 contiguous bytes of row r.
 // Transposed accesses (A_ji, W_ji, dW_ji, W~_ji): the eight lanes with equal t cover 128 contiguous bytes of row c.
 // Only elements on or above the diagonal (r <= c) are processed; their mirrors are written from the same registers.
-// Tile-exchange path (xg.nranks > 1): the rank that owns the tile pair also stores W~_ij, W~_ji and the residual partials
-// into every peer's copy (plain stores through the NVLink peer mappings), so that after the exchange barrier every rank
-// holds the complete W~ and can evaluate the stopping rule on identical numbers.
+// Tile-exchange path (xg.nranks > 1): the rank that owns the tile pair also stores the residual partials into every peer's
+// copy (plain stores through the NVLink peer mappings), so that after the exchange barrier every rank evaluates the
+// stopping rule on identical numbers; the W~ tiles follow in a copy kernel of their own (comm.cu: k_xchg_push_wh).
 __device__ __forceinline__ void epi_post_tile(const double (&acc)[MI][Cfg<true>::NJ][Cfg<true>::NACC][2], const SkTile &ti, int N,
                                               int wm, int wn, int g, int t, const QfEpiPost &E, const QfXchg &xg)
 {
@@ -545,10 +545,6 @@ __device__ __forceinline__ void epi_post_tile(const double (&acc)[MI][Cfg<true>:
                     const double2 whd = zadd(wd[e], d);                            // :481-482
                     Wh[rc] = whd;
                     rowsum += res;
-                    if (xg.nranks > 1) {
-                        for (int p = 0; p < xg.nranks; ++p)
-                            if (p != xg.rank) xg.peerWh[p][moff + rc] = whd;
-                    }
                     if (r < c) {
                         const size_t cr = (size_t)c * N + r;
                         const double2 dm = make_double2(-d.x, d.y);                // dW_ji = -conj(dW_ij)
@@ -556,10 +552,6 @@ __device__ __forceinline__ void epi_post_tile(const double (&acc)[MI][Cfg<true>:
                         const double2 whm = zadd(wt[e], dm);
                         Wh[cr] = whm;
                         colsum[j][e] += res;                                       // the mirrored element has the same residual
-                        if (xg.nranks > 1) {
-                            for (int p = 0; p < xg.nranks; ++p)
-                                if (p != xg.rank) xg.peerWh[p][moff + cr] = whm;
-                        }
                     }
                 }
             }

@@ -159,6 +159,43 @@ def test_isomp_config2_smooth_N512(qf):
     assert relfro(W, Wref) < TOL_100_STEPS
 
 
+def test_isomp_config2_smooth_N512_10000_steps(qf):
+    """BASELINE config 2 at full length: S(512), 10 000 steps in chunks of 1000 (like qf.solve with steps_out=1000; every
+    chunk re-zeroes the iterate dW, isospectral.py:430) against the REAL reference's run of the same schedule
+    (oracle/gen_golden_c2.py -> tests/golden/isomp_S_N512_10k.npz).  Bars: the same mean iteration count in every
+    chunk, Casimir C_2..C_4 and eigenvalue drift no worse than the reference's, and the final state within 1e-8 relative
+    (100x the 100-step bar for 100x the steps: the flow is chaotic, rounding differences grow along the run)."""
+    import os
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "isomp_S_N512_10k.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    g = np.load(path)
+    g0 = golden("isomp_S_N512.npz")
+    N = 512
+    W = unband(g0["W0_band"], N)
+    W0 = W.copy()
+    ev0 = np.linalg.eigvalsh(1j * W0)
+    dt = float(g["dt"])
+    from quflow_b200._cuda import get_handle
+    h = get_handle(N)
+    c0 = g["casimirs"][0]
+    for c in range(int(g["nchunks"])):
+        res, _ = h.isomp(W, dt, int(g["chunk"]))
+        assert res[0]["total_iterations"] / int(g["chunk"]) == float(g["mean_iterations"][c])
+        assert res[0]["tol_used"] == pytest.approx(float(g["tol_auto"][c]), rel=1e-12)
+        drift_ref = np.abs(g["casimirs"][c + 1] - c0)
+        drift = np.abs(oracle.casimirs(W) - c0)
+        assert np.all(drift <= 2 * drift_ref + 1e-12 * np.abs(c0))
+    assert np.abs(W + W.conj().T).max() == 0.0
+    assert np.abs(np.linalg.eigvalsh(1j * W) - ev0).max() <= 2 * float(g["eig_drift"][-1]) + 1e-12
+    idx = g["sample_idx"]
+    scale = float(g["normF"]) / N
+    assert np.abs(W[idx[:, 0], idx[:, 1]] - g["Wfinal_sample"]).max() < 1e-8 * scale * N
+    assert np.linalg.norm(W[:48, :48] - g["Wfinal_block"]) < 1e-8 * np.linalg.norm(g["Wfinal_block"])
+    assert np.linalg.norm(W) == pytest.approx(float(g["normF"]), rel=1e-11)
+
+
 @pytest.mark.parametrize("N", [5, 16, 61, 100, 130, 257])
 def test_isomp_odd_sizes_vs_oracle(qf, N):
     W0 = oracle.random_skewherm(N, N)
@@ -381,6 +418,18 @@ def test_tile_exchange_ranks_in_lockstep_on_one_gpu(qf, N, G, fuse):
     solo.isomp(Wc, dt, 5, compsum=True)
     assert relfro(Wd2[G - 1].cpu().numpy(), Wc) < 1e-13
     assert np.array_equal(Wd2[G - 1].cpu().numpy(), Wd2[0].cpu().numpy())
+    # a state that is NOT bit-for-bit skew-Hermitian (the reference keeps such an asymmetry: it only ever adds exactly
+    # mirrored increments): the upper-only W~ exchange must switch itself off and the run must still match the solo one
+    Wp = W0.copy()
+    Wp[3, 5] += 1e-13
+    Wd3 = [torch.from_numpy(Wp).cuda() for _ in range(G)]
+    _, it3 = isomp_lockstep(hs, Wd3, dt, 4)
+    Wq = Wp.copy()
+    _, it3s = solo.isomp(Wq, dt, 4, want_iters=True)
+    assert list(it3[0]) == list(it3s[0])
+    assert relfro(Wd3[0].cpu().numpy(), Wq) < 1e-13
+    assert np.array_equal(Wd3[G - 1].cpu().numpy(), Wd3[0].cpu().numpy())
+    assert Wd3[0].cpu().numpy()[5, 3] != -np.conj(Wd3[0].cpu().numpy()[3, 5])     # the asymmetry survived
     solo.close()
     for h in hs:
         h.close()
