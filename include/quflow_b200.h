@@ -165,6 +165,16 @@ int qf_step_increment(qf_handle_t h, void *out_dev, void *stream);   /* out = 2 
 int qf_step_update(qf_handle_t h, void *W_dev, const void *F_dev /* may be NULL */, double fscale, void *stream);
 int qf_step_stats(qf_handle_t h, qf_stats *stats, void *stream);
 
+/* ---- matrix <-> real spherical-harmonic coefficients (the callers' data format either side of the path) --------------
+ * Replace quflow/quantization.py `mat2shr_parallel_` (:283-325) and `shr2mat_parallel_` (:172-227) for a quantization
+ * basis resident in HBM.  basis_dev: the reference's flat float64 array (quflow.quantization.get_basis(N)): for every
+ * m = 0..N-1 a dense (N-m) x (N-m) block, row-major [k][el-m], starting at basis_break_index(m, N) (:25-42);
+ * qf_basis_size(N) doubles in all.  omega_dev: float64, nomega = (elmax+1)^2 coefficients ordered el^2 + el + m
+ * (quflow/utils.py:91-105), elmax <= N-1.  Deterministic (fixed summation order); enqueued on `stream`, no sync. */
+long long qf_basis_size(int N);
+int qf_mat2shr(qf_handle_t h, const void *W_dev, const void *basis_dev, void *omega_dev, long long nomega, void *stream);
+int qf_shr2mat(qf_handle_t h, const void *omega_dev, long long nomega, const void *basis_dev, void *W_dev, void *stream);
+
 /* The tail of the fixed-point iteration (dW = S + A - A^H, W~ = W + dW, residual partial sums; isospectral.py:499-536)
  * can run fused into the epilogue of the second GEMM (1) or as a kernel of its own after it (0, default: measured faster,
  * DESIGN.md).  Also QF_FUSE_POST=1 in the environment at handle creation. */

@@ -12,6 +12,7 @@ from .physics import energy_euler, enstrophy, inner_Hm1, norm_Hm1, inner_H1, nor
 from .laplacian import solve_poisson, laplace, select_first  # noqa: F401
 from .integrators import isomp, isomp_fixedpoint, isomp_ensemble  # noqa: F401
 from .simulation import solve, QuSimulation  # noqa: F401
-from . import integrators, simulation, physics, _cuda  # noqa: F401
+from .quantization import mat2shr, shr2mat  # noqa: F401
+from . import integrators, simulation, physics, quantization, _cuda  # noqa: F401
 
 __version__ = "0.1.0"

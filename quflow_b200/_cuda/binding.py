@@ -95,6 +95,9 @@ SYMBOLS = {
     "qf_isomp_lockstep": (_i, [ctypes.POINTER(_vp), _i, ctypes.POINTER(_vp), _d, _i, _d, _i, _i, _u, ctypes.POINTER(qf_stats),
                                ctypes.POINTER(ctypes.c_int32), _vp]),
     "qf_set_fuse_post": (_i, [_vp, _i]),
+    "qf_basis_size": (ctypes.c_longlong, [_i]),
+    "qf_mat2shr": (_i, [_vp, _vp, _vp, _vp, ctypes.c_longlong, _vp]),
+    "qf_shr2mat": (_i, [_vp, _vp, ctypes.c_longlong, _vp, _vp, _vp]),
     "qf_comm_mode": (_i, [_vp]),
 }
 

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(HERE, "..", "csrc"))
 LIB = os.path.join(HERE, "libquflow_b200.so")
-SOURCES = ["api.cu", "poisson.cu", "zgemm.cu", "isomp.cu", "comm.cu", "probe.cu"]
+SOURCES = ["api.cu", "poisson.cu", "zgemm.cu", "isomp.cu", "comm.cu", "probe.cu", "shr.cu"]
 
 
 def _nccl_paths():

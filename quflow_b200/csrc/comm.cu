@@ -227,6 +227,9 @@ static int p2p_finish(qf_handle_s *h, QfP2P *p)
         // outweighs the replicated mirror pass, i.e. from four ranks on.  QF_XCHG_UPPER=0|1 overrides.
         const char *u = getenv("QF_XCHG_UPPER");
         p->desc.upper_only = u ? (u[0] == '1') : (nranks >= 4);
+        const char *m = getenv("QF_XCHG_PUSH");
+        h->xchg_ce = (m && strcmp(m, "ce") == 0) ? 1 : 0;
+        h->skew_host = -1;
     }
     {
         // ranks may legitimately be seconds apart (host work between calls): the bound only has to end a real hang
@@ -513,6 +516,33 @@ int qf_xchg_push_wh(qf_handle_s *h, bool gated, cudaStream_t st)
 {
     const QfXchg *x = qf_xchg_desc(h);
     if (!x) { qf_set_error("qf_xchg_push_wh: the handle has no tile-exchange communicator"); return QF_ERR_INVALID; }
+    if (h->xchg_ce) {
+        // Copy-engine variant (QF_XCHG_PUSH=ce): the same rectangles as k_xchg_push_wh as 2-D device-to-device copies
+        // into the peer mappings — memcpy nodes inside the step graph, no SM involved.  Not gated by the device flag: in
+        // the graph they only run when the loop body runs; with eager launches a repeated copy of unchanged tiles is
+        // harmless.  The upper-only decision needs the host copy of QfCtrl.skew_exact (qf_xchg_skew_check).
+        QfP2P *p = reinterpret_cast<QfP2P *>(h->p2p);
+        const QfArenaLayout l = arena_layout(h);
+        const int N = h->N, hb = x->hb, G = x->nranks;
+        const bool upper_only = x->upper_only && h->skew_host == 1;
+        const size_t pitch = sizeof(double2) * (size_t)N;
+        for (int q = 0; q < 2; ++q) {
+            const int b = q ? 2 * G - 1 - x->rank : x->rank;
+            const size_t r0 = (size_t)b * hb;
+            for (int pr = 0; pr < G; ++pr) {
+                if (pr == x->rank) continue;
+                char *dst = p->peerArena[pr] + l.wh;
+                const char *src = (const char *)h->Wh;
+                const size_t offU = (r0 * N + r0) * sizeof(double2);
+                QF_CUDA(cudaMemcpy2DAsync(dst + offU, pitch, src + offU, pitch, sizeof(double2) * (N - r0), hb, cudaMemcpyDeviceToDevice, st));
+                if (!upper_only && r0 + hb < (size_t)N) {
+                    const size_t offM = ((r0 + hb) * N + r0) * sizeof(double2);
+                    QF_CUDA(cudaMemcpy2DAsync(dst + offM, pitch, src + offM, pitch, sizeof(double2) * hb, N - r0 - hb, cudaMemcpyDeviceToDevice, st));
+                }
+            }
+        }
+        return QF_OK;
+    }
     k_xchg_push_wh<<<h->sm_count * 4, 256, 0, st>>>(*x, h->N, h->ctrl, gated ? 1 : 0);
     h->launches++;
     QF_CUDA(cudaGetLastError());
@@ -594,6 +624,14 @@ int qf_xchg_skew_check(qf_handle_s *h, const double2 *W, cudaStream_t st)
     k_xchg_skew_check<<<dim3(nb, nb), 256, 0, st>>>(W, h->N, h->ctrl);
     h->launches += 2;
     QF_CUDA(cudaGetLastError());
+    if (h->xchg_ce) {
+        // the copy-engine variant enqueues different copies for the two cases: the host has to know
+        QF_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QfCtrl), cudaMemcpyDeviceToHost, st));
+        QF_CUDA(cudaStreamSynchronize(st));
+        const int skew = h->ctrl_host[0].skew_exact;
+        if (skew != h->skew_host) qf_graph_destroy(h);      // the step graph bakes the copies in
+        h->skew_host = skew;
+    }
     return QF_OK;
 }
 

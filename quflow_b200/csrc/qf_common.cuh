@@ -128,7 +128,8 @@ struct qf_handle_s {
     void *p2p = nullptr;          // QfP2P (comm.cu)
     int comm_mode = 0;            // 0: none / emulated, 1: NCCL all-gather of A and S (eager only), 2: peer-memory pull
                                   // kernels for A and S, 5: tile exchange (default: sharded fused tail, W~ pushed by owners)
-    void *xchg = nullptr;         // QfXchgHost (comm.cu)
+    int xchg_ce = 0;              // tile exchange: W~ tiles travel by copy engines (memcpy nodes) instead of a copy kernel
+    int skew_host = -1;           // host copy of QfCtrl.skew_exact of the current call (copy-engine mode only)
     int rank = 0, nranks = 1;     // nranks > 1 with nccl_comm == nullptr: all ranks emulated on this GPU (tests)
     QfGemmPlan *gemm = nullptr;
     // CUDA-graph execution of a step (isomp.cu)

@@ -143,3 +143,28 @@ def test_inner_products_and_loggers(qf):
     qf.isomp(W1, 0.25 * qf.hbar(N), steps=20)
     assert qf.enstrophy(W1) == pytest.approx(qf.enstrophy(W), rel=1e-9)
     assert qf.energy_euler(W1) == pytest.approx(qf.energy_euler(W), rel=1e-8)      # near-conserved (oracle: -7e-10)
+
+
+@pytest.mark.parametrize("N", [16, 33])
+def test_mat2shr_shr2mat_vs_reference_golden(N):
+    """mat2shr / shr2mat on the device against the REAL reference's outputs for its own basis
+    (oracle/gen_golden_shr.py -> tests/golden/shr_N*.npz; reference: quantization.py:172-227, 283-325)."""
+    import torch
+    import quflow_b200 as qf
+    from quflow_b200.quantization import device_basis, basis_size
+    g = golden(f"shr_N{N}.npz")
+    assert basis_size(N) == g["basis"].size
+    B = device_basis(g["basis"])
+    scale = np.abs(g["omega_full"]).max()
+    om = qf.mat2shr(g["W"], B)                                   # numpy in -> numpy out
+    assert isinstance(om, np.ndarray) and np.abs(om - g["omega_full"]).max() < 1e-13 * scale
+    om7 = qf.mat2shr(torch.from_numpy(g["W"]).cuda(), B, elmax=7)    # device in -> device out, truncated
+    assert om7.is_cuda and np.abs(om7.cpu().numpy() - g["omega_trunc"]).max() < 1e-13 * scale
+    Wb = qf.shr2mat(g["omega_band"], g["basis"], N=N)            # basis as numpy: uploaded by the call
+    assert np.abs(Wb - g["W_band"]).max() < 1e-13 * np.abs(g["W_band"]).max()
+    assert np.abs(Wb + Wb.conj().T).max() == 0.0                 # exactly skew-Hermitian
+    WN = qf.shr2mat(g["omega_N"], B)
+    assert relfro(WN, g["W_N"]) < 1e-13
+    # round trip through the device: mat2shr(shr2mat(omega)) == omega
+    back = qf.mat2shr(qf.shr2mat(torch.from_numpy(g["omega_N"]).cuda(), B), B)
+    assert np.abs(back.cpu().numpy() - g["omega_N"]).max() < 1e-12 * np.abs(g["omega_N"]).max()

@@ -218,3 +218,15 @@ def test_live_against_reference():
     W = oracle.isomp(W0.copy(), dt, steps=40, stats=st)
     assert st == st_ref or (st['iterations'] == st_ref['iterations'] and st['tol_auto'] == pytest.approx(st_ref['tol_auto'], rel=1e-14))
     assert relfro(W, Wref) < 1e-12
+
+
+@pytest.mark.parametrize("N", [16, 33])
+def test_shr_oracle_against_reference_golden(N):
+    """The mat2shr / shr2mat restatement against outputs of the real reference (oracle/gen_golden_shr.py)."""
+    from oracle import shr_oracle
+    g = golden(f"shr_N{N}.npz")
+    scale = np.abs(g["omega_full"]).max()
+    assert np.abs(shr_oracle.mat2shr(g["W"], g["basis"]) - g["omega_full"]).max() < 1e-13 * scale
+    assert np.abs(shr_oracle.mat2shr(g["W"], g["basis"], 64) - g["omega_trunc"]).max() < 1e-13 * scale
+    assert relfro(shr_oracle.shr2mat(g["omega_band"], g["basis"], N), g["W_band"]) < 1e-13
+    assert relfro(shr_oracle.shr2mat(g["omega_N"], g["basis"], N), g["W_N"]) < 1e-13

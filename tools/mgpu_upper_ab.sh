@@ -5,9 +5,12 @@ G=${1:-2}; TAG=${2:-r02f}
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1"
 QF_XCHG_UPPER=1 timeout 600 $RUN --master-port 29511 tests/mgpu_check.py > gpurun_out/${TAG}_g${G}_parity_upper.log 2>&1
 grep "MGPU_" gpurun_out/${TAG}_g${G}_parity_upper.log || tail -20 gpurun_out/${TAG}_g${G}_parity_upper.log
-for up in 0 1; do
+QF_XCHG_PUSH=ce QF_XCHG_UPPER=1 timeout 600 $RUN --master-port 29513 tests/mgpu_check.py > gpurun_out/${TAG}_g${G}_parity_ce.log 2>&1
+grep "MGPU_" gpurun_out/${TAG}_g${G}_parity_ce.log || tail -20 gpurun_out/${TAG}_g${G}_parity_ce.log
+for up in 0 1 ce0 ce1; do
     out=gpurun_out/${TAG}_g${G}_upper$up.json
-    QF_XCHG_UPPER=$up timeout 600 $RUN --master-port 2951$up bench.py --gpus $G --steps 40 --warmup 5 --no-cpu-baseline 2>gpurun_out/${TAG}_g${G}_upper$up.err | tail -1 > $out
+    case $up in ce*) export QF_XCHG_PUSH=ce;; *) export QF_XCHG_PUSH=sm;; esac
+    QF_XCHG_UPPER=${up#ce} timeout 600 $RUN --master-port 29515 bench.py --gpus $G --steps 40 --warmup 5 --no-cpu-baseline 2>gpurun_out/${TAG}_g${G}_upper$up.err | tail -1 > $out
     python - "$out" "$up" <<'PY'
 import json, sys
 try:
