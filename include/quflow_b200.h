@@ -200,6 +200,12 @@ typedef struct {
     float gemm2_ms;     /* S = A P~ (+ fused epilogue when enabled) */
     float post_ms;      /* dW = S + A - A^H, residual row sums, control */
     float update_ms;    /* W += 2 (A - A^H) */
+    /* tile-exchange path only (0 otherwise): post_ms split into its parts */
+    float x_tail_ms;    /* sharded tail kernel (dW, W~, residual partials of the owned tile pairs) */
+    float x_push_ms;    /* copy kernel: owned W~ tiles -> every peer */
+    float x_wait_ms;    /* signal + wait for every peer's signal (absorbs the skew between ranks) */
+    float x_mirror_ms;  /* lower triangle of W~ rebuilt locally (upper-only exchange) */
+    float x_control_ms; /* stopping rule */
 } qf_phase_times;
 
 /* Runs `reps` fixed-point iterations on the current state of W_dev (which is left unchanged)

@@ -46,7 +46,9 @@ class qf_stats(ctypes.Structure):
 
 class qf_phase_times(ctypes.Structure):
     _fields_ = [("poisson_ms", ctypes.c_float), ("gemm1_ms", ctypes.c_float), ("gemm2_ms", ctypes.c_float),
-                ("post_ms", ctypes.c_float), ("update_ms", ctypes.c_float)]
+                ("post_ms", ctypes.c_float), ("update_ms", ctypes.c_float), ("x_tail_ms", ctypes.c_float),
+                ("x_push_ms", ctypes.c_float), ("x_wait_ms", ctypes.c_float), ("x_mirror_ms", ctypes.c_float),
+                ("x_control_ms", ctypes.c_float)]
 
 
 _lib = None

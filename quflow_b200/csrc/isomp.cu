@@ -509,7 +509,7 @@ static inline double qf_hbar(int N) { return 2.0 / sqrt((double)N * (double)N - 
 enum { QF_PH_A = 1, QF_PH_B = 2, QF_PH_C = 4, QF_PH_ALL = 7 };
 
 int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit, int minit, cudaStream_t st,
-                         cudaEvent_t *ev /* 5 events or null */, int phases = QF_PH_ALL)
+                         cudaEvent_t *ev /* 11 events or null: 0-4 phases, 7-10 the exchange of the tile path */, int phases = QF_PH_ALL)
 {
     const int N = h->N;
     const int G = h->nranks;
@@ -586,14 +586,18 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
             // the owners of the tile pairs form dW, W~ and the residual partials and push W~ / the partials to every peer
             k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, Gp, W, h->Wh, nullptr, 0.0, *xg);
             h->launches++;
+            if (ev) QF_CUDA(cudaEventRecord(ev[7], st));
             QF_CHECK(qf_xchg_push_wh(h, true, st));
+            if (ev) QF_CUDA(cudaEventRecord(ev[8], st));
             QF_CHECK(qf_xchg_signal(h, QF_XF_X, true, st));
         }
     }
     if (phases & QF_PH_C) {
         if (xmode) {
             QF_CHECK(qf_xchg_wait(h, QF_XF_X, true, st));
+            if (ev) QF_CUDA(cudaEventRecord(ev[9], st));
             QF_CHECK(qf_xchg_mirror_wh(h, true, st));
+            if (ev) QF_CUDA(cudaEventRecord(ev[10], st));
         } else {
             k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, Gp, W, h->Wh, nullptr, 0.0, solo);
             h->launches++;
@@ -1178,8 +1182,10 @@ extern "C" int qf_profile_iteration(qf_handle_t h, const void *W_dev, double dt,
     const int N = h->N, B = h->batch;
     const size_t n2 = h->mat_elems;
     const double eps = dt / (2.0 * qf_hbar(N));
-    cudaEvent_t ev[7];
+    cudaEvent_t ev[11];
     for (auto &e : ev) QF_CUDA(cudaEventCreate(&e));
+    const bool xsplit = h->nranks > 1 && h->comm_mode == 5 && !(h->fuse_post && qf_gemm_can_fuse_post(h));
+    float xacc[5] = {0, 0, 0, 0, 0};
     if (!h->io) QF_CUDA(cudaMalloc(&h->io, sizeof(double2) * n2 * B));
     QF_CUDA(cudaMemcpyAsync(h->io, W_dev, sizeof(double2) * n2 * B, cudaMemcpyDeviceToDevice, st));
     QF_CUDA(cudaMemsetAsync(h->dW, 0, sizeof(double2) * n2 * B, st));
@@ -1202,12 +1208,24 @@ extern "C" int qf_profile_iteration(qf_handle_t h, const void *W_dev, double dt,
         }
         QF_CUDA(cudaEventElapsedTime(&ms, ev[5], ev[6]));
         acc[4] += ms;
+        if (xsplit) {
+            const int order[6] = {3, 7, 8, 9, 10, 4};      // GEMM 2 done | tail kernel | W~ push | signal + wait | mirror | control
+            for (int p = 0; p < 5; ++p) {
+                QF_CUDA(cudaEventElapsedTime(&ms, ev[order[p]], ev[order[p + 1]]));
+                xacc[p] += ms;
+            }
+        }
     }
     out->poisson_ms = acc[0] / reps;
     out->gemm1_ms = acc[1] / reps;
     out->gemm2_ms = acc[2] / reps;
     out->post_ms = acc[3] / reps;
     out->update_ms = acc[4] / reps;
+    out->x_tail_ms = xacc[0] / reps;
+    out->x_push_ms = xacc[1] / reps;
+    out->x_wait_ms = xacc[2] / reps;
+    out->x_mirror_ms = xacc[3] / reps;
+    out->x_control_ms = xacc[4] / reps;
     for (auto &e : ev) cudaEventDestroy(e);
     return QF_OK;
 }

@@ -179,6 +179,7 @@ struct QfXchg {
     unsigned long long *myFlags = nullptr;
     long long timeout_cycles = 60000000000ll;         // give up on a silent peer after this many SM cycles (QF_COMM_TIMEOUT_S)
     int upper_only = 0;                               // W~ exchange: send upper tiles only when W is exactly skew-Hermitian
+    int dbg_skip_a = 0;                               // timing experiments only (QF_XCHG_DEBUG_SKIP_A=1): GEMM 1 pushes nothing
 };
 __host__ __device__ __forceinline__ int qf_owner_of_row(int row, int hb, int G)
 {

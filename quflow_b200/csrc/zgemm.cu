@@ -745,7 +745,7 @@ k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, 
             // tile-exchange path, GEMM 1: a tile strictly below the diagonal is needed (transposed) by the rank that owns
             // its column block; it goes there as plain stores through the NVLink peer mapping while the next tile is
             // being multiplied
-            if (xg.nranks > 1 && ti.col0 + BN <= ti.a_row0) {
+            if (xg.nranks > 1 && ti.col0 + BN <= ti.a_row0 && !xg.dbg_skip_a) {
                 const int oc = qf_owner_of_row(ti.col0, xg.hb, xg.nranks);
                 if (oc != xg.rank)
                     gemm_store_tile<M3>(acc, xg.peerA[oc] + moff, N, ti.c_row0, ti.c_row0 + (ti.row_end - ti.a_row0), ti.col0, wm, wn, g, t);
