@@ -195,13 +195,11 @@ extern "C" int qf_isomp_host(qf_handle_t h, void *W_host, double dt, int steps, 
         const size_t blk = sizeof(double2) * (size_t)hb * h->N;
         const int blocks[2] = {h->rank, 2 * G - 1 - h->rank};
         // everybody has finished reading the previous call's state before anyone overwrites it
-        QF_CHECK(qf_xchg_signal(h, QF_XF_X, false, 0));
-        QF_CHECK(qf_xchg_wait(h, QF_XF_X, false, 0));
+        QF_CHECK(qf_xchg_barrier(h, QF_XF_X, false, 0));
         for (int q = 0; q < 2; ++q)
             QF_CUDA(cudaMemcpyAsync((char *)h->Wst + blocks[q] * blk, (const char *)W_host + blocks[q] * blk, blk, cudaMemcpyHostToDevice, 0));
         QF_CHECK(qf_xchg_push_rows(h, 0));
-        QF_CHECK(qf_xchg_signal(h, QF_XF_X, false, 0));
-        QF_CHECK(qf_xchg_wait(h, QF_XF_X, false, 0));
+        QF_CHECK(qf_xchg_barrier(h, QF_XF_X, false, 0));
         int rc = qf_isomp_impl(h, nullptr, dt, steps, tol, maxit, minit, flags, stats, iters_per_step, 0);
         if (rc != QF_OK && rc != QF_ERR_NONFINITE) return rc;
         for (int q = 0; q < 2; ++q)

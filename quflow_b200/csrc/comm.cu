@@ -429,6 +429,23 @@ __global__ void k_xchg_signal(const QfXchg x, int kind, const QfCtrl *__restrict
     }
 }
 
+// signal + wait in one launch (a real multi-GPU run; the lock-step emulation needs them apart)
+__global__ void k_xchg_barrier(const QfXchg x, int kind, QfCtrl *ctrl, int gated)
+{
+    if (gated && !ctrl[0].active) return;
+    const unsigned long long seq = (kind == QF_XF_G1 ? ctrl[0].gseq : ctrl[0].xseq) + 1ull;
+    const int t = threadIdx.x;
+    if (t < x.nranks && t != x.rank) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(x.peerFlags[t] + kind * QF_MAX_RANKS + x.rank) = seq;
+    }
+    __syncwarp();
+    if (t == 0) {
+        if (ctrl[0].nonfinite != 2 && !xchg_wait_flags(x, kind, seq)) ctrl[0].nonfinite = 2;
+        if (kind == QF_XF_X) ctrl[0].xseq = seq;
+    }
+}
+
 __global__ void k_xchg_wait(const QfXchg x, int kind, QfCtrl *ctrl, int gated)
 {
     if (gated && !ctrl[0].active) return;
@@ -442,6 +459,16 @@ int qf_xchg_signal(qf_handle_s *h, int kind, bool gated, cudaStream_t st)
     const QfXchg *x = qf_xchg_desc(h);
     if (!x) { qf_set_error("qf_xchg_signal: the handle has no tile-exchange communicator"); return QF_ERR_INVALID; }
     k_xchg_signal<<<1, 32, 0, st>>>(*x, kind, h->ctrl, gated ? 1 : 0);
+    h->launches++;
+    QF_CUDA(cudaGetLastError());
+    return QF_OK;
+}
+
+int qf_xchg_barrier(qf_handle_s *h, int kind, bool gated, cudaStream_t st)
+{
+    const QfXchg *x = qf_xchg_desc(h);
+    if (!x) { qf_set_error("qf_xchg_barrier: the handle has no tile-exchange communicator"); return QF_ERR_INVALID; }
+    k_xchg_barrier<<<1, 32, 0, st>>>(*x, kind, h->ctrl, gated ? 1 : 0);
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;
@@ -511,7 +538,7 @@ k_xchg_push_wh(const QfXchg x, int N, const QfCtrl *__restrict__ ctrl, int gated
             }
         }
     }
-    __threadfence_system();      // remote stores are performed before the kernel (and the flag that follows it) completes
+    // no fence: the kernel boundary orders these stores before the signal kernel, whose system-scope fence precedes the flag
 }
 
 int qf_xchg_push_wh(qf_handle_s *h, bool gated, cudaStream_t st)

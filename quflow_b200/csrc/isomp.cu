@@ -91,9 +91,10 @@ __global__ void k_zero(double2 *X, size_t n2, const QfCtrl *__restrict__ ctrl)
 // It also writes the next iterate W~ = W + dW (both triangles), so no separate pass is needed before the Poisson solve.
 // Tile-exchange path (xg.nranks > 1): a tile pair is processed by the rank that owns row block bi only — the rows of A and
 // S it needs are its own, the transposed tile of A was pushed to it by the owner of row block bj during the first GEMM
-// (the block's first thread waits for every peer's "GEMM 1 complete" flag) — and the residual partials are stored into
+// (a wait kernel for every peer's "GEMM 1 complete" flag precedes this one) — and the residual partials are stored into
 // every peer's copy as well, through the NVLink peer mappings; the new W~ tiles follow in a copy kernel of their own
-// (comm.cu: k_xchg_push_wh).
+// (comm.cu: k_xchg_push_wh).  Peer stores need no fence here: the kernel boundary orders them before the signal kernel,
+// whose system-scope fence precedes the flag.
 template <bool FORCING>
 __global__ void __launch_bounds__(256)
 k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *__restrict__ dWg, double *__restrict__ rowpart,
@@ -105,11 +106,7 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
     const int bi = blockIdx.y, bj = blockIdx.x;
     if (bi > bj) return;
     const bool xpush = xg.nranks > 1;
-    if (xpush) {
-        if (qf_owner_of_row(bi * TS, xg.hb, xg.nranks) != xg.rank) return;
-        if (threadIdx.x == 0 && ctrl[0].nonfinite != 2 && !xchg_wait_flags(xg, QF_XF_G1, ctrl[0].gseq + 1ull)) ctrl[0].nonfinite = 2;
-        __syncthreads();
-    }
+    if (xpush && qf_owner_of_row(bi * TS, xg.hb, xg.nranks) != xg.rank) return;
     __shared__ double2 T[TS][TS + 1];
     __shared__ double2 D[TS][TS + 1];
     __shared__ double R[TS][TS + 1];
@@ -192,7 +189,6 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
                     if (p != xg.rank) xg.peerPart[p][(size_t)(mirr - rowpart) + (size_t)j * nslots + bi] = s;
         }
     }
-    if (xpush) __threadfence_system();     // remote stores are performed before the kernel (and the flag that follows it) completes
 }
 
 // ------------------------------------------------------------------------------- control
@@ -559,12 +555,13 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
             if (ev) QF_CUDA(cudaEventRecord(ev[3], st));
             if (xmode) {
                 QF_CHECK(qf_xchg_push_wh(h, true, st));
-                QF_CHECK(qf_xchg_signal(h, QF_XF_X, true, st));
+                if (phases != QF_PH_ALL) QF_CHECK(qf_xchg_signal(h, QF_XF_X, true, st));
             }
         }
         if (phases & QF_PH_C) {
             if (xmode) {
-                QF_CHECK(qf_xchg_wait(h, QF_XF_X, true, st));             // every peer's W~ tiles and partials have landed
+                // every peer's W~ tiles and partials have landed
+                QF_CHECK(phases == QF_PH_ALL ? qf_xchg_barrier(h, QF_XF_X, true, st) : qf_xchg_wait(h, QF_XF_X, true, st));
                 QF_CHECK(qf_xchg_mirror_wh(h, true, st));
             }
             k_control<<<gc, 256, 0, st>>>(part_direct, h->nsd, part_mirror, h->nsm, N, h->ctrl, maxit, minit, nfollow, h->cap_cond,
@@ -583,18 +580,20 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
         if (legacy_comm) QF_CHECK(h->comm_mode == 2 ? qf_comm_p2p_allgather(h, 1, true, st) : qf_comm_allgather_rows(h, h->S, st));
         if (ev) QF_CUDA(cudaEventRecord(ev[3], st));
         if (xmode) {
-            // the owners of the tile pairs form dW, W~ and the residual partials and push W~ / the partials to every peer
+            // the owners of the tile pairs form dW, W~ and the residual partials and push W~ / the partials to every peer;
+            // the transposed A tiles they read were pushed by the peers during THEIR first GEMM: wait for those first
+            QF_CHECK(qf_xchg_wait(h, QF_XF_G1, true, st));
             k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, Gp, W, h->Wh, nullptr, 0.0, *xg);
             h->launches++;
             if (ev) QF_CUDA(cudaEventRecord(ev[7], st));
             QF_CHECK(qf_xchg_push_wh(h, true, st));
             if (ev) QF_CUDA(cudaEventRecord(ev[8], st));
-            QF_CHECK(qf_xchg_signal(h, QF_XF_X, true, st));
+            if (phases != QF_PH_ALL) QF_CHECK(qf_xchg_signal(h, QF_XF_X, true, st));
         }
     }
     if (phases & QF_PH_C) {
         if (xmode) {
-            QF_CHECK(qf_xchg_wait(h, QF_XF_X, true, st));
+            QF_CHECK(phases == QF_PH_ALL ? qf_xchg_barrier(h, QF_XF_X, true, st) : qf_xchg_wait(h, QF_XF_X, true, st));
             if (ev) QF_CUDA(cudaEventRecord(ev[9], st));
             QF_CHECK(qf_xchg_mirror_wh(h, true, st));
             if (ev) QF_CUDA(cudaEventRecord(ev[10], st));
@@ -633,11 +632,11 @@ int qf_enqueue_update(qf_handle_s *h, double2 *W, bool compsum, bool reinit, cud
         QF_CUDA(cudaGetLastError());
         if (xmode) {
             QF_CHECK(qf_xchg_push_wh(h, false, st));
-            QF_CHECK(qf_xchg_signal(h, QF_XF_X, false, st));
+            if (phases != 3) QF_CHECK(qf_xchg_signal(h, QF_XF_X, false, st));
         }
     }
     if ((phases & 2) && xmode) {
-        QF_CHECK(qf_xchg_wait(h, QF_XF_X, false, st));
+        QF_CHECK(phases == 3 ? qf_xchg_barrier(h, QF_XF_X, false, st) : qf_xchg_wait(h, QF_XF_X, false, st));
         QF_CHECK(qf_xchg_mirror_wh(h, false, st));
     }
     return QF_OK;
@@ -855,10 +854,10 @@ static int isomp_call_gather(qf_handle_s *h, const IsompCall &c, void *W_dev, cu
     if (!c.xmode) return QF_OK;
     if (phases & 1) {
         QF_CHECK(qf_xchg_push_state(h, st));
-        QF_CHECK(qf_xchg_signal(h, QF_XF_X, false, st));
+        if (phases != 3) QF_CHECK(qf_xchg_signal(h, QF_XF_X, false, st));
     }
     if (phases & 2) {
-        QF_CHECK(qf_xchg_wait(h, QF_XF_X, false, st));
+        QF_CHECK(phases == 3 ? qf_xchg_barrier(h, QF_XF_X, false, st) : qf_xchg_wait(h, QF_XF_X, false, st));
         if (W_dev) QF_CUDA(cudaMemcpyAsync(W_dev, h->Wst, sizeof(double2) * h->mat_elems, cudaMemcpyDeviceToDevice, st));
     }
     return QF_OK;

@@ -263,6 +263,7 @@ void qf_p2p_destroy(qf_handle_s *h);
 const QfXchg *qf_xchg_desc(qf_handle_s *h);                                          // nullptr unless comm_mode == 5
 int qf_xchg_signal(qf_handle_s *h, int kind, bool gated, cudaStream_t st);           // raise my flag of `kind` at every peer
 int qf_xchg_wait(qf_handle_s *h, int kind, bool gated, cudaStream_t st);             // until every peer raised its flag here
+int qf_xchg_barrier(qf_handle_s *h, int kind, bool gated, cudaStream_t st);          // both in one launch (not for the lock-step emulation)
 int qf_xchg_push_wh(qf_handle_s *h, bool gated, cudaStream_t st);                    // my tiles of W~ -> every peer
 int qf_xchg_mirror_wh(qf_handle_s *h, bool gated, cudaStream_t st);                  // lower triangle of W~ from the upper one
 int qf_xchg_skew_check(qf_handle_s *h, const double2 *W, cudaStream_t st);           // -> ctrl[0].skew_exact

@@ -752,7 +752,8 @@ k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, 
             }
         }
     }
-    if (xg.nranks > 1) __threadfence_system();   // remote stores are performed before the kernel (and the flag that follows it) completes
+    // peer stores need no fence here: the kernel boundary orders them before the signal kernel, whose system-scope fence
+    // precedes the flag
 }
 
 }   // namespace
