@@ -363,6 +363,18 @@ def gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = args.steps / (ms * 1e-3)
+    # run-to-run spread: the same K-step region again (the state simply keeps evolving), NOT part of `value`
+    repeat_values = []
+    for _ in range(max(args.repeats - 1, 0)):
+        barrier()
+        e0.record()
+        handle.isomp(W, kw["dt"], args.steps, maxit=kw["maxit"], minit=kw["minit"])
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        repeat_values.append(args.steps / (float(t.item()) * 1e-3))
 
     # ---- e2e: public API, host buffers, one call per step ------------------------------------------
     Wpin = torch.from_numpy(W0.copy()).pin_memory()
@@ -494,6 +506,8 @@ def gpu_arm(args):
                         f"{world} GPUs: one simulation sharded by row blocks, data path '{handle.comm_mode()}' over NVLink "
                         f"peer memory (DESIGN.md section 4)"),
         "iterations_per_sec": value * its,
+        "repeat_values": {"values": repeat_values, "note": f"the same {args.steps}-step region timed {len(repeat_values)} more "
+                          "time(s) right after `value` (the state keeps evolving): run-to-run spread on this box"},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "steps/s",
                 "h2d_bytes_per_step": 16 * N * N * (1 if (world == 1 or own_rows) else world),
@@ -629,6 +643,7 @@ def main():
                     help="matrix size N (use --size under torch.distributed.run, whose own parser claims --n*)")
     ap.add_argument("--mode", default="natural", choices=["natural", "profile"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--repeats", type=int, default=3, help="timed regions in all: `value` is the first, the others are reported as spread")
     ap.add_argument("--workload", default="single", choices=["single", "ensemble"],
                     help="single: one R(N,42) simulation (row-sharded across GPUs); ensemble: BASELINE config 5, "
                          "--members independent N=256 simulations per GPU (weak scaling, no collective)")

@@ -32,11 +32,12 @@ static bool qf_poisson_plan_host(int N, int &L, int &M, int &NT, int &CL, std::v
 {
     // Measured at N = 2048: 16 positions per thread, 4 diagonals per band and CTAs of up to 512
     // threads are the fastest combination (8 positions: +13 us; 8 diagonals: +7 us; 256-thread cluster pairs: +3 us).
-    L = 16;
+    // Up to N = 1024 a band fits one CTA even with 8 positions per thread, and the solve is a pure latency chain there:
+    // half the sequential depth per thread wins (measured 14.2 -> 12.5 us at N = 512, 19.3 -> 17.0 us at N = 1024).
+    L = (N <= 1024) ? 8 : 16;
     {
-        // QF_POISSON_L=8: eight positions per thread (half the sequential chain, twice the threads per diagonal)
-        const char *env = getenv("QF_POISSON_L");
-        if (env && atoi(env) == 8) L = 8;
+        const char *env = getenv("QF_POISSON_L");          // 8 or 16: override for experiments
+        if (env && (atoi(env) == 8 || atoi(env) == 16)) L = atoi(env);
     }
     M = 4;
     const int NTMAX = 512;

@@ -18,8 +18,10 @@ state stays on the GPU for the whole run; every output interval costs one asynch
 double buffer, and the callbacks (HDF5 append, loggers) run on a worker thread while the next chunk of steps is already
 computing (``_OutputPipeline``).
 
-Only the ``mat`` representation is written (``fun``/``shr``/``shc`` need the spherical-harmonic transforms, which are
-outside the hot path).  h5py is imported lazily: it is not part of this image, and nothing on the compute path needs it.
+The ``mat`` and ``shr`` representations are written (``shr``: real spherical-harmonic coefficients through the device
+``mat2shr``, given the reference's quantization basis); ``fun``/``funL2``/``shc`` need the spherical-harmonic transforms
+of the reference, which are outside the hot path.  h5py is imported lazily: it is not part of this image, and nothing on
+the compute path needs it.
 """
 import datetime
 import inspect
@@ -51,10 +53,16 @@ def _h5py():
 class QuSimulation(object):
     """HDF5-backed simulation record, usable as the ``callback`` of :func:`solve` (simulation.py:49-478)."""
 
+    _SUPPORTED_QUTYPES = ('mat', 'shr')
+
     def __init__(self, filename, qutypes=None, datapath="/", overwrite=False, loggers=None, state=None, time=None,
-                 **fields):
+                 basis=None, **fields):
+        """``basis`` (new; not stored in the file): the reference's quantization basis for this N
+        (``quflow.quantization.get_basis(N)``, numpy array or CUDA tensor).  With it the ``'shr'`` representation
+        (real spherical-harmonic coefficients, ``mat2shr`` on the device) can be stored next to ``'mat'``."""
         if datapath[-1] != "/":
             raise ValueError("Datapath must end with /")                       # simulation.py:110-111
+        self.basis = basis
         self.filename = filename
         self.datapath = datapath
         self.args_datapath = datapath + "args/"
@@ -64,10 +72,7 @@ class QuSimulation(object):
             if state is None:
                 raise ValueError("At least `state` must be provided to initialize a QuSimulation.")
             self.qutypes = {'mat': None} if qutypes is None else dict(qutypes)
-            unsupported = [q for q in self.qutypes if q != 'mat']
-            if unsupported:
-                raise NotImplementedError("quflow_b200.QuSimulation stores the 'mat' representation only "
-                                          f"(got {unsupported}); fun/shr/shc need the SHT layer of the reference")
+            self._check_qutypes(filename)
             self._create(np.asarray(state), 0.0 if time is None else float(time), fields)
         else:
             if state is not None:
@@ -77,15 +82,30 @@ class QuSimulation(object):
             with _h5py().File(filename, "r") as f:
                 g = f[self.datapath]
                 self.qutypes = pickle.loads(bytes(g.attrs["qutypes"][0]))
-                unsupported = [q for q in self.qutypes if q != 'mat']
-                if unsupported:
-                    # appending only `mat` would leave the other datasets one row behind per record: refuse
-                    raise NotImplementedError(
-                        f"{filename} stores the representations {sorted(self.qutypes)}; quflow_b200.QuSimulation can only "
-                        "continue files whose qutypes are {'mat'} (fun/shr/shc need the SHT layer of the reference)")
+                # appending only some of the stored representations would leave the others one row behind per record
+                self._check_qutypes(filename)
                 if "loggers" in g.attrs:
                     self.loggers = pickle.loads(bytes(g.attrs["loggers"][0]))
         self._refresh_fieldnames()
+
+    def _check_qutypes(self, filename):
+        unsupported = [q for q in self.qutypes if q not in self._SUPPORTED_QUTYPES]
+        if unsupported:
+            raise NotImplementedError(
+                f"{filename}: quflow_b200.QuSimulation stores the representations 'mat' and 'shr' (got {sorted(self.qutypes)}); "
+                "fun/funL2/shc need the spherical-harmonic transforms of the reference")
+        if 'shr' in self.qutypes and self.basis is None:
+            raise ValueError(f"{filename}: the 'shr' representation needs the quantization basis: QuSimulation(..., basis=get_basis(N))")
+
+    def _representations(self, W):
+        """(dataset name, array, qutype) for every stored representation (reference: qutypes_iterator, simulation.py:287-355)."""
+        for qutype, dtype in self.qutypes.items():
+            if qutype == 'mat':
+                yield 'mat', W.astype(dtype or W.dtype), qutype
+            elif qutype == 'shr':
+                from .quantization import mat2shr
+                omega = np.squeeze(np.array([mat2shr(np.ascontiguousarray(Wi), self.basis) for Wi in W.reshape((-1,) + W.shape[-2:])]))
+                yield 'shr', omega.astype(dtype or omega.dtype), qutype
 
     # ------------------------------------------------------------------ creation
     def _create(self, W, time, fields):
@@ -101,12 +121,11 @@ class QuSimulation(object):
             except (AttributeError, pickle.PicklingError):
                 pass
             f.create_group(self.args_datapath)
-            dtype = self.qutypes['mat'] or W.dtype
-            arr = W.astype(dtype)
-            ds = f.create_dataset(self.datapath + "mat", (1,) + arr.shape, dtype=arr.dtype, maxshape=(None,) + arr.shape,
-                                  chunks=(1,) + arr.shape)
-            ds[0, ...] = arr
-            ds.attrs["qutype"] = "mat"
+            for name, arr, qutype in self._representations(W):                # simulation.py:367-375
+                ds = f.create_dataset(self.datapath + name, (1,) + arr.shape, dtype=arr.dtype, maxshape=(None,) + arr.shape,
+                                      chunks=(1,) + arr.shape)
+                ds[0, ...] = arr
+                ds.attrs["qutype"] = qutype
             g.attrs["N"] = W.shape[-1]
             f.create_dataset(self.datapath + "time", (1,), dtype=np.float64, maxshape=(None,))[0] = time
             f.create_dataset(self.datapath + "step", (1,), dtype=int, maxshape=(None,))[0] = 0
@@ -144,8 +163,8 @@ class QuSimulation(object):
                 ds[-1, ...] = value
                 return ds
 
-            ds = f[self.datapath + "mat"]
-            push("mat", W.astype(ds.dtype))
+            for name, arr, _ in self._representations(W):                      # simulation.py:450-453
+                push(name, arr.astype(f[self.datapath + name].dtype))
             t = f[self.datapath + "time"]
             push("time", t[-1] + delta_time)
             s = f[self.datapath + "step"]

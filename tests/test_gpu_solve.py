@@ -1,4 +1,6 @@
 """GPU tests of solve() with the device-resident isomp (BASELINE config 3's driver path, without HDF5)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -64,3 +66,33 @@ def test_solve_passes_hooks_with_the_numpy_convention(cuda_device):
         t += n * dt
     assert relfro(W, Wref) < 1e-12
     np.testing.assert_allclose(seen, ref_seen, rtol=1e-11)
+
+
+def test_qusimulation_stores_shr_through_device_mat2shr(cuda_device, tmp_path, monkeypatch):
+    """QuSimulation with qutypes {'mat', 'shr'}: the spherical-harmonic coefficients of every record come from the device
+    mat2shr (reference layout: dataset 'shr' (T, N**2), attribute qutype, quflow/simulation.py:297-304, 367-375); the run
+    goes through solve() with the asynchronous output pipeline."""
+    import sys
+    import fake_h5py
+    monkeypatch.setitem(sys.modules, "h5py", fake_h5py)
+    import quflow_b200 as qf
+    from oracle import shr_oracle
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "shr_N33.npz"))
+    N = 33
+    W = np.ascontiguousarray(g["W"])
+    fn = str(tmp_path / "shr.hdf5")
+    sim = qf.QuSimulation(fn, overwrite=True, state=W, qutypes={'mat': None, 'shr': None}, basis=g["basis"])
+    with pytest.raises(ValueError):
+        qf.QuSimulation(str(tmp_path / "nobasis.hdf5"), overwrite=True, state=W, qutypes={'shr': None})
+    qf.solve(W, stepsize=0.2, steps=30, steps_out=10, callback=sim, progress_bar=False)
+    assert sim['mat'].shape == (4, N, N) and sim['shr'].shape == (4, N * N)
+    f = fake_h5py.File(fn, "r")
+    assert f["/shr"].attrs["qutype"] == "shr" and f["/shr"].dtype == np.float64
+    for r in range(4):
+        ref = shr_oracle.mat2shr(sim['mat', r], g["basis"])
+        assert np.abs(sim['shr', r] - ref).max() < 1e-13 * np.abs(ref).max()
+    np.testing.assert_array_equal(sim['mat', -1], W)          # the caller's array ends up advanced, as with the reference
+    again = qf.QuSimulation(fn, basis=g["basis"])             # reopening a file with 'shr' needs the basis again
+    assert set(again.qutypes) == {'mat', 'shr'}
+    with pytest.raises(ValueError):
+        qf.QuSimulation(fn)

@@ -75,6 +75,14 @@ def test_qusimulation_layout_matches_reference(sim_mod, tmp_path):
     g = f["/"]
     assert set(g.attrs) >= {"version", "created", "qutypes", "loggers", "N"}           # simulation.py:134-143, 374
     assert pickle.loads(bytes(g.attrs["qutypes"][0])) == {'mat': None}
+    # byte level: the attribute values are exactly what the reference writes — a length-1 numpy bytes array holding
+    # pickle.dumps(...) of the qutypes / loggers dict (quflow/simulation.py:136-142), an ISO timestamp, the version string
+    assert g.attrs["qutypes"].shape == (1,) and g.attrs["qutypes"].dtype.kind == "S"
+    assert bytes(g.attrs["qutypes"][0]) == np.array([pickle.dumps({'mat': None})])[0]
+    assert bytes(g.attrs["loggers"][0]) == np.array([pickle.dumps({})])[0]
+    import datetime
+    datetime.datetime.fromisoformat(g.attrs["created"])
+    assert isinstance(g.attrs["version"], str)
     assert g.attrs["N"] == N
     mat = f["/mat"]
     assert mat.shape == (1, N, N) and mat.chunks == (1, N, N) and mat.maxshape == (None, N, N)   # :364-368
