@@ -205,8 +205,6 @@ int qf_build_tables(qf_handle_s *h)
         h->p_NT = NT;
         h->p_NTMAX = NTMAX;
         h->p_nunits = (int)nunits;
-        const char *occ = getenv("QF_POISSON_OCC");          // 2: two CTAs per SM (L = 8 only), experiments
-        h->p_occ = (occ && atoi(occ) == 2 && L == 8) ? 2 : 1;
     }
     return qf_poisson_prepare(h);
 }
@@ -305,9 +303,8 @@ __device__ __forceinline__ void pb_prefetch_unit(int un, const int4 *__restrict_
     }
 }
 
-// OCC: CTAs per SM the register allocation is bounded for (2 only with L = 8: 64 registers per thread)
-template <int L, int M, int CL, int NTMAX, int OCC = 1>
-__global__ void __launch_bounds__(NTMAX, OCC * 512 / NTMAX)
+template <int L, int M, int CL, int NTMAX>
+__global__ void __launch_bounds__(NTMAX, 512 / NTMAX)
 k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const double *__restrict__ tw,
                const double *__restrict__ tiu, const int4 *__restrict__ units, int N, int nunits, int pf_stride,
                double eps, const QfCtrl *__restrict__ ctrl, int gated)
@@ -772,13 +769,10 @@ __global__ void k_laplace(const double2 *__restrict__ P, double2 *__restrict__ W
 static void *poisson_band_fn(const qf_handle_s *h)
 {
     void *fn = nullptr;
-#define QF_PB(LL, CC) if (h->p_L == LL && h->p_M == 4 && h->p_CL == CC && h->p_NTMAX == 512 && h->p_occ == 1) fn = (void *)k_poisson_band<LL, 4, CC, 512, 1>;
+#define QF_PB(LL, CC) if (h->p_L == LL && h->p_M == 4 && h->p_CL == CC && h->p_NTMAX == 512) fn = (void *)k_poisson_band<LL, 4, CC, 512>;
     QF_PB(16, 1) QF_PB(16, 2) QF_PB(16, 4) QF_PB(16, 8)
     QF_PB(8, 1) QF_PB(8, 2) QF_PB(8, 4) QF_PB(8, 8)
 #undef QF_PB
-#define QF_PB2(CC) if (h->p_L == 8 && h->p_M == 4 && h->p_CL == CC && h->p_NTMAX == 512 && h->p_occ == 2) fn = (void *)k_poisson_band<8, 4, CC, 512, 2>;
-    QF_PB2(1) QF_PB2(2) QF_PB2(4) QF_PB2(8)
-#undef QF_PB2
     return fn;
 }
 
@@ -831,7 +825,7 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
         const int4 *a4 = reinterpret_cast<const int4 *>(h->ptab_units);
         int a5 = N, a6 = h->p_nunits;
         // L2 prefetch distance = units resident at once (one 512-thread CTA per SM), a multiple of the cluster size
-        int a7 = pf ? (pf > 1 ? pf : h->p_occ * (512 / h->p_NTMAX) * h->sm_count) / CL * CL : 0;
+        int a7 = pf ? (pf > 1 ? pf : (512 / h->p_NTMAX) * h->sm_count) / CL * CL : 0;
         double a8 = eps;
         const QfCtrl *a9 = h->ctrl;
         int a10 = g;

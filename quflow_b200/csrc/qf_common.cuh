@@ -102,7 +102,6 @@ struct qf_handle_s {
     int p_NT = 0;                   // threads per CTA
     int p_NTMAX = 256;              // launch bound of the instantiation in use
     int p_nunits = 0;               // CTAs in the launch
-    int p_occ = 1;                  // CTAs per SM the instantiation in use is bounded for
     int p_pf = 1;                   // L2 prefetch of the following unit (QF_POISSON_PF, read at handle creation)
     // work matrices, batch * N * N complex128 each
     double2 *dW = nullptr, *Wh = nullptr, *P = nullptr, *A = nullptr, *S = nullptr, *scratch = nullptr;
