@@ -272,26 +272,25 @@ __device__ __forceinline__ void pb_prefetch_unit(int un, const int4 *__restrict_
 
 // LU factors of position k of diagonal m (file header): closed form for m >= 1, the small table for m = 0; zero outside
 // the diagonal, which also decouples the two pieces of a unit (w = 0 at k = 0 comes out of the formula by itself).
+// All products of indices are exact in double (< 2^44);  w = -sqrt(a/b) is evaluated as -a * rsqrt(a b),  1/u with the
+// IEEE reciprocal: one special-function instruction each.
+__device__ __forceinline__ double hy_w(int k, int m, int N, bool valid, const double *__restrict__ tw0)
+{
+    if (!valid || k == 0) return 0.0;
+    if (m == 0) return __ldg(tw0 + k);
+    const double a = (double)k * (double)(N - k - m), b = (double)(k + m) * (double)(N - k);
+    return -a * rsqrt(a * b);
+}
 __device__ __forceinline__ void hy_factors(int k, int m, int N, bool valid, const double *__restrict__ tw0,
                                            const double *__restrict__ tiu0, double &w, double &iu)
 {
-    if (!valid) {
-        w = 0.0;
+    w = hy_w(k, m, N, valid, tw0);
+    if (!valid)
         iu = 0.0;
-    } else if (m == 0) {
-        w = __ldg(tw0 + k);
+    else if (m == 0)
         iu = __ldg(tiu0 + k);
-    } else {
-        const double a = (double)k * (double)(N - k - m), b = (double)(k + m) * (double)(N - k);
-        w = -sqrt(a / b);
-        iu = -1.0 / ((double)(k + m + 1) * (double)(N - k - 1));
-    }
-}
-__device__ __forceinline__ double hy_w(int k, int m, int N, bool valid, const double *__restrict__ tw0)
-{
-    if (!valid) return 0.0;
-    if (m == 0) return __ldg(tw0 + k);
-    return -sqrt(((double)k * (double)(N - k - m)) / ((double)(k + m) * (double)(N - k)));
+    else
+        iu = -__drcp_rn((double)(k + m + 1) * (double)(N - k - 1));
 }
 
 template <int L, int M, int CL, int NTMAX>
@@ -375,7 +374,20 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
     double2 r[L];
     double w[L + 1];                               // w[L]: w of the first position after the chunk
     if (warp_work) {
-        // LU factors of this thread's positions, computed from the indices while the loads below are in flight; 1/u is
+        if (nvalid == L) {
+            const double2 *rp = R + ((unsigned)plo * stride + offD);
+#pragma unroll
+            for (int i = 0; i < L; ++i) r[i] = rp[(size_t)i * stride];
+        } else {
+#pragma unroll
+            for (int i = 0; i < L; ++i) {
+                const int pl = plo + i;
+                const bool sh = pl >= PS;
+                const bool ok = sh ? (pl - PS < nS) : (pl < nL);
+                r[i] = ok ? R[(unsigned)pl * stride + (sh ? offS : offL)] : make_double2(0.0, 0.0);
+            }
+        }
+        // LU factors of this thread's positions, computed from the indices while the loads above are in flight; 1/u is
         // parked in shared memory until the forward sweep consumes it
         if (!straddle) {
             const int k0 = in_short ? plo - PS : posbase + plo, m0 = in_short ? mS : mL;
@@ -393,19 +405,6 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
                 double iu;
                 hy_factors(sh ? pl - PS : posbase + pl, sh ? mS : mL, N, sh ? (pl - PS < nS) : (pl < nL), tw, tiu, w[i], iu);
                 iu_s[i * blockDim.x + tid] = iu;
-            }
-        }
-        if (nvalid == L) {
-            const double2 *rp = R + ((unsigned)plo * stride + offD);
-#pragma unroll
-            for (int i = 0; i < L; ++i) r[i] = rp[(size_t)i * stride];
-        } else {
-#pragma unroll
-            for (int i = 0; i < L; ++i) {
-                const int pl = plo + i;
-                const bool sh = pl >= PS;
-                const bool ok = sh ? (pl - PS < nS) : (pl < nL);
-                r[i] = ok ? R[(unsigned)pl * stride + (sh ? offS : offL)] : make_double2(0.0, 0.0);
             }
         }
         // w of the position after the chunk: next chunk of this unit, or the first chunk of the next linked rank
