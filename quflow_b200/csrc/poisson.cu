@@ -6,16 +6,9 @@
 // Math.  Element (k, k+m) of the upper triangle is position k of the tridiagonal system of
 // diagonal m (length N-m):  o_k x_{k-1} + d_k x_k + o_{k+1} x_{k+1} = r_k  with
 //   d_k = -((N-1)(2k+1+m) - 2k(k+m)),   o_k = sqrt((k+m)(N-k-m) k (N-k)),   d_0 -= 1/2 for m = 0.
-// The matrices do not depend on W, so neither do their LU factors  w_k = o_k/u_{k-1}, u_k = d_k - w_k o_k  (the reference
-// recomputes them on every call).  For every diagonal m >= 1 the pivots have a CLOSED FORM,
-//     u_k = -(k+m+1)(N-k-1),      hence      w_k = -sqrt( k (N-k-m) / ((k+m)(N-k)) ),     1/u_k = -1 / ((k+m+1)(N-k-1))
-// (induction: u_0 = d_0 = -(N-1)(m+1), and d_k + o_k^2 / ((k+m)(N-k)) = -(k+m+1)(N-k-1) identically in k, m, N).
-// Both separate into a row factor times a column factor (hy_factors below), so two tables of N entries each, resident
-// in L1/L2, replace the N^2/2-entry factor tables of the first version: no factor table travels through HBM at all, the
-// solve reads the upper triangle of W~ and writes P~, nothing else.  The closed form is also MORE accurate than the
-// floating-point recurrence (2.5e-15 against 7e-13 relative to an extended-precision solve at N = 1100, m = 1).  Only
-// the main diagonal m = 0, whose matrix is singular up to the reference's d[0,0] -= 1/2 fix, keeps a table of N entries
-// built by the recurrence on the host.
+// The matrices do not depend on W, so their LU factors  w_k = o_k/u_{k-1}, u_k = d_k - w_k o_k
+// are built once per N on the host (the reference recomputes them every call) and kept in HBM packed
+// in the order the solve kernel reads them (k_poisson_band below).
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -142,53 +135,77 @@ extern "C" int qf_poisson_plan(int N, int *params_out, int *units_out, int cap)
 int qf_build_tables(qf_handle_s *h)
 {
     const int N = h->N;
-    // m = 0: the one diagonal without a closed form (bc perturbation, cpu.py:90): factors by the recurrence (cpu.py:320-328)
-    std::vector<double> tw(N, 0.0), tiu(N, 0.0);
+    const size_t n2 = (size_t)N * N;
+    std::vector<double> tw(n2, 0.0), tiu(n2, 0.0);
     const double dN = (double)N;
-    {
+    for (int m = 0; m < N; ++m) {
         double u_prev = 0.0;
-        for (int k = 0; k < N; ++k) {
-            const double dk = (double)k;
-            double d = -((dN - 1.0) * (2.0 * dk + 1.0) - 2.0 * dk * dk);                    // cpu.py:82, m = 0
-            const double o = sqrt((dk * (dN - dk)) * (dk * (dN - dk)));                     // cpu.py:83
-            if (k == 0) d -= 0.5;                                                           // cpu.py:90
+        for (int k = 0; k < N - m; ++k) {
+            const size_t idx = (size_t)k * N + (k + m);
+            const double dk = (double)k, dm = (double)m;
+            double d = -((dN - 1.0) * (2.0 * dk + 1.0 + dm) - 2.0 * dk * (dk + dm));   // cpu.py:82
+            const double o = sqrt(((dk + dm) * (dN - dk - dm)) * (dk * (dN - dk)));    // cpu.py:83
+            if (m == 0 && k == 0) d -= 0.5;                                             // cpu.py:90
             double w = 0.0, u = d;
             if (k > 0) {
-                w = o / u_prev;                                                             // cpu.py:324
-                u = d - w * o;                                                              // cpu.py:325
+                w = o / u_prev;                                                         // cpu.py:324
+                u = d - w * o;                                                          // cpu.py:325
             }
-            tw[k] = w;
-            tiu[k] = 1.0 / u;
+            tw[idx] = w;
+            tiu[idx] = 1.0 / u;
             u_prev = u;
         }
     }
-    int L, M, NT, CL;
-    std::vector<int> units;     // 8 ints per unit: bL, posbase, bS, PS, nlink, rank0, 0, 0
-    if (!qf_poisson_plan_host(N, L, M, NT, CL, units)) {
-        qf_set_error("N=%d needs more than 8 CTAs per band of diagonals: not supported", N);
-        return QF_ERR_UNSUPPORTED;
+    // ---- unit-packed tables for k_poisson_band (work plan: qf_poisson_plan_host above).  The factor entries of a unit
+    // are contiguous and ordered [warp block][i][chunk in block][s]: the 32 lanes of a warp read 32 consecutive doubles
+    // for every i.  Entries outside the diagonals are 0 (which also decouples the pieces of a unit).
+    {
+        int L, M, NT, CL;
+        std::vector<int> units;     // 8 ints per unit: bL, posbase, bS, PS, nlink, rank0, 0, 0
+        if (!qf_poisson_plan_host(N, L, M, NT, CL, units)) {
+            qf_set_error("N=%d needs more than 8 CTAs per band of diagonals: not supported", N);
+            return QF_ERR_UNSUPPORTED;
+        }
+        const int NTMAX = 512;
+        const int PC = (NT / M) * L, WB = (32 / M) * L;
+        const size_t nunits = units.size() / 8;
+        const size_t total = nunits * (size_t)PC * M;
+        if (total >= (1ull << 31)) { qf_set_error("factor tables of N=%d exceed 2^31 entries", N); return QF_ERR_UNSUPPORTED; }
+        const int CPW = 32 / M;
+        std::vector<double> pw(total, 0.0), piu(total, 0.0);
+        for (size_t u = 0; u < nunits; ++u) {
+            const int bL = units[8 * u], posbase = units[8 * u + 1], bS = units[8 * u + 2], PS = units[8 * u + 3];
+            for (int sl = 0; sl < M; ++sl) {
+                for (int pl = 0; pl < PC; ++pl) {
+                    int m = -1, k = 0;
+                    if (pl < PS) {
+                        if (bL >= 0) { m = M * bL + sl; k = posbase + pl; }
+                    } else if (bS >= 0) {
+                        m = M * bS + sl;
+                        k = pl - PS;
+                    }
+                    if (m < 0 || m >= N || k >= N - m) continue;
+                    const size_t src = (size_t)k * N + (k + m);
+                    const size_t dst = u * (size_t)PC * M + (size_t)(pl / WB) * WB * M + (size_t)(pl % L) * 32 +
+                                       (size_t)((pl / L) % CPW) * M + sl;
+                    pw[dst] = tw[src];
+                    piu[dst] = tiu[src];
+                }
+            }
+        }
+        QF_CUDA(cudaMalloc(&h->ptab_w, total * sizeof(double)));
+        QF_CUDA(cudaMalloc(&h->ptab_iu, total * sizeof(double)));
+        QF_CUDA(cudaMalloc(&h->ptab_units, units.size() * sizeof(int)));
+        QF_CUDA(cudaMemcpy(h->ptab_w, pw.data(), total * sizeof(double), cudaMemcpyHostToDevice));
+        QF_CUDA(cudaMemcpy(h->ptab_iu, piu.data(), total * sizeof(double), cudaMemcpyHostToDevice));
+        QF_CUDA(cudaMemcpy(h->ptab_units, units.data(), units.size() * sizeof(int), cudaMemcpyHostToDevice));
+        h->p_L = L;
+        h->p_M = M;
+        h->p_CL = CL;
+        h->p_NT = NT;
+        h->p_NTMAX = NTMAX;
+        h->p_nunits = (int)nunits;
     }
-    // tables: [0, N) tk = (alpha_k, delta_k), [N, 2N) tj = (beta_j, gamma_j), [2N, 3N) t0 = (w, 1/u) of the main diagonal
-    std::vector<double> tab(6 * (size_t)N, 0.0);
-    for (int k = 0; k < N; ++k) {
-        const double dk = (double)k;
-        tab[2 * k + 0] = sqrt(dk / (dN - dk));                                   // alpha_k
-        tab[2 * k + 1] = (k < N - 1) ? 1.0 / (dN - dk - 1.0) : 0.0;              // delta_k
-        tab[2 * (N + k) + 0] = (k > 0) ? sqrt((dN - dk) / dk) : 0.0;            // beta_j
-        tab[2 * (N + k) + 1] = 1.0 / (dk + 1.0);                                 // gamma_j
-        tab[2 * (2 * N + k) + 0] = tw[k];
-        tab[2 * (2 * N + k) + 1] = tiu[k];
-    }
-    QF_CUDA(cudaMalloc(&h->ptab_w, tab.size() * sizeof(double)));
-    QF_CUDA(cudaMalloc(&h->ptab_units, units.size() * sizeof(int)));
-    QF_CUDA(cudaMemcpy(h->ptab_w, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
-    QF_CUDA(cudaMemcpy(h->ptab_units, units.data(), units.size() * sizeof(int), cudaMemcpyHostToDevice));
-    h->p_L = L;
-    h->p_M = M;
-    h->p_CL = CL;
-    h->p_NT = NT;
-    h->p_NTMAX = 512;
-    h->p_nunits = (int)(units.size() / 8);
     return qf_poisson_prepare(h);
 }
 
@@ -225,13 +242,13 @@ __global__ void k_whalf(const double2 *__restrict__ W, const double2 *__restrict
 //     of the diagonal to an affine map; the maps travel through distributed shared memory with st.async, which
 //     signals an mbarrier in the receiving CTA.  No cluster-wide barrier and no memory fence sits in the solve
 //     (a fence would wait for every load and prefetch the CTA has in flight);
-//   * the LU factors come from the closed form (file header), evaluated while the loads of W~ are in flight; 1/u is
-//     parked in shared memory and consumed between the sweeps;
+//   * factor tables are unit-packed: every warp load is 256 contiguous bytes; 1/u goes straight to shared
+//     memory with cp.async and is consumed between the sweeps;
 //   * the skew-Hermitian mirror P[j,i] = -conj(P[i,j]) is transposed through shared memory, so the mirrored
 //     stores are 16 M-byte row pieces like the direct ones (no scattered 16-byte stores);
 //   * once its own loads have landed a CTA prefetches into L2 the inputs of the unit that will follow it on its
 //     SM slot (pf_stride units ahead), so HBM keeps streaming while the resident CTAs run their sweeps.
-// HBM traffic: upper triangle of W~ (8 N^2 B) + full P (16 N^2 B) = 24 N^2 B (algorithmic accounting: 32 N^2 B).
+// HBM traffic: upper triangle of W~ (8 N^2 B) + w and 1/u (8 N^2 B) + full P (16 N^2 B) = 32 N^2 B.
 // ---------------------------------------------------------------------------------------
 #ifdef QF_PTRACE
 __device__ unsigned long long g_ptrace[4096 * 16];
@@ -256,15 +273,20 @@ __device__ __forceinline__ void pb_send(double *local_slot, uint64_t *local_mbar
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(ra), "d"(v), "r"(rm) : "memory");
 }
 
-// L2 prefetch of the inputs of unit `un` with this CTA's thread mapping: the row pieces of W~, one request per end of a
-// piece (fire and forget: no data comes back to the SM, so these requests do not occupy the L1 miss queue that throttles
-// ordinary loads to about 30 GB/s per SM at DRAM latency).
+// L2 prefetch of the inputs of unit `un` with this CTA's thread mapping: the factor tables as two bulk requests, the
+// row pieces of W~ one request per end of a piece (fire and forget: no data comes back to the SM, so these requests do
+// not occupy the L1 miss queue that throttles ordinary loads to about 30 GB/s per SM at DRAM latency).
 template <int L, int M>
-__device__ __forceinline__ void pb_prefetch_unit(int un, const int4 *__restrict__ units, const double2 *__restrict__ R, int N,
+__device__ __forceinline__ void pb_prefetch_unit(int un, const int4 *__restrict__ units, const double *__restrict__ tw,
+                                                 const double *__restrict__ tiu, const double2 *__restrict__ R, int N, int PC,
                                                  int tid, int s, int plo)
 {
     const unsigned stride = (unsigned)N + 1u;
     const int4 nd = __ldg(units + 2 * un);
+    if (tid < 2) {
+        const double *t = (tid == 0 ? tw : tiu) + (size_t)un * PC * M;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t), "r"(PC * M * 8) : "memory");
+    }
     if (s == 0 || s == M - 1) {
         const int nmL = nd.x * M + s, nmS = nd.z * M + s;
         const int nnL = (nd.x >= 0) ? min(nd.w, max(0, N - nmL - nd.y)) : 0;
@@ -281,39 +303,10 @@ __device__ __forceinline__ void pb_prefetch_unit(int un, const int4 *__restrict_
     }
 }
 
-// LU factors of position k of diagonal m (file header).  The closed form separates into a row factor and a column
-// factor (j = k + m is the column of the element):
-//     w_k = -alpha_k * beta_j,    alpha_k = sqrt(k / (N-k)),   beta_j = sqrt((N-j) / j)
-//     1/u_k = -gamma_j * delta_k, gamma_j = 1 / (j+1),         delta_k = 1 / (N-k-1)
-// so two tables of N double2 — tk[k] = (alpha_k, delta_k), tj[j] = (beta_j, gamma_j), 64 KB in all at N = 2048, resident in
-// L1/L2 — replace the N^2/2-entry factor tables; m = 0 (no closed form) reads its own N-entry table.  Zero outside the
-// diagonal, which also decouples the two pieces of a unit (alpha_0 = 0 makes w = 0 at k = 0 by itself).
-__device__ __forceinline__ double hy_w(int k, int m, int N, bool valid, const double2 *__restrict__ tk, const double2 *__restrict__ tj,
-                                       const double2 *__restrict__ t0)
-{
-    if (!valid) return 0.0;
-    if (m == 0) return __ldg(&t0[k].x);
-    return -(__ldg(&tk[k].x) * __ldg(&tj[k + m].x));
-}
-__device__ __forceinline__ void hy_factors(int k, int m, int N, bool valid, const double2 *__restrict__ tk,
-                                           const double2 *__restrict__ tj, const double2 *__restrict__ t0, double &w, double &iu)
-{
-    if (!valid) {
-        w = 0.0;
-        iu = 0.0;
-    } else if (m == 0) {
-        w = __ldg(&t0[k].x);
-        iu = __ldg(&t0[k].y);
-    } else {
-        w = -(__ldg(&tk[k].x) * __ldg(&tj[k + m].x));
-        iu = -(__ldg(&tj[k + m].y) * __ldg(&tk[k].y));
-    }
-}
-
 template <int L, int M, int CL, int NTMAX>
 __global__ void __launch_bounds__(NTMAX, 512 / NTMAX)
-k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const double2 *__restrict__ tk,
-               const double2 *__restrict__ tj, const double2 *__restrict__ t0, const int4 *__restrict__ units, int N, int nunits, int pf_stride,
+k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const double *__restrict__ tw,
+               const double *__restrict__ tiu, const int4 *__restrict__ units, int N, int nunits, int pf_stride,
                double eps, const QfCtrl *__restrict__ ctrl, int gated)
 {
     const int mem = blockIdx.y;
@@ -390,26 +383,16 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
 
     double2 r[L];
     double w[L + 1];                               // w[L]: w of the first position after the chunk
+    const uint32_t iu_base = (uint32_t)__cvta_generic_to_shared(iu_s) + (uint32_t)tid * 8u;
+    const uint32_t iu_pitch = blockDim.x * 8u;
     if (warp_work) {
-        // LU factors of this thread's positions, from the L1/L2-resident row and column tables; 1/u is
-        // parked in shared memory until the forward sweep consumes it
-        if (!straddle) {
-            const int k0 = in_short ? plo - PS : posbase + plo, m0 = in_short ? mS : mL;
+        const size_t tb = (size_t)unit * PC * M + (size_t)warp * (WB * M) + lane;
+        const double *wp = tw + tb;
+        const double *up = tiu + tb;
 #pragma unroll
-            for (int i = 0; i < L; ++i) {
-                double iu;
-                hy_factors(k0 + i, m0, N, i < nvalid, tk, tj, t0, w[i], iu);
-                iu_s[i * blockDim.x + tid] = iu;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < L; ++i) {
-                const int pl = plo + i;
-                const bool sh = pl >= PS;
-                double iu;
-                hy_factors(sh ? pl - PS : posbase + pl, sh ? mS : mL, N, sh ? (pl - PS < nS) : (pl < nL), tk, tj, t0, w[i], iu);
-                iu_s[i * blockDim.x + tid] = iu;
-            }
+        for (int i = 0; i < L; ++i) {
+            w[i] = __ldg(wp + i * 32);             // zero outside the diagonals
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(iu_base + i * iu_pitch), "l"(up + i * 32));
         }
         if (nvalid == L) {
             const double2 *rp = R + ((unsigned)plo * stride + offD);
@@ -426,20 +409,18 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
         }
         // w of the position after the chunk: next chunk of this unit, or the first chunk of the next linked rank
         w[L] = 0.0;
-        {
-            const int pl = plo + L;
-            if (pl < PC) {
-                const bool sh = pl >= PS;
-                w[L] = hy_w(sh ? pl - PS : posbase + pl, sh ? mS : mL, N, sh ? (pl - PS < nS) : (pl < nL), tk, tj, t0);
-            } else if (linked && grank + 1 < nlink) {
-                w[L] = hy_w(posbase + PC, mL, N, posbase + PC < N - mL, tk, tj, t0);       // first position of the next linked rank
-            }
+        if (plo + L < PC) {
+            const int cn = c + 1;
+            w[L] = __ldg(tw + (size_t)unit * PC * M + (size_t)(cn / CPW) * (WB * M) + (cn % CPW) * M + s);
+        } else if (linked && grank + 1 < nlink) {
+            w[L] = __ldg(tw + (size_t)(unit + 1) * PC * M + s);
         }
     } else {
 #pragma unroll
         for (int i = 0; i < L; ++i) { r[i] = make_double2(0.0, 0.0); w[i] = 0.0; }
         w[L] = 0.0;
     }
+    asm volatile("cp.async.commit_group;");
     PT(1);
 
     // ---- m = 0: remove the mean of the diagonal from the right-hand side (cpu.py:311-317,327-328)
@@ -516,7 +497,7 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
     PT(2);
     // ---- L2 prefetch of the unit pf_stride ahead: it will follow this one on the same SM slot
     if (pf_stride > 0 && unit + pf_stride < nunits)
-        pb_prefetch_unit<L, M>(unit + pf_stride, units, R, N, tid, s, plo);
+        pb_prefetch_unit<L, M>(unit + pf_stride, units, tw, tiu, R, N, PC, tid, s, plo);
     if (lane >= 32 - M) { totA[warp][s] = A; totBx[warp][s] = B.x; totBy[warp][s] = B.y; }
     __syncthreads();
     PT(3);
@@ -557,7 +538,7 @@ k_poisson_band(const double2 *__restrict__ Wh, double2 *__restrict__ P, const do
         carry.y = xA * pBy + xBy;
     }
     // ---- forward, pass 2 from the true carry-in; r becomes z = c / u
-    // (1/u was written to shared memory by this very thread: no barrier needed)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's own 1/u values (no cross-thread sharing)
     if (warp_work) {
 #pragma unroll
         for (int i = 0; i < L; ++i) {
@@ -840,7 +821,7 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
         cfg.numAttrs = 1;
         const double2 *a0 = Wh;
         double2 *a1 = P;
-        const double2 *a2 = reinterpret_cast<const double2 *>(h->ptab_w), *a3 = a2 + N, *a3b = a2 + 2 * N;
+        const double *a2 = h->ptab_w, *a3 = h->ptab_iu;
         const int4 *a4 = reinterpret_cast<const int4 *>(h->ptab_units);
         int a5 = N, a6 = h->p_nunits;
         // L2 prefetch distance = units resident at once (one 512-thread CTA per SM), a multiple of the cluster size
@@ -848,7 +829,7 @@ int qf_launch_poisson(qf_handle_s *h, const double2 *W, const double2 *dW, doubl
         double a8 = eps;
         const QfCtrl *a9 = h->ctrl;
         int a10 = g;
-        void *args[] = {&a0, &a1, &a2, &a3, &a3b, &a4, &a5, &a6, &a7, &a8, &a9, &a10};
+        void *args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10};
         QF_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
         h->launches++;
     } else {

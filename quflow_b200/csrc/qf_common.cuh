@@ -93,8 +93,8 @@ struct qf_handle_s {
     int device = 0;
     int sm_count = 148;
     size_t mat_elems = 0;      // N*N
-    // LU factor tables of the Hoppe-Yau tridiagonal systems (poisson.cu): 3 N double2 = row factors, column factors, m = 0
-    double *ptab_w = nullptr, *ptab_iu = nullptr;   // ptab_iu: unused since the closed-form factors (kept for the free list)
+    // unit-packed LDL^T factors of the Hoppe-Yau tridiagonal systems: w_k = o_k / u_{k-1}, 1/u_k (poisson.cu)
+    double *ptab_w = nullptr, *ptab_iu = nullptr;
     int *ptab_units = nullptr;      // [nunits][8] = bL, posbase, bS, PS, nlink, 0, 0, 0 (poisson.cu: qf_build_tables)
     int p_L = 0;                    // positions per thread (0: band kernel not available for this N)
     int p_M = 8;                    // diagonals per band
