@@ -227,8 +227,9 @@ static int p2p_finish(qf_handle_s *h, QfP2P *p)
         // replicated mirror pass (14 us at N = 2048); measured faster at 2, 4 and 8 GPUs.  QF_XCHG_UPPER=0 switches it off.
         const char *u = getenv("QF_XCHG_UPPER");
         p->desc.upper_only = u ? (u[0] == '1') : 1;
-        const char *m = getenv("QF_XCHG_PUSH");
+        const char *m = getenv("QF_XCHG_PUSH");       // sm (copy kernel) | inline (from the tail / update kernels) | ce (copy engines)
         h->xchg_ce = (m && strcmp(m, "ce") == 0) ? 1 : 0;
+        p->desc.push_inline = (m && strcmp(m, "inline") == 0) ? 1 : 0;
         h->skew_host = -1;
         const char *d = getenv("QF_XCHG_DEBUG_SKIP_A");
         p->desc.dbg_skip_a = (d && d[0] == '1') ? 1 : 0;
@@ -545,6 +546,7 @@ int qf_xchg_push_wh(qf_handle_s *h, bool gated, cudaStream_t st)
 {
     const QfXchg *x = qf_xchg_desc(h);
     if (!x) { qf_set_error("qf_xchg_push_wh: the handle has no tile-exchange communicator"); return QF_ERR_INVALID; }
+    if (x->push_inline && !h->fuse_post) return QF_OK;      // the tail / update kernels have stored the tiles themselves
     if (h->xchg_ce) {
         // Copy-engine variant (QF_XCHG_PUSH=ce): the same rectangles as k_xchg_push_wh as 2-D device-to-device copies
         // into the peer mappings — memcpy nodes inside the step graph, no SM involved.  Not gated by the device flag: in

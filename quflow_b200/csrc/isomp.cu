@@ -107,6 +107,8 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
     if (bi > bj) return;
     const bool xpush = xg.nranks > 1;
     if (xpush && qf_owner_of_row(bi * TS, xg.hb, xg.nranks) != xg.rank) return;
+    const bool wpush = xpush && xg.push_inline;                                   // W~ tiles go to the peers from here
+    const bool wpush_lower = wpush && !(xg.upper_only && ctrl[0].skew_exact);     // ... the mirrored half only if it cannot be rebuilt
     __shared__ double2 T[TS][TS + 1];
     __shared__ double2 D[TS][TS + 1];
     __shared__ double R[TS][TS + 1];
@@ -147,7 +149,11 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
             const double2 old = dW[ij];
             r = zabs(zsub(old, dn));                                  // :526,:534
             dW[ij] = dn;
-            Wh[ij] = zadd(W[ij], dn);                                 // next iterate W~ = W + dW (:481-482)
+            const double2 wh = zadd(W[ij], dn);                       // next iterate W~ = W + dW (:481-482)
+            Wh[ij] = wh;
+            if (wpush)
+                for (int p = 0; p < xg.nranks; ++p)
+                    if (p != xg.rank) xg.peerWh[p][off + ij] = wh;
         }
         D[ii][tx] = d;                                                // without the forcing term: mirrored below
         R[ii][tx] = r;
@@ -178,7 +184,11 @@ k_post(const double2 *__restrict__ Ag, const double2 *__restrict__ Sg, double2 *
                 rl = R[tx][jj];
             }
             dW[ji] = dm;
-            Wh[ji] = zadd(W[ji], dm);
+            const double2 wh = zadd(W[ji], dm);
+            Wh[ji] = wh;
+            if (wpush_lower)
+                for (int p = 0; p < xg.nranks; ++p)
+                    if (p != xg.rank) xg.peerWh[p][off + ji] = wh;
         }
         double s = rl;
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -305,6 +315,8 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
     if (bi > bj) return;
     const bool xpush = xg.nranks > 1;
     if (xpush && qf_owner_of_row(bi * TS, xg.hb, xg.nranks) != xg.rank) return;
+    const bool wpush = xpush && xg.push_inline;
+    const bool wpush_lower = wpush && !(xg.upper_only && c.skew_exact);
     __shared__ double2 T[TS][TS + 1];
     const size_t off = (size_t)b * N * N;
     const double2 *A = Ag + off;
@@ -341,7 +353,11 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
                 if (FORCING) w = zadd(w, zscale(2.0, zscale(fscale, F[ij])));   // FW *= 2; W += FW (:594-596)
             }
             W[ij] = w;
-            Wh[ij] = reinit ? w : zadd(w, dW[ij]);
+            const double2 wh = reinit ? w : zadd(w, dW[ij]);
+            Wh[ij] = wh;
+            if (wpush)
+                for (int p = 0; p < xg.nranks; ++p)
+                    if (p != xg.rank) xg.peerWh[p][off + ij] = wh;
         }
         cv[q] = cm;
     }
@@ -367,7 +383,11 @@ k_update(const double2 *__restrict__ Ag, double2 *__restrict__ Wg, double2 *__re
                 if (FORCING) w = zadd(w, zscale(2.0, zscale(fscale, F[ji])));
             }
             W[ji] = w;
-            Wh[ji] = reinit ? w : zadd(w, dW[ji]);
+            const double2 wh = reinit ? w : zadd(w, dW[ji]);
+            Wh[ji] = wh;
+            if (wpush_lower)
+                for (int p = 0; p < xg.nranks; ++p)
+                    if (p != xg.rank) xg.peerWh[p][off + ji] = wh;
         }
     }
 }
@@ -505,7 +525,7 @@ static inline double qf_hbar(int N) { return 2.0 / sqrt((double)N * (double)N - 
 enum { QF_PH_A = 1, QF_PH_B = 2, QF_PH_C = 4, QF_PH_ALL = 7 };
 
 int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit, int minit, cudaStream_t st,
-                         cudaEvent_t *ev /* 11 events or null: 0-4 phases, 7-10 the exchange of the tile path */, int phases = QF_PH_ALL)
+                         cudaEvent_t *ev /* 12 events or null: 0-4 phases, 7-11 the exchange of the tile path */, int phases = QF_PH_ALL)
 {
     const int N = h->N;
     const int G = h->nranks;
@@ -520,8 +540,33 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
     const bool multistate = h->multistate && h->batch > 1;
     if (phases & QF_PH_A) {
         if (ev) QF_CUDA(cudaEventRecord(ev[0], st));
+        // Tile exchange, upper-only W~ exchange: the lower triangle of W~ is rebuilt locally from the upper tiles the peers
+        // pushed.  Only the first GEMM reads it — the Poisson solve reads the upper triangle — so inside the step graph the
+        // mirror runs on a forked branch next to the solve and joins before the GEMM.
+        bool forked = false;
+        if (xmode && xg->upper_only) {
+            if (ev) QF_CUDA(cudaEventRecord(ev[9], st));
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            QF_CUDA(cudaStreamIsCapturing(st, &cs));
+            if (cs == cudaStreamCaptureStatusActive) {
+                if (!h->side_stream) {
+                    QF_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+                    QF_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+                    QF_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+                }
+                QF_CUDA(cudaEventRecord(h->ev_fork, st));
+                QF_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+                QF_CHECK(qf_xchg_mirror_wh(h, true, h->side_stream));
+                QF_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
+                forked = true;
+            } else {
+                QF_CHECK(qf_xchg_mirror_wh(h, true, st));
+            }
+            if (ev) QF_CUDA(cudaEventRecord(ev[10], st));
+        }
         // W~ = W + dW was written by the previous iteration / update (or copied at call start): solve straight from it
         QF_CHECK(qf_launch_poisson(h, h->Wh, nullptr, h->Wh, h->P, eps, true, st, multistate ? 1 : h->batch));
+        if (forked) QF_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
         if (multistate) {
             const size_t n2 = h->mat_elems;
             k_bcast_p<<<(unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)h->sm_count * 8), 256, 0, st>>>(h->P, n2, h->batch, h->ctrl);
@@ -562,7 +607,6 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
             if (xmode) {
                 // every peer's W~ tiles and partials have landed
                 QF_CHECK(phases == QF_PH_ALL ? qf_xchg_barrier(h, QF_XF_X, true, st) : qf_xchg_wait(h, QF_XF_X, true, st));
-                QF_CHECK(qf_xchg_mirror_wh(h, true, st));
             }
             k_control<<<gc, 256, 0, st>>>(part_direct, h->nsd, part_mirror, h->nsm, N, h->ctrl, maxit, minit, nfollow, h->cap_cond,
                                           h->cap_use_cond);
@@ -594,9 +638,7 @@ int qf_enqueue_iteration(qf_handle_s *h, const double2 *W, double eps, int maxit
     if (phases & QF_PH_C) {
         if (xmode) {
             QF_CHECK(phases == QF_PH_ALL ? qf_xchg_barrier(h, QF_XF_X, true, st) : qf_xchg_wait(h, QF_XF_X, true, st));
-            if (ev) QF_CUDA(cudaEventRecord(ev[9], st));
-            QF_CHECK(qf_xchg_mirror_wh(h, true, st));
-            if (ev) QF_CUDA(cudaEventRecord(ev[10], st));
+            if (ev) QF_CUDA(cudaEventRecord(ev[11], st));
         } else {
             k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, hb, Gp, W, h->Wh, nullptr, 0.0, solo);
             h->launches++;
@@ -637,7 +679,7 @@ int qf_enqueue_update(qf_handle_s *h, double2 *W, bool compsum, bool reinit, cud
     }
     if ((phases & 2) && xmode) {
         QF_CHECK(phases == 3 ? qf_xchg_barrier(h, QF_XF_X, false, st) : qf_xchg_wait(h, QF_XF_X, false, st));
-        QF_CHECK(qf_xchg_mirror_wh(h, false, st));
+        // (the lower triangle of the new W~ is rebuilt at the start of the next iteration, next to its Poisson solve)
     }
     return QF_OK;
 }
@@ -674,6 +716,11 @@ void qf_graph_destroy(qf_handle_s *h)
     h->step_graph = nullptr;
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     h->cap_stream = nullptr;
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    h->side_stream = nullptr;
+    h->ev_fork = h->ev_join = nullptr;
 
 }
 
@@ -1181,7 +1228,7 @@ extern "C" int qf_profile_iteration(qf_handle_t h, const void *W_dev, double dt,
     const int N = h->N, B = h->batch;
     const size_t n2 = h->mat_elems;
     const double eps = dt / (2.0 * qf_hbar(N));
-    cudaEvent_t ev[11];
+    cudaEvent_t ev[12];
     for (auto &e : ev) QF_CUDA(cudaEventCreate(&e));
     const bool xsplit = h->nranks > 1 && h->comm_mode == 5 && !(h->fuse_post && qf_gemm_can_fuse_post(h));
     float xacc[5] = {0, 0, 0, 0, 0};
@@ -1208,10 +1255,15 @@ extern "C" int qf_profile_iteration(qf_handle_t h, const void *W_dev, double dt,
         QF_CUDA(cudaEventElapsedTime(&ms, ev[5], ev[6]));
         acc[4] += ms;
         if (xsplit) {
-            const int order[6] = {3, 7, 8, 9, 10, 4};      // GEMM 2 done | tail kernel | W~ push | signal + wait | mirror | control
-            for (int p = 0; p < 5; ++p) {
+            const int order[5] = {3, 7, 8, 11, 4};         // GEMM 2 done | tail kernel | W~ push | signal + wait | control
+            for (int p = 0; p < 4; ++p) {
                 QF_CUDA(cudaEventElapsedTime(&ms, ev[order[p]], ev[order[p + 1]]));
-                xacc[p] += ms;
+                xacc[p == 3 ? 4 : p] += ms;
+            }
+            if (qf_xchg_desc(h)->upper_only) {
+                QF_CUDA(cudaEventElapsedTime(&ms, ev[9], ev[10]));   // the local mirror at the start of the iteration (serial here, forked in the graph)
+                xacc[3] += ms;
+                acc[0] -= ms;                                        // ... which the event pair of the Poisson phase spans as well
             }
         }
     }

@@ -135,6 +135,8 @@ struct qf_handle_s {
     // CUDA-graph execution of a step (isomp.cu)
     void *step_graph = nullptr;
     cudaStream_t cap_stream = nullptr;
+    cudaStream_t side_stream = nullptr;          // forked branch of the iteration (tile exchange: local mirror of W~)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int use_graph = 1;
     unsigned long long cap_cond = 0;   // conditional handle of the step graph being captured
     int cap_use_cond = 0;              // k_control arms the WHILE node (set only while capturing)
@@ -179,6 +181,8 @@ struct QfXchg {
     unsigned long long *myFlags = nullptr;
     long long timeout_cycles = 60000000000ll;         // give up on a silent peer after this many SM cycles (QF_COMM_TIMEOUT_S)
     int upper_only = 0;                               // W~ exchange: send upper tiles only when W is exactly skew-Hermitian
+    int push_inline = 0;                              // W~ tiles are stored to the peers by the tail / update kernels themselves
+                                                      // (overlaps the NVLink stores with their memory latency) instead of k_xchg_push_wh
     int dbg_skip_a = 0;                               // timing experiments only (QF_XCHG_DEBUG_SKIP_A=1): GEMM 1 pushes nothing
 };
 __host__ __device__ __forceinline__ int qf_owner_of_row(int row, int hb, int G)

@@ -4,10 +4,10 @@
 G=${1:-2}; TAG=${2:-probe}
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1"
 i=0
-for cfg in "QF_XCHG_UPPER=0" "QF_XCHG_UPPER=1" "QF_XCHG_UPPER=0 QF_XCHG_DEBUG_SKIP_A=1"; do
+for cfg in "QF_XCHG_PUSH=sm" "QF_XCHG_PUSH=inline" "QF_XCHG_PUSH=inline QF_XCHG_UPPER=0"; do
     i=$((i+1))
     out=gpurun_out/${TAG}_g${G}_$i.json
-    env $cfg timeout 600 $RUN --master-port 2952$i bench.py --gpus $G --steps 20 --warmup 3 --no-cpu-baseline 2>gpurun_out/${TAG}_g${G}_$i.err | tail -1 > $out
+    env $cfg timeout 600 $RUN --master-port 2952$i bench.py --gpus $G --steps 40 --warmup 5 --no-cpu-baseline 2>gpurun_out/${TAG}_g${G}_$i.err | tail -1 > $out
     python - "$out" "$cfg" <<'PY'
 import json, sys
 try:
