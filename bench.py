@@ -122,9 +122,9 @@ def mode_kwargs(mode, N):
 
 def ncu_traffic(kernel_prefix, index=0):
     """DRAM bytes (read + write) per launch of a kernel from the committed `ncu --set full` capture
-    (profiles/r01_ncu_full_kernels.json, N=2048); None for other sizes or when the file is missing."""
+    (profiles/r02_ncu_full_kernels.json, N=2048); None for other sizes or when the file is missing."""
     try:
-        rows = [r for r in json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_kernels.json")))
+        rows = [r for r in json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_full_kernels.json")))
                 if r["kernel"].startswith(kernel_prefix)]
         r = rows[index]
 
@@ -459,7 +459,7 @@ def gpu_arm(args):
         "achieved": gemm1_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": gemm1_tf / fp64_peak,
         "traffic": ncu_traffic("k_zgemm3m_ws") if (N == 2048 and is3m) else None,
         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full capture at N=2048 "
-                        "(profiles/r01_ncu_full_kernels.json); algorithmic operand bytes 3*16*N^2",
+                        "(profiles/r02_ncu_full_kernels.json); algorithmic operand bytes 3*16*N^2",
         "peak_source": "FP64 DMMA (mma.sync.m8n8k4.f64) issue peak measured on this GPU in this run "
                        "(qf_measure_fp64_tensor_peak, 16 warps/SM x 8 chains, best of 5); MEASURED_PEAKS.json has no FP64 "
                        f"entry; round-1 value {FP64_TENSOR_PEAK_TFLOPS_R01} TF/s, datasheet ~37-40 TF/s",
