@@ -227,9 +227,12 @@ static int p2p_finish(qf_handle_s *h, QfP2P *p)
         // replicated mirror pass (14 us at N = 2048); measured faster at 2, 4 and 8 GPUs.  QF_XCHG_UPPER=0 switches it off.
         const char *u = getenv("QF_XCHG_UPPER");
         p->desc.upper_only = u ? (u[0] == '1') : 1;
-        const char *m = getenv("QF_XCHG_PUSH");       // sm (copy kernel) | inline (from the tail / update kernels) | ce (copy engines)
+        // How the W~ tiles travel: stored to the peers by the tail / update kernels themselves ("inline", default: the NVLink
+        // stores overlap those kernels' memory latency; 361.8 vs 352.8 steps/s at 2 GPUs), by a copy kernel on all SMs
+        // ("sm"), or by copy engines ("ce", memcpy nodes in the step graph; slowest: the rows are too short for DMA).
+        const char *m = getenv("QF_XCHG_PUSH");
         h->xchg_ce = (m && strcmp(m, "ce") == 0) ? 1 : 0;
-        p->desc.push_inline = (m && strcmp(m, "inline") == 0) ? 1 : 0;
+        p->desc.push_inline = (m && (strcmp(m, "sm") == 0 || strcmp(m, "ce") == 0)) ? 0 : 1;
         h->skew_host = -1;
         const char *d = getenv("QF_XCHG_DEBUG_SKIP_A");
         p->desc.dbg_skip_a = (d && d[0] == '1') ? 1 : 0;

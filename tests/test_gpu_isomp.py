@@ -374,8 +374,8 @@ def test_row_sharded_data_path_emulated_on_one_gpu(qf, N, G):
     h1.close(); hG.close()
 
 
-@pytest.mark.parametrize("N,G,fuse,push", [(256, 2, False, "sm"), (256, 2, True, "sm"), (512, 4, False, "sm"), (512, 4, False, "ce"),
-                                           (1024, 8, False, "sm"), (1024, 8, True, "ce")])
+@pytest.mark.parametrize("N,G,fuse,push", [(256, 2, False, "inline"), (256, 2, True, "inline"), (512, 4, False, "sm"), (512, 4, False, "ce"),
+                                           (1024, 8, False, "inline"), (1024, 8, True, "ce")])
 def test_tile_exchange_ranks_in_lockstep_on_one_gpu(qf, N, G, fuse, push, monkeypatch):
     """The tile-exchange multi-GPU path (comm_mode 5) for G ranks on ONE GPU: G handles attached to each other through
     plain device pointers are advanced in lock step (every phase enqueued for all ranks before the next phase of any
@@ -396,7 +396,7 @@ def test_tile_exchange_ranks_in_lockstep_on_one_gpu(qf, N, G, fuse, push, monkey
     Ws = W0.copy()
     _, its_solo = solo.isomp(Ws, dt, steps, want_iters=True)
     hs = [Handle(N) for _ in range(G)]
-    monkeypatch.setenv("QF_XCHG_PUSH", push)        # W~ tiles by the copy kernel ("sm") or by copy engines ("ce")
+    monkeypatch.setenv("QF_XCHG_PUSH", push)        # W~ tiles from the tail / update kernels ("inline"), a copy kernel ("sm"), copy engines ("ce")
     attach_local(hs)
     assert all(h.comm_mode() == "tile" for h in hs)
     for h in hs:
