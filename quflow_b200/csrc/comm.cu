@@ -234,8 +234,6 @@ static int p2p_finish(qf_handle_s *h, QfP2P *p)
         h->xchg_ce = (m && strcmp(m, "ce") == 0) ? 1 : 0;
         p->desc.push_inline = (m && (strcmp(m, "sm") == 0 || strcmp(m, "ce") == 0)) ? 0 : 1;
         h->skew_host = -1;
-        const char *d = getenv("QF_XCHG_DEBUG_SKIP_A");
-        p->desc.dbg_skip_a = (d && d[0] == '1') ? 1 : 0;
     }
     {
         // ranks may legitimately be seconds apart (host work between calls): the bound only has to end a real hang

@@ -1049,15 +1049,36 @@ extern "C" int qf_isomp_lockstep(qf_handle_t *hs, int G, void **W_devs, double d
 static int step_check(qf_handle_s *h, const char *who)
 {
     if (!h) { qf_set_error("%s: null handle", who); return QF_ERR_INVALID; }
-    if (h->batch != 1 || h->nranks != 1) { qf_set_error("%s: the host-stepped driver runs one member on one GPU", who); return QF_ERR_UNSUPPORTED; }
+    if (h->batch != 1) { qf_set_error("%s: the host-stepped driver advances one member", who); return QF_ERR_UNSUPPORTED; }
+    if (h->nranks > 1 && !(h->comm_mode == 1 || h->comm_mode == 2 || h->comm_mode == 5)) {
+        qf_set_error("%s: the handle is set up for emulated ranks", who);
+        return QF_ERR_UNSUPPORTED;
+    }
     if (!h->step_open) { qf_set_error("%s: qf_step_open was not called", who); return QF_ERR_INVALID; }
     return QF_OK;
+}
+
+// Several GPUs in the host-stepped mode: the hooks run host code on EVERY rank and must see complete matrices there, so
+// this mode uses the all-gather data path whatever the handle's default is — the two GEMMs are sharded by row blocks
+// (rank-permuted output rows, qf_prow), A and S are completed on every rank by the pull kernels (or NCCL), and the tail,
+// the stopping rule and the update run replicated on identical bytes.
+struct StepLayout { int rank, G, hb; bool nccl; };
+static StepLayout step_layout(const qf_handle_s *h)
+{
+    StepLayout l;
+    l.G = h->nranks;
+    l.rank = l.G > 1 ? h->rank : -1;
+    l.hb = l.G > 1 ? qf_block_rows(h->N, l.G) : h->N;
+    l.nccl = l.G > 1 && h->comm_mode == 1;
+    return l;
 }
 
 extern "C" int qf_step_open(qf_handle_t h, const void *W_dev, double dt, double tol, unsigned flags, double *tol_used, void *stream)
 {
     if (!h || !W_dev) { qf_set_error("qf_step_open: null argument"); return QF_ERR_INVALID; }
-    if (h->batch != 1 || h->nranks != 1) { qf_set_error("qf_step_open: the host-stepped driver runs one member on one GPU"); return QF_ERR_UNSUPPORTED; }
+    if (h->batch != 1) { qf_set_error("qf_step_open: the host-stepped driver advances one member"); return QF_ERR_UNSUPPORTED; }
+    if (h->nranks > 1 && !(h->comm_mode == 1 || h->comm_mode == 2 || h->comm_mode == 5)) { qf_set_error("qf_step_open: the handle is set up for emulated ranks"); return QF_ERR_UNSUPPORTED; }
+    if (h->nranks > 1) QF_CHECK(qf_gemm_prepare_gather(h));
     QF_ON_DEVICE(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n2 = h->mat_elems;
@@ -1128,8 +1149,11 @@ extern "C" int qf_step_products(qf_handle_t h, void *stream)
     QF_CHECK(step_check(h, "qf_step_products"));
     QF_ON_DEVICE(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    QF_CHECK(qf_launch_zgemm(h, h->P, h->Wh, h->A, false, true, -1, 1, false, st));   // :496
-    QF_CHECK(qf_launch_zgemm(h, h->A, h->P, h->S, true, true, -1, 1, true, st));      // :499
+    const StepLayout l = step_layout(h);
+    QF_CHECK(qf_launch_zgemm(h, h->P, h->Wh, h->A, false, true, l.rank, l.G, false, st));       // :496 (own row blocks)
+    if (l.G > 1) QF_CHECK(l.nccl ? qf_comm_allgather_rows(h, h->A, st) : qf_comm_p2p_allgather(h, 0, true, st));
+    QF_CHECK(qf_launch_zgemm(h, h->A, h->P, h->S, true, true, l.rank, l.G, l.G > 1, st));        // :499
+    if (l.G > 1) QF_CHECK(l.nccl ? qf_comm_allgather_rows(h, h->S, st) : qf_comm_p2p_allgather(h, 1, true, st));
     return QF_OK;
 }
 
@@ -1143,11 +1167,12 @@ extern "C" int qf_step_close_iteration(qf_handle_t h, const void *W_dev, const v
     const int N = h->N;
     const int nb = (N + TS - 1) / TS;
     dim3 g(nb, nb, 1);
+    const StepLayout l = step_layout(h);
     if (F_dev)
-        k_post<true><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, N, 1, (const double2 *)W_dev, h->Wh,
+        k_post<true><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, l.hb, l.G, (const double2 *)W_dev, h->Wh,
                                         (const double2 *)F_dev, fscale, QfXchg());
     else
-        k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, N, 1, (const double2 *)W_dev, h->Wh, nullptr, 0.0,
+        k_post<false><<<g, 256, 0, st>>>(h->A, h->S, h->dW, h->rowpart, N, h->nslots, h->ctrl, l.hb, l.G, (const double2 *)W_dev, h->Wh, nullptr, 0.0,
                                          QfXchg());
     k_control<<<dim3((N + 7) / 8, 1), 256, 0, st>>>(h->rowpart, h->nslots, h->rowpart + (size_t)h->nslots * N, h->nslots, N, h->ctrl,
                                                     maxit, minit, 0, 0, 0);
@@ -1172,7 +1197,8 @@ extern "C" int qf_step_increment(qf_handle_t h, void *out_dev, void *stream)
     QF_ON_DEVICE(h->device);
     const int N = h->N;
     const int nb = (N + TS - 1) / TS;
-    k_increment<<<dim3(nb, nb, 1), 256, 0, (cudaStream_t)stream>>>(h->A, (double2 *)out_dev, N, N, 1);
+    const StepLayout l = step_layout(h);
+    k_increment<<<dim3(nb, nb, 1), 256, 0, (cudaStream_t)stream>>>(h->A, (double2 *)out_dev, N, l.hb, l.G);
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;
@@ -1191,12 +1217,13 @@ extern "C" int qf_step_update(qf_handle_t h, void *W_dev, const void *F_dev, dou
     dim3 g(nb, nb, 1);
     const int reinit = (h->step_flags & QF_FLAG_REINITIALIZE) ? 1 : 0;
     double2 *W = (double2 *)W_dev;
+    const StepLayout l = step_layout(h);
     if (compsum)
-        k_update<true, false><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, nullptr, 0.0, QfXchg());
+        k_update<true, false><<<g, 256, 0, st>>>(h->A, W, h->kahan_c, N, h->ctrl, nullptr, 0, l.hb, l.G, h->dW, h->Wh, reinit, nullptr, 0.0, QfXchg());
     else if (F_dev)
-        k_update<false, true><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, (const double2 *)F_dev, fscale, QfXchg());
+        k_update<false, true><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, nullptr, 0, l.hb, l.G, h->dW, h->Wh, reinit, (const double2 *)F_dev, fscale, QfXchg());
     else
-        k_update<false, false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, nullptr, 0, N, 1, h->dW, h->Wh, reinit, nullptr, 0.0, QfXchg());
+        k_update<false, false><<<g, 256, 0, st>>>(h->A, W, nullptr, N, h->ctrl, nullptr, 0, l.hb, l.G, h->dW, h->Wh, reinit, nullptr, 0.0, QfXchg());
     h->launches++;
     QF_CUDA(cudaGetLastError());
     return QF_OK;

@@ -183,7 +183,6 @@ struct QfXchg {
     int upper_only = 0;                               // W~ exchange: send upper tiles only when W is exactly skew-Hermitian
     int push_inline = 0;                              // W~ tiles are stored to the peers by the tail / update kernels themselves
                                                       // (overlaps the NVLink stores with their memory latency) instead of k_xchg_push_wh
-    int dbg_skip_a = 0;                               // timing experiments only (QF_XCHG_DEBUG_SKIP_A=1): GEMM 1 pushes nothing
 };
 __host__ __device__ __forceinline__ int qf_owner_of_row(int row, int hb, int G)
 {
@@ -276,7 +275,8 @@ int qf_xchg_push_rows(qf_handle_s *h, cudaStream_t st);                         
 // isomp.cu: qf_isomp with W_dev == NULL allowed on the tile-exchange path (state already staged in h->Wst)
 int qf_isomp_impl(qf_handle_s *h, void *W_dev, double dt, int steps, double tol, int maxit, int minit, unsigned flags,
                   qf_stats *stats, int32_t *iters_per_step, cudaStream_t st);
-int qf_gemm_prepare(qf_handle_s *h, int rank, int nranks);                  // zgemm.cu: build tile lists (allocates)
+int qf_gemm_prepare(qf_handle_s *h, int rank, int nranks);
+int qf_gemm_prepare_gather(qf_handle_s *h);                                 // zgemm.cu: tile lists of the all-gather path                  // zgemm.cu: build tile lists (allocates)
 void qf_graph_destroy(qf_handle_s *h);                                      // isomp.cu
 
 // isomp.cu

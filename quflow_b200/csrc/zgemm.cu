@@ -745,7 +745,7 @@ k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, 
             // tile-exchange path, GEMM 1: a tile strictly below the diagonal is needed (transposed) by the rank that owns
             // its column block; it goes there as plain stores through the NVLink peer mapping while the next tile is
             // being multiplied
-            if (xg.nranks > 1 && ti.col0 + BN <= ti.a_row0 && !xg.dbg_skip_a) {
+            if (xg.nranks > 1 && ti.col0 + BN <= ti.a_row0) {
                 const int oc = qf_owner_of_row(ti.col0, xg.hb, xg.nranks);
                 if (oc != xg.rank)
                     gemm_store_tile<M3>(acc, xg.peerA[oc] + moff, N, ti.c_row0, ti.c_row0 + (ti.row_end - ti.a_row0), ti.col0, wm, wn, g, t);
@@ -932,6 +932,17 @@ int qf_gemm_prepare(qf_handle_s *h, int rank, int nranks)
         QF_CHECK(get_tile_list(h, false, rank, nranks, false, false, &t, &n));
         QF_CHECK(get_tile_list(h, true, rank, nranks, true, false, &t, &n));
     }
+    return QF_OK;
+}
+
+// Tile lists of the all-gather data path (rank-permuted output rows) for this handle's rank: used by the host-stepped
+// driver on several GPUs whatever the handle's default data path is.
+int qf_gemm_prepare_gather(qf_handle_s *h)
+{
+    const SkTile *t;
+    int n;
+    QF_CHECK(get_tile_list(h, false, h->rank, h->nranks, false, false, &t, &n));
+    QF_CHECK(get_tile_list(h, true, h->rank, h->nranks, true, false, &t, &n));
     return QF_OK;
 }
 

@@ -103,7 +103,9 @@ class ShardedIsomp:
     GPUs between output intervals; give the output callback (``QuSimulation``) to rank 0 only.
 
     The parameter list mirrors ``isomp_fixedpoint`` (isospectral.py:338-353) so that ``solve`` finds ``stats`` by
-    introspection (simulation.py:729); hooks that run host code inside the step are single-GPU only.
+    introspection (simulation.py:729).  Hooks that run host code inside the step (``callback``, ``forcing``,
+    ``strang_splitting``, custom Hamiltonians) run on EVERY rank; that mode shards the two GEMMs and completes their outputs
+    on every rank (all-gather path), so the hooks see complete, identical matrices.
     """
     device_resident = True      # solve(): keep the state on the device between output intervals
 
@@ -127,10 +129,15 @@ class ShardedIsomp:
         from .laplacian import _is_torch
         assert minit >= 1, "minit must be at least 1."          # isospectral.py:400
         assert maxit >= minit, "maxit must be at minit."         # isospectral.py:401
-        if forcing is not None or strang_splitting is not None or callback is not None or not _is_default_hamiltonian(hamiltonian):
-            raise NotImplementedError("ShardedIsomp runs the default Hamiltonian without hooks; hooks are single-GPU (quflow_b200.isomp)")
         if W.ndim != 2:
             raise NotImplementedError("ShardedIsomp advances one (N, N) state; ensembles shard per member (member_slice)")
+        if forcing is not None or strang_splitting is not None or callback is not None or not _is_default_hamiltonian(hamiltonian):
+            # hooks run host code on every rank: host-stepped mode, GEMMs sharded, everything else replicated; the hooks
+            # receive arrays of the same kind as W (numpy copies or device tensors), as on one GPU
+            from .integrators import _isomp_host_stepped
+            return _isomp_host_stepped(W, dt, steps, hamiltonian, time, forcing, strang_splitting, stats, callback, tol, maxit,
+                                       minit, verbatim and self.dist.get_rank() == 0, compsum, reinitialize,
+                                       handle=self.handle(W.shape[-1]))
         auto = (isinstance(tol, str) and tol == 'auto') or (not isinstance(tol, str) and tol < 0)
         if _is_torch(W):
             Wc = W if W.is_contiguous() else W.contiguous()

@@ -34,9 +34,12 @@ def _is_default_hamiltonian(hamiltonian):
 
 
 def _isomp_host_stepped(W, dt, steps, hamiltonian, time, forcing, strang_splitting, stats, callback, tol, maxit,
-                        minit, verbatim, compsum, reinitialize):
+                        minit, verbatim, compsum, reinitialize, handle=None):
     """isomp_fixedpoint with host code inside the step (isospectral.py:403-424, 466-467, 488-491, 511-520, 550-551,
-    594-603).  The matrices stay on the GPU; what the hooks see is of the same kind as the caller's ``W``."""
+    594-603).  The matrices stay on the GPU; what the hooks see is of the same kind as the caller's ``W``.
+
+    ``handle``: a row-sharded handle (``distributed.ShardedIsomp``): the two GEMMs of every iteration run sharded over the
+    ranks, A and S are completed on every rank, and everything the hooks see is complete and identical on every rank."""
     import torch
     torch_in = _is_torch(W)
     if torch_in:
@@ -87,7 +90,7 @@ def _isomp_host_stepped(W, dt, steps, hamiltonian, time, forcing, strang_splitti
     auto = (isinstance(tol, str) and tol == 'auto') or (not isinstance(tol, str) and tol < 0)   # :440
     if isinstance(tol, str) and not auto:
         raise ValueError("tol must be a float or 'auto'")
-    h = get_handle(N, 1, dev.index)
+    h = handle if handle is not None else get_handle(N, 1, dev.index)
     with h.use():      # pinned: hooks may create other handles while views of this one's buffers are alive
         tol_used = h.step_open(Wd, dt, -1.0 if auto else float(tol), compsum=bool(compsum), reinitialize=bool(reinitialize))
         if auto:
