@@ -8,17 +8,23 @@ norm_L2 = 1, N = 2048 by default (the size BASELINE.json's metr
 natural mode: dt = 0.25*hbar(N), tol='auto', maxit=10, minit=1 (about 3 fixed-point iterations per step).
 A "step" is one isospectral-midpoint time step.
 
-* ``value``  : steps/s with W resident in HBM, timed with CUDA events over exactly K steps (max over ranks).
+* ``value``  : steps/s with W resident in HBM, timed with CUDA events over exactly K steps (max over ranks);
+               ``repeat_values`` times the same region again (run-to-run spread, not part of ``value``).
 * ``e2e``    : the same metric through the public Python API with HOST buffers (numpy in pinned memory): every step
                is one ``qf.isomp(W_host, dt, steps=1)`` call = H2D copy of W + one step + D2H copy of W.  On several
-               GPUs the same host-buffer call goes to the row-sharded handle: every rank copies the replicated state
-               in over its own PCIe link, the step runs sharded, every rank reads the result back.
+               GPUs the host state is row-distributed (``host_rows="own"``): every rank copies its own 1/G of the rows
+               in and out over its own PCIe link and the state is completed over NVLink.
 * ``roofline``: the dominant kernel (k_zgemm3m_ws, FP64 DMMA) — EXECUTED flops per launch / CUDA-event launch time,
-               against the FP64 tensor peak measured on this pool (MEASURED_PEAKS.json has no FP64 entry; see
-               profiles/r01_fp64_pipes.txt).  ``roofline_poisson`` reports the HBM-bound Poisson solve against
-               MEASURED_PEAKS.json's copy bandwidth.
-* ``cpu_baseline`` / ``--impl reference``: the CPU oracle port of the reference path (numpy BLAS zgemm + OpenMP
-               Thomas, all host cores) on a bounded sample of the same workload.
+               against the FP64 tensor peak MEASURED IN THE SAME RUN (qf_measure_fp64_tensor_peak; MEASURED_PEAKS.json
+               has no FP64 entry).  ``roofline_poisson`` reports the HBM-bound Poisson solve against
+               MEASURED_PEAKS.json's copy bandwidth.  ``incumbent``: cuBLAS ZGEMM and cusparseDgtsv2StridedBatch, the
+               library kernels the reference's own GPU prototype calls, timed in the same run.
+* ``parity`` : N=1: the GPU against the CPU arm on the same two calls; N>1: the sharded handle against a single-GPU
+               handle (rel. Frobenius, iteration counts, ranks bit-identical by checksum all-gather).
+* ``cpu_baseline`` / ``--impl reference``: the UNMODIFIED reference ``isomp_fixedpoint`` (numba Thomas solve + BLAS
+               zgemm) staged under oracle/_ref, all host cores (thread counts forced before numpy loads and reported
+               through threadpoolctl), on a bounded sample of the same workload; falls back to the oracle port.
+* ``--workload ensemble``: BASELINE config 5 (independent N=256 members sharded per member, no collective).
 """
 import argparse
 import json

@@ -137,7 +137,9 @@ int qf_laplace_host(qf_handle_t h, const void *P_host, void *W_host);
  * `strang_splitting(dt/2, W)` (:466-467, :602-603) and custom or time-dependent Hamiltonians
  * (:416-424, :488-491).  For them the same device kernels are driven one fixed-point iteration at a
  * time; the host may read or replace the intermediate matrices between the calls.  One member
- * (batch = 1), one GPU.  Call order per qf_isomp-equivalent run:
+ * (batch = 1).  On a row-sharded handle (several GPUs) every rank makes the same calls: qf_step_products shards the
+ * two GEMMs and completes A and S on every rank (all-gather path), everything else runs replicated on identical
+ * bytes, so the host code sees complete matrices on every rank.  Call order per qf_isomp-equivalent run:
  *   qf_step_open                                   dW = 0, tolerance from ||W||_inf      (:430, :440-452)
  *   per step:   [W = strang(dt/2, W)]  qf_step_begin        W~ = W + dW, resnorm = inf   (:470-472, :481-482)
  *     per iteration:  qf_step_hamiltonian  P~ = eps Delta^-1 W~                          (:489, :492)

@@ -13,22 +13,32 @@ class Attrs(dict):
 
 
 class Dataset:
+    """Resizable along axis 0 with amortised O(1) appends (capacity doubling), like a chunked HDF5 dataset whose append
+    writes one new chunk instead of rewriting the file."""
+
     def __init__(self, shape, dtype, maxshape=None, chunks=None):
-        self._a = np.zeros(shape, dtype=dtype)
+        self._buf = np.zeros(shape, dtype=dtype)
+        self._n = shape[0] if len(shape) else 0
         self.maxshape, self.chunks = maxshape, chunks
         self.attrs = Attrs()
 
+    @property
+    def _a(self):
+        return self._buf[:self._n] if self._buf.ndim else self._buf
+
     shape = property(lambda self: self._a.shape)
-    dtype = property(lambda self: self._a.dtype)
+    dtype = property(lambda self: self._buf.dtype)
 
     def resize(self, size, axis=0):
-        assert self.maxshape is not None and self.maxshape[axis] is None, "dataset is not resizable along this axis"
-        new = list(self._a.shape)
-        new[axis] = size
-        b = np.zeros(new, dtype=self._a.dtype)
-        n = min(size, self._a.shape[axis])
-        b[:n] = self._a[:n]
-        self._a = b
+        assert axis == 0 and self.maxshape is not None and self.maxshape[0] is None, "dataset is not resizable along this axis"
+        if size > self._buf.shape[0]:
+            cap = max(size, 2 * self._buf.shape[0])
+            nb = np.zeros((cap,) + self._buf.shape[1:], dtype=self._buf.dtype)
+            nb[:self._n] = self._buf[:self._n]
+            self._buf = nb
+        elif size > self._n:
+            self._buf[self._n:size] = 0
+        self._n = size
 
     def __getitem__(self, idx):
         return self._a[idx]
