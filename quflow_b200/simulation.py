@@ -364,11 +364,13 @@ def solve(W,
 class _OutputPipeline:
     """Overlaps the output of `solve` with the computation ("overlap D2H of W with the next chunk").
 
-    `submit(Wdev, kwargs)` enqueues an asynchronous device-to-host copy of the state into one of two pinned buffers on a
-    side stream (ordered after the compute stream by an event) and hands the record to a worker thread, which waits for
-    the copy and then calls the callbacks in submission order with a numpy view of the buffer — exactly what the
-    reference's callbacks receive (`cfun(W, delta_time=, delta_steps=, **stats)`, simulation.py:794-798).  The main thread
-    returns at once and starts the next chunk; it blocks only if both buffers are still in use."""
+    `submit(Wdev, kwargs)` snapshots the state into one of two device staging buffers on the compute stream (a
+    device-to-device copy: microseconds), enqueues the device-to-host copy of that snapshot into the matching pinned
+    buffer on a side stream (ordered after the snapshot by an event) and hands the record to a worker thread, which waits
+    for the copy and then calls the callbacks in submission order with a numpy view of the pinned buffer — exactly what
+    the reference's callbacks receive (`cfun(W, delta_time=, delta_steps=, **stats)`, simulation.py:794-798).  The compute
+    stream never waits for the PCIe copy: the main thread returns at once and starts the next chunk; it blocks only if
+    both buffer pairs are still in use."""
 
     def __init__(self, shape, device, callbacks, depth=2):
         import queue
@@ -379,6 +381,7 @@ class _OutputPipeline:
         self.callbacks = callbacks
         self.stream = torch.cuda.Stream(device=device)
         self.buffers = [torch.empty(shape, dtype=torch.complex128).pin_memory() for _ in range(depth)]
+        self.staging = [torch.empty(shape, dtype=torch.complex128, device=device) for _ in range(depth)]
         self.free = queue.Queue()
         for i in range(depth):
             self.free.put(i)
@@ -408,16 +411,17 @@ class _OutputPipeline:
         torch = self._torch
         if self.error is not None:
             self.close()
-        i = self.free.get()                 # blocks only when every buffer is still being written out
+        i = self.free.get()                 # blocks only when every buffer pair is still being written out
+        compute = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(compute):
+            self.staging[i].copy_(Wdev, non_blocking=True)      # snapshot: the next chunk may overwrite W right away
         ready = torch.cuda.Event()
-        ready.record(torch.cuda.current_stream(self.device))
+        ready.record(compute)
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
-            self.buffers[i].copy_(Wdev, non_blocking=True)
+            self.buffers[i].copy_(self.staging[i], non_blocking=True)
             done = torch.cuda.Event()
             done.record(self.stream)
-        # the next chunk must not overwrite W before the snapshot has been read: order the compute stream after the copy
-        torch.cuda.current_stream(self.device).wait_event(done)
         self.work.put((i, done, dict(kwargs)))
 
     def close(self):

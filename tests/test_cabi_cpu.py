@@ -77,6 +77,21 @@ def test_python_signatures_mirror_the_reference():
     assert qf.hbar(512) == 2.0 / np.sqrt(512.0 ** 2 - 1)             # geometry.py:7-9
 
 
+def test_sharded_integrator_and_quantization_signatures():
+    """The multi-GPU integrator object lists the reference's isomp parameters (so that solve() finds `stats` by
+    introspection, quflow/simulation.py:729, like it does for the reference's IsompCUDA object); mat2shr / shr2mat keep the
+    reference's names and argument meaning plus the explicit basis (quflow/quantization.py:440-519)."""
+    import quflow_b200 as qf
+    from quflow_b200.distributed import ShardedIsomp
+    spec = inspect.getfullargspec(ShardedIsomp.__call__)
+    assert spec.args[1:] == inspect.getfullargspec(qf.isomp).args
+    assert ShardedIsomp.device_resident is True
+    assert inspect.getfullargspec(qf.mat2shr).args == ['W', 'basis', 'elmax']
+    assert inspect.getfullargspec(qf.shr2mat).args == ['omega', 'basis', 'N']
+    from quflow_b200.quantization import basis_size
+    assert basis_size(33) == sum((33 - m) ** 2 for m in range(33))      # host arithmetic only: no CUDA call
+
+
 def test_logger_signatures_mirror_the_reference():
     """quflow/geometry.py:53-76 and quflow/physics.py:9-38: same names and argument lists."""
     import quflow_b200 as qf
