@@ -33,17 +33,23 @@ namespace {
 constexpr int GEMM_THREADS = 256;
 constexpr int MI = 4;   // 8-row sub-tiles per warp (warp tile is 32 rows in both variants)
 
-template <bool M3>
+// M3: 0 = 4M arithmetic (128 x 64 tiles), 1 = 3M arithmetic (64 x 64 tiles), 2 = 3M arithmetic with 64 x 32 tiles for
+// small problems (twice as many tiles: every SM owns a whole, unsplit tile where 64 x 64 tiles would fill half the GPU)
+template <int M3>
 struct Cfg;
 template <>
-struct Cfg<false> {
+struct Cfg<0> {
     static constexpr int BM = 128, BN = 64, BK = 16, WN = 2, NJ = 4, NACC = 2, STAGES = 3;
 };
 template <>
-struct Cfg<true> {
+struct Cfg<1> {
     static constexpr int BM = 64, BN = 64, BK = 32, WN = 4, NJ = 2, NACC = 3, STAGES = 3;
 };
-template <bool M3>
+template <>
+struct Cfg<2> {
+    static constexpr int BM = 64, BN = 32, BK = 32, WN = 4, NJ = 1, NACC = 3, STAGES = 3;
+};
+template <int M3>
 struct Geo {
     using C = Cfg<M3>;
     static constexpr int A_STAGE_BYTES = C::BM * C::BK * 16;   // BK/8 boxes [BM rows][128 B]
@@ -83,7 +89,7 @@ __device__ __forceinline__ double2 lds128(uint32_t addr)
 }
 
 // ---- cp.async loader (fallback when the driver has no tensor-map encoder, or QF_GEMM_LOAD=cpasync) --------
-template <bool M3>
+template <int M3>
 __device__ __forceinline__ void load_stage(uint32_t sA, uint32_t sB, const double2 *__restrict__ A,
                                            const double2 *__restrict__ B, int N, int row0, int row_end, int col0, int k0,
                                            int tid)
@@ -115,12 +121,12 @@ __device__ __forceinline__ void load_stage(uint32_t sA, uint32_t sB, const doubl
 // Fragments are double-buffered in registers: the LDS.128 (and, for 3M, the DADDs forming Are+Aim / Bre+Bim) of
 // k-step ks+1 are issued before the DMMAs of k-step ks, so the tensor pipe never waits on shared-memory latency
 // inside a stage.
-template <bool M3>
+template <int M3>
 struct Frag {
     double a_re[MI], a_im[MI], a_x[MI], b_re[Cfg<M3>::NJ], b_im[Cfg<M3>::NJ], b_x[Cfg<M3>::NJ];
 };
 
-template <bool M3>
+template <int M3>
 __device__ __forceinline__ void gemm_load_frag(Frag<M3> &f, uint32_t sb, const uint32_t (&a_off)[2], const uint32_t (&b_off)[2],
                                                int ks)
 {
@@ -141,7 +147,7 @@ __device__ __forceinline__ void gemm_load_frag(Frag<M3> &f, uint32_t sb, const u
 }
 
 // derived operands: 3M  Are+Aim, Bre+Bim (DADD on the FP64 pipe);  4M  -Aim (integer XOR)
-template <bool M3>
+template <int M3>
 __device__ __forceinline__ void gemm_finish_frag(Frag<M3> &f)
 {
 #pragma unroll
@@ -150,7 +156,7 @@ __device__ __forceinline__ void gemm_finish_frag(Frag<M3> &f)
     for (int j = 0; j < Cfg<M3>::NJ; ++j) f.b_x[j] = M3 ? (f.b_re[j] + f.b_im[j]) : 0.0;
 }
 
-template <bool M3>
+template <int M3>
 __device__ __forceinline__ void gemm_mma_frag(double (&acc)[MI][Cfg<M3>::NJ][Cfg<M3>::NACC][2], const Frag<M3> &f)
 {
     constexpr int NJ = Cfg<M3>::NJ;
@@ -185,7 +191,7 @@ __device__ __forceinline__ void gemm_mma_frag(double (&acc)[MI][Cfg<M3>::NJ][Cfg
     }
 }
 
-template <bool M3>
+template <int M3>
 __device__ __forceinline__ void gemm_compute_stage(double (&acc)[MI][Cfg<M3>::NJ][Cfg<M3>::NACC][2], uint32_t sb,
                                                    const uint32_t (&a_off)[2], const uint32_t (&b_off)[2])
 {
@@ -213,7 +219,7 @@ __device__ __forceinline__ void gemm_compute_stage(double (&acc)[MI][Cfg<M3>::NJ
     }
 }
 
-template <bool M3>
+template <int M3>
 __device__ __forceinline__ void gemm_frag_offsets(uint32_t (&a_off)[2], uint32_t (&b_off)[2], int wm, int wn, int g, int t)
 {
     // per-thread fragment base offsets inside a stage (see file header for the k permutation)
@@ -226,7 +232,7 @@ __device__ __forceinline__ void gemm_frag_offsets(uint32_t (&a_off)[2], uint32_t
 }
 
 // Accumulate k-tiles [kt_begin, kt_end) of one output tile; cp.async multi-stage pipeline.
-template <bool M3>
+template <int M3>
 __device__ __forceinline__ void gemm_mainloop(double (&acc)[MI][Cfg<M3>::NJ][Cfg<M3>::NACC][2], uint32_t smem_base,
                                               const double2 *__restrict__ A, const double2 *__restrict__ B, int N, int row0,
                                               int row_end, int col0, int kt_begin, int kt_end, int tid, int wm, int wn, int g, int t)
@@ -263,7 +269,7 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[MI][Cfg<M3>::NJ][Cfg
 // Same main loop fed by TMA: one elected thread issues 2 (A) + BN/8 (B) cp.async.bulk.tensor boxes of 128-byte rows
 // per stage into the SWIZZLE_128B layout; completion is tracked by one mbarrier per stage (expect_tx = stage bytes).
 // `gk` counts the k-tiles this CTA has consumed since kernel start: stage = gk % STAGES, phase = (gk / STAGES) & 1.
-template <bool M3>
+template <int M3>
 __device__ __forceinline__ void gemm_mainloop_tma(double (&acc)[MI][Cfg<M3>::NJ][Cfg<M3>::NACC][2], uint32_t smem_base,
                                                   uint32_t bars, const CUtensorMap *tmA, const CUtensorMap *tmB, int member,
                                                   int a_mem_row0, int col0, int kt_begin, int kt_end, uint32_t &gk, int tid,
@@ -304,7 +310,7 @@ __device__ __forceinline__ void gemm_mainloop_tma(double (&acc)[MI][Cfg<M3>::NJ]
 }
 
 // each thread owns, per 8x8 sub-tile, row g and the two adjacent columns 2t, 2t+1 (row0 / row_end: OUTPUT rows)
-template <bool M3>
+template <int M3>
 __device__ __forceinline__ void gemm_store_tile(const double (&acc)[MI][Cfg<M3>::NJ][Cfg<M3>::NACC][2], double2 *__restrict__ C,
                                                 int N, int row0, int row_end, int col0, int wm, int wn, int g, int t)
 {
@@ -387,7 +393,7 @@ struct SkSched {
 // written to rows c_row0.. of C (C may use the rank-permuted row layout of the multi-GPU path, see qf_common.cuh).
 struct SkTile { int member, a_row0, c_row0, col0, row_end, op_row0, pad1, pad2; };   // op_row0: first row of the A operand in memory
 
-template <bool M3, bool TMA>
+template <int M3, bool TMA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, double2 *__restrict__ Cg, int N,
            const SkTile *__restrict__ tiles, int ntiles, double2 *__restrict__ ws, int *__restrict__ flags,
@@ -493,10 +499,10 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
 // Tile-exchange path (xg.nranks > 1): the rank that owns the tile pair also stores the residual partials into every peer's
 // copy (plain stores through the NVLink peer mappings), so that after the exchange barrier every rank evaluates the
 // stopping rule on identical numbers; the W~ tiles follow in a copy kernel of their own (comm.cu: k_xchg_push_wh).
-__device__ __forceinline__ void epi_post_tile(const double (&acc)[MI][Cfg<true>::NJ][Cfg<true>::NACC][2], const SkTile &ti, int N,
+__device__ __forceinline__ void epi_post_tile(const double (&acc)[MI][Cfg<1>::NJ][Cfg<1>::NACC][2], const SkTile &ti, int N,
                                               int wm, int wn, int g, int t, const QfEpiPost &E, const QfXchg &xg)
 {
-    constexpr int NJ = Cfg<true>::NJ;
+    constexpr int NJ = Cfg<1>::NJ;
     const size_t moff = (size_t)ti.member * N * N;
     const double2 *__restrict__ A = E.A + moff;
     const double2 *__restrict__ W = E.W + moff;
@@ -602,14 +608,15 @@ __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 
 // at the (named) barrier around the fix-up.
 constexpr int WS_THREADS = GEMM_THREADS + 32;
 
-template <bool POST>
+template <int M3, bool POST>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, int ntiles, double2 *__restrict__ ws,
              int *__restrict__ flags, const QfCtrl *__restrict__ ctrl, int gated, const __grid_constant__ CUtensorMap tmA,
              const __grid_constant__ CUtensorMap tmB, const QfEpiPost epi, const QfXchg xg)
 {
     const CUtensorMap *tmAp = &tmA;
-    constexpr bool M3 = true;
+    static_assert(M3 == 1 || M3 == 2, "warp-specialised kernel: 3M arithmetic only");
+    static_assert(!POST || M3 == 1, "the fused tail is written for the 64 x 64 tile");
     constexpr int STAGES = Cfg<M3>::STAGES, NJ = Cfg<M3>::NJ, NACC = Cfg<M3>::NACC, WN = Cfg<M3>::WN;
     constexpr int BM = Cfg<M3>::BM, BN = Cfg<M3>::BN, BK = Cfg<M3>::BK;
     constexpr int STAGE_BYTES = Geo<M3>::STAGE_BYTES, A_STAGE_BYTES = Geo<M3>::A_STAGE_BYTES;
@@ -729,7 +736,7 @@ k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, 
                     ++peer;
                 }
             }
-            if (POST) {
+            if constexpr (POST) {
                 // GEMM 2 of the fixed-point iteration: dW, W~ and the residual partials straight from the accumulators
                 if (xg.nranks > 1 && !g1_seen) {
                     // the transposed A tiles this rank needs were pushed by their owners during THEIR first GEMM: wait (once
@@ -785,12 +792,25 @@ struct QfGemmPlan {
     double2 *ws = nullptr;      // [max_ctas][32][256] partial tiles
     int *flags = nullptr;       // [max_ctas]
     // cached tile lists keyed by (upper_only, rank, nranks, a_permuted); rank < 0 = all ranks (single-GPU emulation)
-    struct List { int upper, rank, nranks, aperm, natural, ntiles; SkTile *dev; };
+    struct List { int upper, rank, nranks, aperm, natural, bn, ntiles; SkTile *dev; };
     std::vector<List> lists;
-    int BM() const { return m3 ? Cfg<true>::BM : Cfg<false>::BM; }
-    int BN() const { return m3 ? Cfg<true>::BN : Cfg<false>::BN; }
-    int BK() const { return m3 ? Cfg<true>::BK : Cfg<false>::BK; }
+    bool small_tiles = true;    // QF_GEMM_SMALL=0: never use the 64 x 32 tile variant
+    int BM() const { return m3 ? Cfg<1>::BM : Cfg<0>::BM; }
+    int BN(bool small = false) const { return m3 ? (small ? Cfg<2>::BN : Cfg<1>::BN) : Cfg<0>::BN; }
+    int BK() const { return m3 ? Cfg<1>::BK : Cfg<0>::BK; }
 };
+
+// The 64 x 32 tile variant pays off when the 64 x 64 tiles of a launch would occupy at most half of the SMs (N <= 512 for
+// one simulation): twice as many tiles, every SM owns a whole tile (or a clean share of one) instead of a stream-K
+// fragment.  Single GPU, warp-specialised 3M TMA kernel only.
+static bool use_small_tiles(const qf_handle_s *h, bool upper_only, int nranks)
+{
+    const QfGemmPlan *p = h->gemm;
+    if (!(p->small_tiles && p->m3 && p->tma && p->warp_spec && nranks == 1 && h->N >= 8)) return false;
+    const int nt = (h->N + 63) / 64;
+    const long long tiles64 = (long long)h->batch * (upper_only ? (long long)nt * (nt + 1) / 2 : (long long)nt * nt);
+    return 2 * tiles64 <= p->max_ctas;
+}
 
 int qf_gemm_create(qf_handle_s *h)
 {
@@ -800,17 +820,22 @@ int qf_gemm_create(qf_handle_s *h)
     p->m3 = !(env && env[0] == '0');
     p->max_ctas = h->sm_count;
     {
+        const char *sm = getenv("QF_GEMM_SMALL");
+        p->small_tiles = !(sm && sm[0] == '0');
+    }
+    {
         const char *c = getenv("QF_GEMM_COOP");
         int coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
         p->cooperative = coop && !(c && c[0] == '0');
     }
-    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<false>::SMEM));
-    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<false>::SMEM));
-    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM));
-    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM));
-    QF_CUDA(cudaFuncSetAttribute(k_zgemm3m_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM));
-    QF_CUDA(cudaFuncSetAttribute(k_zgemm3m_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<0>::SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<0>::SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1>::SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm_sk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1>::SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm3m_ws<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1>::SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm3m_ws<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1>::SMEM));
+    QF_CUDA(cudaFuncSetAttribute(k_zgemm3m_ws<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2>::SMEM));
     {
         const char *w = getenv("QF_GEMM_WS");
         p->warp_spec = !(w && w[0] == '0');
@@ -844,7 +869,7 @@ extern "C" int qf_gemm_is_3m(qf_handle_t h) { return h && h->gemm && h->gemm->m3
 extern "C" double qf_gemm_executed_flops(qf_handle_t h, int upper_only)
 {
     if (!h || !h->gemm) return 0.0;
-    const int N = h->N, BMv = h->gemm->BM(), BNv = h->gemm->BN();
+    const int N = h->N, BMv = h->gemm->BM(), BNv = h->gemm->BN(use_small_tiles(h, upper_only != 0, h->nranks));
     long long tiles = 0;
     for (int r0 = 0; r0 < N; r0 += BMv)
         for (int c0 = 0; c0 < N; c0 += BNv)
@@ -876,19 +901,20 @@ static int make_tmap(qf_handle_s *h, const double2 *base, int box_rows, CUtensor
 // natural: output rows keep their natural positions (single GPU: always true in effect; tile-exchange path); otherwise the
 // output uses the rank-permuted row layout of the legacy all-gather paths (qf_prow).
 static int get_tile_list(qf_handle_s *h, bool upper_only, int rank, int nranks, bool a_permuted, bool natural, const SkTile **dev,
-                         int *ntiles)
+                         int *ntiles, bool small = false)
 {
     QfGemmPlan *p = h->gemm;
     if (nranks == 1) { natural = true; a_permuted = false; }      // one rank: the permutation is the identity
+    const int BNv = p->BN(small);
     for (auto &l : p->lists)
         if (l.upper == (int)upper_only && l.rank == rank && l.nranks == nranks && l.aperm == (int)a_permuted &&
-            l.natural == (int)natural) {
+            l.natural == (int)natural && l.bn == BNv) {
             *dev = l.dev;
             *ntiles = l.ntiles;
             return QF_OK;
         }
     std::vector<SkTile> tl;
-    const int N = h->N, BMv = p->BM(), BNv = p->BN();
+    const int N = h->N, BMv = p->BM();
     const int hb = qf_block_rows(N, nranks);
     for (int b = 0; b < h->batch; ++b)
         for (int r = 0; r < nranks; ++r) {
@@ -901,7 +927,7 @@ static int get_tile_list(qf_handle_s *h, bool upper_only, int rank, int nranks, 
                 // Tile order = L2 blocking.  Column groups of CG tile-columns, row-major inside a group: the B panel of a
                 // group (CG * BN columns, 33 MB at N=2048) stays L2-resident while the waves stream the A row panels past
                 // it, so A is read ncols/CG times and B once (all 32 tile-columns at once re-reads B every wave).
-                const int CG = 16 * BNv;
+                const int CG = 1024;      // complex columns per group
                 for (int cg = 0; cg < N; cg += CG)
                     for (int r0 = rb; r0 < re; r0 += BMv)
                         for (int c0 = cg; c0 < std::min(N, cg + CG); c0 += BNv) {
@@ -911,7 +937,7 @@ static int get_tile_list(qf_handle_s *h, bool upper_only, int rank, int nranks, 
                         }
             }
         }
-    QfGemmPlan::List l{(int)upper_only, rank, nranks, (int)a_permuted, (int)natural, (int)tl.size(), nullptr};
+    QfGemmPlan::List l{(int)upper_only, rank, nranks, (int)a_permuted, (int)natural, BNv, (int)tl.size(), nullptr};
     QF_CUDA(cudaMalloc(&l.dev, sizeof(SkTile) * std::max<size_t>(tl.size(), 1)));
     QF_CUDA(cudaMemcpy(l.dev, tl.data(), sizeof(SkTile) * tl.size(), cudaMemcpyHostToDevice));
     p->lists.push_back(l);
@@ -927,6 +953,8 @@ int qf_gemm_prepare(qf_handle_s *h, int rank, int nranks)
     if (h->comm_mode == 5 || nranks == 1) {
         QF_CHECK(get_tile_list(h, false, rank, nranks, false, true, &t, &n));
         QF_CHECK(get_tile_list(h, true, rank, nranks, false, true, &t, &n));    // fused GEMM-2 tail
+        if (use_small_tiles(h, false, nranks)) QF_CHECK(get_tile_list(h, false, rank, nranks, false, true, &t, &n, true));
+        if (use_small_tiles(h, true, nranks)) QF_CHECK(get_tile_list(h, true, rank, nranks, false, true, &t, &n, true));
     }
     if (h->comm_mode != 5) {
         QF_CHECK(get_tile_list(h, false, rank, nranks, false, false, &t, &n));
@@ -948,7 +976,7 @@ int qf_gemm_prepare_gather(qf_handle_s *h)
 
 // The stream-K CTAs wait on one another (finisher <- contributors), so they must all be resident at the same time:
 // the launch is cooperative, which makes the driver co-schedule the whole grid (grid <= #SMs, 1 CTA/SM).
-template <bool M3, bool TMA>
+template <int M3, bool TMA>
 static cudaError_t launch_sk_impl(qf_handle_s *h, int G, const double2 *A, const double2 *B, double2 *C, const SkTile *tiles,
                                   int ntiles, int gated, const CUtensorMap &tmA, const CUtensorMap &tmB, cudaStream_t st)
 {
@@ -967,7 +995,7 @@ static cudaError_t launch_sk_impl(qf_handle_s *h, int G, const double2 *A, const
                               (const QfCtrl *)h->ctrl, gated, tmA, tmB);
 }
 
-template <bool M3>
+template <int M3>
 static cudaError_t launch_sk(qf_handle_s *h, bool tma, int G, const double2 *A, const double2 *B, double2 *C, const SkTile *tiles,
                              int ntiles, int gated, const CUtensorMap &tmA, const CUtensorMap &tmB, cudaStream_t st)
 {
@@ -983,7 +1011,8 @@ int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 
     QfGemmPlan *p = h->gemm;
     const SkTile *tiles;
     int ntiles;
-    QF_CHECK(get_tile_list(h, upper_only, rank, nranks, a_permuted, natural, &tiles, &ntiles));
+    const bool small = !xg && use_small_tiles(h, upper_only, nranks);
+    QF_CHECK(get_tile_list(h, upper_only, rank, nranks, a_permuted, natural, &tiles, &ntiles, small));
     if (ntiles == 0) return QF_OK;
     const int BK = p->BK();
     const int KT = (N + BK - 1) / BK;
@@ -1007,7 +1036,7 @@ int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(G);
         cfg.blockDim = dim3(WS_THREADS);
-        cfg.dynamicSmemBytes = Geo<true>::SMEM;
+        cfg.dynamicSmemBytes = small ? Geo<2>::SMEM : Geo<1>::SMEM;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeCooperative;
@@ -1016,8 +1045,12 @@ int qf_launch_zgemm(qf_handle_s *h, const double2 *A, const double2 *B, double2 
         cfg.numAttrs = p->cooperative ? 1 : 0;
         const QfEpiPost none = {};
         const QfXchg solo;
-        QF_CUDA(cudaLaunchKernelEx(&cfg, k_zgemm3m_ws<false>, C, N, tiles, ntiles, p->ws, p->flags, (const QfCtrl *)h->ctrl,
-                                   gated ? 1 : 0, tmA, tmB, none, xg ? *xg : solo));
+        if (small)
+            QF_CUDA(cudaLaunchKernelEx(&cfg, k_zgemm3m_ws<2, false>, C, N, tiles, ntiles, p->ws, p->flags, (const QfCtrl *)h->ctrl,
+                                       gated ? 1 : 0, tmA, tmB, none, solo));
+        else
+            QF_CUDA(cudaLaunchKernelEx(&cfg, k_zgemm3m_ws<1, false>, C, N, tiles, ntiles, p->ws, p->flags, (const QfCtrl *)h->ctrl,
+                                       gated ? 1 : 0, tmA, tmB, none, xg ? *xg : solo));
     } else {
         QF_CUDA(p->m3 ? launch_sk<true>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st)
                       : launch_sk<false>(h, tma, G, A, B, C, tiles, ntiles, gated ? 1 : 0, tmA, tmB, st));
@@ -1056,7 +1089,7 @@ int qf_launch_zgemm_post(qf_handle_s *h, const double2 *A, const double2 *B, con
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(G);
     cfg.blockDim = dim3(WS_THREADS);
-    cfg.dynamicSmemBytes = Geo<true>::SMEM;
+    cfg.dynamicSmemBytes = Geo<1>::SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;
@@ -1065,7 +1098,7 @@ int qf_launch_zgemm_post(qf_handle_s *h, const double2 *A, const double2 *B, con
     cfg.numAttrs = p->cooperative ? 1 : 0;
     double2 *nullC = nullptr;
     const QfXchg solo;
-    QF_CUDA(cudaLaunchKernelEx(&cfg, k_zgemm3m_ws<true>, nullC, N, tiles, ntiles, p->ws, p->flags, (const QfCtrl *)h->ctrl,
+    QF_CUDA(cudaLaunchKernelEx(&cfg, k_zgemm3m_ws<1, true>, nullC, N, tiles, ntiles, p->ws, p->flags, (const QfCtrl *)h->ctrl,
                                gated ? 1 : 0, tmA, tmB, epi, xg ? *xg : solo));
     h->launches++;
     QF_CUDA(cudaGetLastError());
