@@ -794,7 +794,7 @@ struct QfGemmPlan {
     // cached tile lists keyed by (upper_only, rank, nranks, a_permuted); rank < 0 = all ranks (single-GPU emulation)
     struct List { int upper, rank, nranks, aperm, natural, bn, ntiles; SkTile *dev; };
     std::vector<List> lists;
-    bool small_tiles = true;    // QF_GEMM_SMALL=0: never use the 64 x 32 tile variant
+    int small_tiles = 1;        // QF_GEMM_SMALL=0: never use the 64 x 32 tile variant, 2: always (experiments)
     int BM() const { return m3 ? Cfg<1>::BM : Cfg<0>::BM; }
     int BN(bool small = false) const { return m3 ? (small ? Cfg<2>::BN : Cfg<1>::BN) : Cfg<0>::BN; }
     int BK() const { return m3 ? Cfg<1>::BK : Cfg<0>::BK; }
@@ -807,6 +807,7 @@ static bool use_small_tiles(const qf_handle_s *h, bool upper_only, int nranks)
 {
     const QfGemmPlan *p = h->gemm;
     if (!(p->small_tiles && p->m3 && p->tma && p->warp_spec && nranks == 1 && h->N >= 8)) return false;
+    if (p->small_tiles == 2) return true;
     const int nt = (h->N + 63) / 64;
     const long long tiles64 = (long long)h->batch * (upper_only ? (long long)nt * (nt + 1) / 2 : (long long)nt * nt);
     return 2 * tiles64 <= p->max_ctas;
@@ -821,7 +822,7 @@ int qf_gemm_create(qf_handle_s *h)
     p->max_ctas = h->sm_count;
     {
         const char *sm = getenv("QF_GEMM_SMALL");
-        p->small_tiles = !(sm && sm[0] == '0');
+        p->small_tiles = sm ? atoi(sm) : 1;
     }
     {
         const char *c = getenv("QF_GEMM_COOP");
