@@ -60,6 +60,18 @@ struct Geo {
 };
 constexpr int WS_D2_PER_THREAD = 32;   // workspace slot = 32 double2 per thread (max over the variants)
 
+// Stream-K finisher: wait for a contributor's partial tile.  The contributor computed its share FIRST, so with all CTAs
+// resident (cooperative launch) the wait is short; without co-residency (QF_GEMM_COOP=0 on a busy GPU) it could never
+// end, so it is bounded: after about five seconds the kernel traps (a launch failure the host reports) instead of hanging.
+__device__ __forceinline__ void sk_wait_partial(int *flag)
+{
+    const long long t0 = clock64();
+    while (atomicAdd(flag, 0) == 0) {
+        __nanosleep(64);
+        if (clock64() - t0 > 10000000000ll) __trap();
+    }
+}
+
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -466,7 +478,7 @@ k_zgemm_sk(const double2 *__restrict__ Ag, const double2 *__restrict__ Bg, doubl
                 long long covered = sched.it_end;
                 while (covered < tile_end) {
                     if (tid == 0) {
-                        while (atomicAdd(flags + peer, 0) == 0) __nanosleep(64);
+                        sk_wait_partial(flags + peer);
                         atomicExch(flags + peer, 0);   // consume: flags are all zero again when the kernel ends
                     }
                     __syncthreads();
@@ -716,7 +728,7 @@ k_zgemm3m_ws(double2 *__restrict__ Cg, int N, const SkTile *__restrict__ tiles, 
                 long long covered = sched.it_end;
                 while (covered < tile_end) {
                     if (tid == 0) {
-                        while (atomicAdd(flags + peer, 0) == 0) __nanosleep(64);
+                        sk_wait_partial(flags + peer);
                         atomicExch(flags + peer, 0);
                     }
                     consumer_bar_sync();
