@@ -437,6 +437,28 @@ def test_tile_exchange_ranks_in_lockstep_on_one_gpu(qf, N, G, fuse, push, monkey
         h.close()
 
 
+def test_tile_exchange_silent_peer_times_out_instead_of_hanging(qf, monkeypatch):
+    """A rank whose peer never shows up must not hang the GPU inside a kernel: the peer waits are bounded
+    (QF_COMM_TIMEOUT_S), the run is marked failed on the device, later waits return at once, and the call reports
+    QF_ERR_COMM.  Here rank 0 of a local two-rank group is run on its own, so rank 1's flags never arrive."""
+    import time
+    import torch
+    from quflow_b200._cuda import Handle
+    from quflow_b200._cuda.binding import attach_local, QfError, QF_ERR_COMM
+    N = 256
+    monkeypatch.setenv("QF_COMM_TIMEOUT_S", "0.2")
+    hs = [Handle(N) for _ in range(2)]
+    attach_local(hs)
+    W = torch.from_numpy(oracle.random_skewherm(N, 3)).cuda()
+    t0 = time.perf_counter()
+    with pytest.raises(QfError) as info:
+        hs[0].isomp(W, 0.25 * qf.hbar(N), 3)
+    assert info.value.code == QF_ERR_COMM
+    assert time.perf_counter() - t0 < 10.0          # one bounded wait, then everything falls through
+    for h in hs:
+        h.close()
+
+
 @pytest.mark.parametrize("N", [32, 100, 257, 512])
 def test_fused_gemm2_tail_matches_separate_kernel(qf, N):
     """The tail of the iteration fused into the GEMM-2 epilogue (qf_set_fuse_post) against the separate k_post launch and
