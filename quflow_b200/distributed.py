@@ -25,6 +25,21 @@ def row_blocks(N: int, world: int):
     return [[(r * hb, (r + 1) * hb), ((2 * world - 1 - r) * hb, (2 * world - r) * hb)] for r in range(world)]
 
 
+def owner_of_row(i: int, N: int, world: int) -> int:
+    """Rank that owns logical row i — and, on the tile-exchange path, every tile pair {(I, J), (J, I)}, I <= J, whose
+    row block I contains i.  Mirrors qf_owner_of_row() in csrc/qf_common.cuh."""
+    if world == 1:
+        return 0
+    blk = i // (N // (2 * world))
+    return blk if blk < world else 2 * world - 1 - blk
+
+
+def tile_exchange_supported(N: int, world: int) -> bool:
+    """The tile-exchange data path needs ownership blocks made of whole 64-row tiles: N divisible by 128 * world
+    (csrc/comm.cu: p2p_finish); otherwise the library falls back to the pull all-gather."""
+    return world == 1 or N % (128 * world) == 0
+
+
 def permuted_row(i: int, N: int, world: int) -> int:
     """Row index of logical row i in the rank-permuted layout of the GEMM outputs."""
     if world == 1:

@@ -29,6 +29,24 @@ def test_row_partition_is_a_balanced_permutation(N, world):
         assert max(work) - min(work) <= hb * hb
 
 
+@pytest.mark.parametrize("N,world", [(256, 2), (1024, 4), (2048, 8), (1024, 8)])
+def test_tile_pair_ownership_is_a_balanced_partition(N, world):
+    """Tile-exchange path: the upper 64 x 64 tiles (I <= J) belong to the owner of row block I.  Every tile has exactly one
+    owner, the owners agree with row_blocks(), and pairing block r with block 2*world-1-r balances the upper-triangular
+    work: tile counts per rank differ by at most one tile column."""
+    assert qd.tile_exchange_supported(N, world)
+    nt = N // 64
+    counts = [0] * world
+    for I in range(nt):
+        owner = qd.owner_of_row(64 * I, N, world)
+        assert all(qd.owner_of_row(r, N, world) == owner for r in range(64 * I, 64 * I + 64))      # whole tiles
+        assert any(a <= 64 * I < b for a, b in qd.row_blocks(N, world)[owner])
+        counts[owner] += nt - I                                                                    # tiles (I, J >= I)
+    assert sum(counts) == nt * (nt + 1) // 2
+    assert max(counts) - min(counts) <= N // (2 * world) // 64
+    assert not qd.tile_exchange_supported(N + 64, world)
+
+
 def test_row_partition_rejects_bad_sizes():
     with pytest.raises(ValueError):
         qd.row_blocks(1000, 8)
