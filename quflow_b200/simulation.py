@@ -97,15 +97,29 @@ class QuSimulation(object):
         if 'shr' in self.qutypes and self.basis is None:
             raise ValueError(f"{filename}: the 'shr' representation needs the quantization basis: QuSimulation(..., basis=get_basis(N))")
 
-    def _representations(self, W):
-        """(dataset name, array, qutype) for every stored representation (reference: qutypes_iterator, simulation.py:287-355)."""
+    def _representations(self, W, shr=None):
+        """(dataset name, array, qutype) for every stored representation (reference: qutypes_iterator, simulation.py:287-355).
+        ``shr``: coefficients already computed on the device from the device-resident state (``device_shr``)."""
         for qutype, dtype in self.qutypes.items():
             if qutype == 'mat':
                 yield 'mat', W.astype(dtype or W.dtype), qutype
             elif qutype == 'shr':
-                from .quantization import mat2shr
-                omega = np.squeeze(np.array([mat2shr(np.ascontiguousarray(Wi), self.basis) for Wi in W.reshape((-1,) + W.shape[-2:])]))
-                yield 'shr', omega.astype(dtype or omega.dtype), qutype
+                if shr is None:
+                    from .quantization import mat2shr
+                    shr = np.squeeze(np.array([mat2shr(np.ascontiguousarray(Wi), self.basis)
+                                               for Wi in W.reshape((-1,) + W.shape[-2:])]))
+                yield 'shr', np.asarray(shr).astype(dtype or np.asarray(shr).dtype), qutype
+
+    def device_shr(self, Wdev):
+        """Spectral output without the host: mat2shr of a device-resident (N, N) state against the device-resident basis
+        (uploaded once).  Returns a CUDA tensor, or None when this store keeps no 'shr' representation.  Used by
+        ``solve`` so that a record's coefficients are computed from the state on the GPU and only N**2 doubles travel."""
+        if 'shr' not in self.qutypes or self.basis is None or Wdev.ndim != 2:
+            return None
+        from .quantization import mat2shr, device_basis
+        if not hasattr(self.basis, "is_cuda"):
+            self.basis = device_basis(self.basis, Wdev.device)         # once; later records reuse it
+        return mat2shr(Wdev, self.basis)
 
     # ------------------------------------------------------------------ creation
     def _create(self, W, time, fields):
@@ -156,6 +170,7 @@ class QuSimulation(object):
     def __call__(self, W, delta_time, delta_steps=1, **kwargs):
         """Append one output record (simulation.py:433-478)."""
         W = np.asarray(W)
+        shr = kwargs.pop('_device_shr', None)      # handed over by solve()'s output pipeline (not a user field)
         with _h5py().File(self.filename, "r+") as f:
             def push(name, value):
                 ds = f[self.datapath + name]
@@ -163,7 +178,7 @@ class QuSimulation(object):
                 ds[-1, ...] = value
                 return ds
 
-            for name, arr, _ in self._representations(W):                      # simulation.py:450-453
+            for name, arr, _ in self._representations(W, shr):                 # simulation.py:450-453
                 push(name, arr.astype(f[self.datapath + name].dtype))
             t = f[self.datapath + "time"]
             push("time", t[-1] + delta_time)
@@ -382,6 +397,7 @@ class _OutputPipeline:
         self.stream = torch.cuda.Stream(device=device)
         self.buffers = [torch.empty(shape, dtype=torch.complex128).pin_memory() for _ in range(depth)]
         self.staging = [torch.empty(shape, dtype=torch.complex128, device=device) for _ in range(depth)]
+        self.shr_host = [dict() for _ in range(depth)]      # per buffer pair: callback index -> pinned coefficient buffer
         self.free = queue.Queue()
         for i in range(depth):
             self.free.put(i)
@@ -395,13 +411,16 @@ class _OutputPipeline:
             item = self.work.get()
             if item is None:
                 return
-            i, done, kwargs = item
+            i, done, kwargs, shr = item
             try:
                 if self.error is None:
                     done.synchronize()
                     Wcb = self.buffers[i].numpy()
-                    for cfun in self.callbacks:
-                        cfun(Wcb, **kwargs)
+                    for j, cfun in enumerate(self.callbacks):
+                        if j in shr:
+                            cfun(Wcb, _device_shr=shr[j].numpy(), **kwargs)
+                        else:
+                            cfun(Wcb, **kwargs)
             except BaseException as e:      # surfaced by close() on the caller's thread
                 self.error = e
             finally:
@@ -413,16 +432,28 @@ class _OutputPipeline:
             self.close()
         i = self.free.get()                 # blocks only when every buffer pair is still being written out
         compute = torch.cuda.current_stream(self.device)
+        shr_dev = {}
         with torch.cuda.stream(compute):
             self.staging[i].copy_(Wdev, non_blocking=True)      # snapshot: the next chunk may overwrite W right away
+            for j, cfun in enumerate(self.callbacks):           # spectral output straight from the device-resident state
+                om = cfun.device_shr(self.staging[i]) if isinstance(cfun, QuSimulation) else None
+                if om is not None:
+                    shr_dev[j] = om
         ready = torch.cuda.Event()
         ready.record(compute)
+        shr = {}
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
             self.buffers[i].copy_(self.staging[i], non_blocking=True)
+            for j, om in shr_dev.items():
+                if j not in self.shr_host[i]:
+                    self.shr_host[i][j] = torch.empty(om.shape, dtype=om.dtype).pin_memory()
+                self.shr_host[i][j].copy_(om, non_blocking=True)
+                om.record_stream(self.stream)                   # the allocator must not recycle it before the copy ran
+                shr[j] = self.shr_host[i][j]
             done = torch.cuda.Event()
             done.record(self.stream)
-        self.work.put((i, done, dict(kwargs)))
+        self.work.put((i, done, dict(kwargs), shr))
 
     def close(self):
         if self.thread is not None:
