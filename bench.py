@@ -13,7 +13,9 @@ A "step" is one isospectral-midpoint time step.
 * ``e2e``    : the same metric through the public Python API with HOST buffers (numpy in pinned memory): every step
                is one ``qf.isomp(W_host, dt, steps=1)`` call = H2D copy of W + one step + D2H copy of W.  On several
                GPUs the host state is row-distributed (``host_rows="own"``): every rank copies its own 1/G of the rows
-               in and out over its own PCIe link and the state is completed over NVLink.
+               in and out over its own PCIe link and the state is completed over NVLink.  ``e2e.copies`` times the
+               two copies alone and reports the iterations per step of the one-step calls (each call starts from
+               dW = 0 like the reference, so it needs about one more iteration than a step inside a long call).
 * ``roofline``: the dominant kernel (k_zgemm3m_ws, FP64 DMMA) — EXECUTED flops per launch / CUDA-event launch time,
                against the FP64 tensor peak MEASURED IN THE SAME RUN (qf_measure_fp64_tensor_peak; MEASURED_PEAKS.json
                has no FP64 entry).  ``roofline_poisson`` reports the HBM-bound Poisson solve against
@@ -391,11 +393,16 @@ def gpu_arm(args):
     # paths: every rank copies the whole state in and out.)
     own_rows = world > 1 and handle.comm_mode() == "tile"
 
+    e2e_its = []
+
     def e2e_step():
         if world == 1:
-            qf.isomp(Wh, kw["dt"], steps=1, maxit=kw["maxit"], minit=kw["minit"])
+            st = {"iterations": 0.0}
+            qf.isomp(Wh, kw["dt"], steps=1, maxit=kw["maxit"], minit=kw["minit"], stats=st)
+            e2e_its.append(st["iterations"])
         else:
-            handle.isomp(Wh, kw["dt"], 1, maxit=kw["maxit"], minit=kw["minit"], host_rows="own" if own_rows else "all")
+            st, _ = handle.isomp(Wh, kw["dt"], 1, maxit=kw["maxit"], minit=kw["minit"], host_rows="own" if own_rows else "all")
+            e2e_its.append(st[0]["total_iterations"])
     for _ in range(min(args.warmup, 2)):
         e2e_step()
     barrier()
@@ -409,6 +416,32 @@ def gpu_arm(args):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = e2e_steps / float(t.item())
+
+    # what bounds e2e: the pinned-memory copies of one call, timed alone with CUDA events (the bytes this rank moves per
+    # step, each direction), next to the device time of the step itself
+    nb_rank = 16 * N * N // (world if own_rows else 1)
+    stage = torch.empty(nb_rank, dtype=torch.uint8, device=dev)
+    pin8 = Wpin.view(torch.uint8).reshape(-1)[:nb_rank]
+    cp = {}
+    for name, (dst, src) in (("h2d", (stage, pin8)), ("d2h", (pin8, stage))):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            dst.copy_(src, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        cp[name] = c0.elapsed_time(c1) / 5.0
+    del stage
+    e2e_copy = {"bytes_per_rank_each_way": nb_rank, "h2d_ms": cp["h2d"], "d2h_ms": cp["d2h"],
+                "h2d_GBps": nb_rank / cp["h2d"] / 1e6, "d2h_GBps": nb_rank / cp["d2h"] / 1e6,
+                "e2e_ms_per_step": 1e3 / e2e_val, "device_ms_per_step": ms / max(args.steps, 1),
+                "e2e_iterations_per_step": float(np.mean(e2e_its[-e2e_steps:])), "device_iterations_per_step": its,
+                "note": "rank 0's pinned-memory copies of one call timed alone (CUDA events, 5 repeats).  e2e_ms_per_step - "
+                        "device_ms_per_step = these two copies + the extra fixed-point iterations of a one-step call (every call "
+                        "starts from dW = 0 like the reference, isospectral.py:430, so it cannot reuse the previous step's "
+                        "increment as its first guess) + per-call set-up (tolerance norm, statistics read-back)"}
 
     ph_sharded = None
     if world > 1:
@@ -520,7 +553,8 @@ def gpu_arm(args):
                 "d2h_bytes_per_step": 16 * N * N * (1 if (world == 1 or own_rows) else world),
                 "note": "one qf.isomp(W_numpy_pinned, dt, steps=1) call per step; on several GPUs the host state is "
                         "row-distributed (every rank copies its own 1/G of the rows in and out, bytes are the sum over ranks) "
-                        "and completed over NVLink; chunked calls reset the warm start like the reference (isospectral.py:430)"},
+                        "and completed over NVLink; chunked calls reset the warm start like the reference (isospectral.py:430)",
+                "copies": e2e_copy},
         "gpu_launches": launches,
         "roofline": roofline,
         "roofline_poisson": roofline_poisson,
